@@ -1,0 +1,429 @@
+"""CPU oracle for the EI-Nexus extraction-and-matching hot path.
+
+TEST INFRASTRUCTURE ONLY.  This module is a numpy restatement of the reference
+algorithm (ZhonghuaYi/EI-Nexus_official); it is the *checker* for the CUDA path,
+never the product.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.  The
+package ``ei-nexus_official_b200`` must never import anything from ``oracle/``.
+
+Parity pinning: every function below is checked in ``tests/test_oracle_golden.py``
+against fixtures under ``tests/golden/`` that were produced by importing the
+reference's own Python functions in the build container
+(``tests/golden/make_golden.py``) and against the two property tests the
+reference carries for this path
+(``core/modules/image_extractors/silk/backbones/superpoint/utils_test.py:17-63``).
+
+Reference citations are relative to the reference repository root.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+F32 = np.float32
+
+
+# --------------------------------------------------------------------------- #
+# a1 / a2  event representation  (datasets/representations.py:8-22, 66-124)
+# --------------------------------------------------------------------------- #
+def time_normalization(t):
+    """t <- (t - t[0]) / (t[-1] - t[0] + 1e-8) in fp64 (representations.py:19-20)."""
+    t = np.asarray(t, dtype=np.float64)
+    t = t - t[0]
+    return t / (t[-1] + 1e-8)
+
+
+def voxel_event_terms(x, y, t, p, bins):
+    """fp32 per-event quantities exactly as representations.py:73-89 builds them.
+
+    Returns (xf, yf, tn, pol): fp32 x, fp32 y, fp32 normalised time in
+    [0, bins-1], polarity with ``p < 1 -> -1``.
+    """
+    t64 = time_normalization(t)
+    xf = np.asarray(x).astype(F32)
+    yf = np.asarray(y).astype(F32)
+    pf = np.asarray(p).astype(F32)
+    tf = t64.astype(F32)
+    # (bins-1) * (t - t0) / (tN - t0), evaluated left to right in fp32 (:80-81)
+    tn = (F32(bins - 1) * (tf - tf[0])) / (tf[-1] - tf[0])
+    pol = np.where(pf < F32(1), F32(-1), pf).astype(F32)  # :88-89
+    return xf, yf, tn.astype(F32), pol
+
+
+def events_to_voxel_grid(x, y, t, p, bins, H, W, normalize=True, return_l1=False):
+    """Trilinear event splat + non-zero mean/std normalisation.
+
+    Follows datasets/representations.py:66-124.  The 8 corner contributions are
+    accumulated in fp64 and rounded once to fp32 (the reference accumulates in
+    fp32 with a thread-dependent order), so this is the
+    order-free value the parity rule ``|d| <= 1e-5 * max(|ref|, sum|w|)`` is
+    stated against.  ``return_l1`` also returns sum|w| per cell.
+    """
+    xf, yf, tn, pol = voxel_event_terms(x, y, t, p, bins)
+    x0 = np.trunc(xf).astype(np.int32)  # .int() truncates toward zero (:83-85)
+    y0 = np.trunc(yf).astype(np.int32)
+    t0 = np.trunc(tn).astype(np.int32)
+    ncell = bins * H * W
+    acc = np.zeros(ncell, dtype=np.float64)
+    l1 = np.zeros(ncell, dtype=np.float64)
+    one = F32(1)
+    for xl in (x0, x0 + 1):  # corner order of :91-93
+        for yl in (y0, y0 + 1):
+            for tl in (t0, t0 + 1):
+                ok = (xl < W) & (xl >= 0) & (yl < H) & (yl >= 0) & (tl >= 0) & (tl < bins)
+                w = pol * (one - np.abs(xl.astype(F32) - xf))
+                w = w * (one - np.abs(yl.astype(F32) - yf))
+                w = (w * (one - np.abs(tl.astype(F32) - tn))).astype(F32)
+                idx = (H * W) * tl.astype(np.int64) + W * yl.astype(np.int64) + xl.astype(np.int64)
+                acc += np.bincount(idx[ok], weights=w[ok].astype(np.float64), minlength=ncell)
+                if return_l1:
+                    l1 += np.bincount(idx[ok], weights=np.abs(w[ok]).astype(np.float64), minlength=ncell)
+    grid = acc.astype(F32).reshape(bins, H, W)
+    if normalize:
+        grid = normalize_nonzero(grid)
+    if return_l1:
+        return grid, l1.astype(F32).reshape(bins, H, W)
+    return grid
+
+
+def normalize_nonzero(grid):
+    """Mean / unbiased std over cells != 0, applied to those cells (:114-122)."""
+    grid = np.array(grid, dtype=F32, copy=True)
+    m = grid != 0
+    n = int(m.sum())
+    if n > 0:
+        vals = grid[m].astype(np.float64)
+        mean = F32(vals.mean())
+        # torch.std is unbiased; one element gives nan, which fails `std > 0`
+        std = F32(vals.std(ddof=1)) if n > 1 else F32(np.nan)
+        if std > 0:
+            grid[m] = (grid[m] - mean) / std
+        else:
+            grid[m] = grid[m] - mean
+    return grid
+
+
+# --------------------------------------------------------------------------- #
+# a3 / a4  border removal + iterative NMS  (detector_util.py:138-164, 243-337)
+# --------------------------------------------------------------------------- #
+def remove_border_points(v, border):
+    """Zero a ``border``-wide frame in place on (..., H, W) (detector_util.py:151-162)."""
+    if border > 0:
+        v[..., :, :border] = 0
+        v[..., :, -border:] = 0
+        v[..., :border, :] = 0
+        v[..., -border:, :] = 0
+    return v
+
+
+def _window_maxes(v, r):
+    """Max over the raster-earlier and raster-later halves of the (2r+1)^2 window.
+
+    v: (B, H, W) fp32, zero padding outside the image (F.unfold padding, :289-295).
+    """
+    B, H, W = v.shape
+    P = np.zeros((B, H + 2 * r, W + 2 * r), dtype=v.dtype)
+    P[:, r:r + H, r:r + W] = v
+    row_full = P[:, :, 0:W].copy()
+    for dx in range(1, 2 * r + 1):
+        np.maximum(row_full, P[:, :, dx:dx + W], out=row_full)
+    earlier = np.zeros_like(v)
+    later = np.zeros_like(v)
+    for dy in range(0, r):  # rows above the centre
+        np.maximum(earlier, row_full[:, dy:dy + H], out=earlier)
+    for dy in range(r + 1, 2 * r + 1):  # rows below
+        np.maximum(later, row_full[:, dy:dy + H], out=later)
+    for dx in range(0, r):  # same row, left
+        np.maximum(earlier, P[:, r:r + H, dx:dx + W], out=earlier)
+    for dx in range(r + 1, 2 * r + 1):  # same row, right
+        np.maximum(later, P[:, r:r + H, dx:dx + W], out=later)
+    return earlier, later
+
+
+def local_maxima(v, r):
+    """Centre == first-occurrence argmax of its zero-padded window (:298-299).
+
+    argmax returns the first maximal slot in window raster order, so the centre
+    wins iff it is strictly greater than every earlier slot and >= every later
+    one; a zero centre never wins (slot 0 of the window ties or beats it).
+    """
+    earlier, later = _window_maxes(v, r)
+    return (v > 0) & (v > earlier) & (v >= later)
+
+
+def _dilate(mask, r):
+    B, H, W = mask.shape
+    P = np.zeros((B, H + 2 * r, W + 2 * r), dtype=bool)
+    P[:, r:r + H, r:r + W] = mask
+    rows = P[:, :, 0:W].copy()
+    for dx in range(1, 2 * r + 1):
+        rows |= P[:, :, dx:dx + W]
+    out = rows[:, 0:H].copy()
+    for dy in range(1, 2 * r + 1):
+        out |= rows[:, dy:dy + H]
+    return out
+
+
+def fast_nms(v, r, return_rounds=False):
+    """Iterative NMS to the fixpoint, with the reference's batch-wide stop rule.
+
+    detector_util.py:286-335: find local maxima, stop when their count over the
+    whole batch is unchanged, otherwise zero every pixel that has a local
+    maximum in its window (the maximum itself excepted).  v: (B, H, W) >= 0.
+    """
+    v = np.array(v, dtype=F32, copy=True)
+    if r == 0:
+        return (v, 0) if return_rounds else v
+    count = None
+    rounds = 0
+    while True:
+        lm = local_maxima(v, r)
+        c = int(lm.sum())
+        if c == count:
+            break
+        count = c
+        v[_dilate(lm, r) & ~lm] = 0
+        rounds += 1
+    return (v, rounds) if return_rounds else v
+
+
+def greedy_nms(v, r):
+    """Greedy NMS in (value desc, raster asc) order; zeros never selected.
+
+    Small-case cross-check only (pure Python loop).  SURVEY.md section 8 a4: the
+    iterative fixpoint equals this ordering of detector_util.py:167-240.
+    """
+    v = np.array(v, dtype=F32, copy=True)
+    H, W = v.shape
+    flat = v.ravel()
+    order = np.lexsort((np.arange(flat.size), -flat.astype(np.float64)))
+    out = np.zeros_like(v)
+    alive = v > 0
+    for idx in order:
+        yy, xx = divmod(int(idx), W)
+        if not alive[yy, xx]:
+            continue
+        out[yy, xx] = v[yy, xx]
+        alive[max(0, yy - r):yy + r + 1, max(0, xx - r):xx + r + 1] = False
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# a5  top-k threshold  (detector_util.py:108-133)
+# --------------------------------------------------------------------------- #
+def topk_ranks(n, k):
+    """fp32 emulation of ``q = (n-k)/n`` and ``rank = q*(n-1)`` (:113-124).
+
+    torch divides an int64 tensor by a Python int in fp32 and ``quantile``
+    multiplies q by (n-1) in the input dtype, so both steps round to fp32.
+    """
+    q = F32(n - k) / F32(n)
+    rank = F32(q * F32(n - 1))
+    return int(np.floor(rank)), int(np.ceil(rank))
+
+
+def topk_threshold(flat, k):
+    """'midpoint' quantile of one image's n values, zeros included (:108-124)."""
+    flat = np.asarray(flat, dtype=F32).ravel()
+    n = flat.size
+    if k >= n:
+        return F32(0)
+    lo, hi = topk_ranks(n, k)
+    s = np.sort(flat)
+    a, b = s[lo], s[hi]
+    # torch.lerp(a, b, 0.5) takes the |w| >= 0.5 branch: b - (b - a) * (1 - w)
+    return F32(b - F32(F32(b - a) * F32(0.5)))
+
+
+def prob_map_to_points_map(prob_map, prob_thresh=0.015, nms_dist=4, border_dist=4, top_k=None):
+    """Border removal -> fast_nms -> top-k / prob threshold (detector_util.py:80-135).
+
+    prob_map: (B, 1, H, W) or (B, H, W) fp32; border zeroing happens IN PLACE on
+    the caller's array, like the reference.  Returns the (B, H, W) nms map.
+    """
+    remove_border_points(prob_map, border_dist)
+    v = prob_map.reshape(prob_map.shape[0], prob_map.shape[-2], prob_map.shape[-1])
+    v = fast_nms(v, nms_dist)
+    B = v.shape[0]
+    thr = np.full((B,), F32(prob_thresh), dtype=F32)
+    if top_k:
+        for i in range(B):
+            thr[i] = min(topk_threshold(v[i], int(top_k)), F32(prob_thresh))
+    return np.where(v > thr[:, None, None], v, F32(0)).astype(F32)
+
+
+# --------------------------------------------------------------------------- #
+# a6  positions  (detector_util.py:451-484)
+# --------------------------------------------------------------------------- #
+def prob_map_to_positions_with_prob(nms, threshold=0.0, ordering="yx"):
+    """Raster-order (y+.5, x+.5, prob) rows per image (:470-484)."""
+    nms = nms.reshape(nms.shape[0], nms.shape[-2], nms.shape[-1])
+    out = []
+    for i in range(nms.shape[0]):
+        yy, xx = np.nonzero(nms[i] > threshold)
+        pos = np.stack([yy, xx], axis=1).astype(F32) + F32(0.5)
+        if ordering == "xy":
+            pos = pos[:, ::-1]
+        out.append(np.concatenate([pos, nms[i][yy, xx][:, None]], axis=1).astype(F32))
+    return tuple(out)
+
+
+def padder_sizes(h, w, p):
+    """(w0, w1, h0, h1) of core/modules/utils/util.py:9-15."""
+    hp = (((h // p) + 1) * p - h) % p
+    wp = (((w // p) + 1) * p - w) % p
+    return (wp // 2, wp - wp // 2, hp // 2, hp - hp // 2)
+
+
+# --------------------------------------------------------------------------- #
+# a7  descriptor sampling  (descriptor_util.py:21-28, 50-128)
+# --------------------------------------------------------------------------- #
+def normalize_descriptors(d, scale=1.0, normalize=True):
+    """scale * d / max(||d||_2, 1e-12) over dim 1 (descriptor_util.py:21-28)."""
+    d = np.asarray(d, dtype=F32)
+    if not normalize:
+        return (F32(scale) * d).astype(F32)
+    nrm = np.sqrt((d.astype(np.float64) ** 2).sum(axis=1, keepdims=True)).astype(F32)
+    return (F32(scale) * (d / np.maximum(nrm, F32(1e-12)))).astype(F32)
+
+
+def sparsify_full_resolution_descriptors(raw, positions, scale=1.0, normalize=True):
+    """Integer gather raw[i, :, floor(y), floor(x)] + L2 (descriptor_util.py:50-71)."""
+    out = []
+    for i, pos in enumerate(positions):
+        yy = np.floor(pos[:, 0]).astype(np.int64)
+        xx = np.floor(pos[:, 1]).astype(np.int64)
+        d = raw[i][:, yy, xx].T
+        out.append(normalize_descriptors(d, scale, normalize))
+    return tuple(out)
+
+
+def sparsify_low_resolution_descriptors(raw, positions, image_size, scale=1.0, normalize=True):
+    """Bilinear sampling of the coarse map + L2 (descriptor_util.py:74-128).
+
+    Restates F.grid_sample(bilinear, zeros padding, align_corners=False) on the
+    grid ``2*((pos-0.5)/(size-1)) - 1``: the un-normalisation is
+    ``((g+1)*size_in - 1)/2``; taps outside the coarse map contribute 0.
+    """
+    Hp, Wp = F32(image_size[0]), F32(image_size[1])
+    out = []
+    for i, pos in enumerate(positions):
+        C, Hc, Wc = raw[i].shape
+        n = pos.shape[0]
+        if n == 0:
+            out.append(np.zeros((0, C), dtype=F32))
+            continue
+        py = pos[:, 0].astype(F32) - F32(0.5)
+        px = pos[:, 1].astype(F32) - F32(0.5)
+        gy = F32(2) * (py / (Hp - F32(1))) - F32(1)
+        gx = F32(2) * (px / (Wp - F32(1))) - F32(1)
+        iy = ((gy + F32(1)) * F32(Hc) - F32(1)) / F32(2)
+        ix = ((gx + F32(1)) * F32(Wc) - F32(1)) / F32(2)
+        y0 = np.floor(iy)
+        x0 = np.floor(ix)
+        wy1 = (iy - y0).astype(F32)
+        wx1 = (ix - x0).astype(F32)
+        wy0 = ((y0 + F32(1)) - iy).astype(F32)
+        wx0 = ((x0 + F32(1)) - ix).astype(F32)
+        y0 = y0.astype(np.int64)
+        x0 = x0.astype(np.int64)
+        d = np.zeros((n, C), dtype=F32)
+        # tap order nw, ne, sw, se as in ATen's grid_sampler_2d
+        for (yy, xx, w) in ((y0, x0, wx0 * wy0), (y0, x0 + 1, wx1 * wy0),
+                            (y0 + 1, x0, wx0 * wy1), (y0 + 1, x0 + 1, wx1 * wy1)):
+            ok = (yy >= 0) & (yy < Hc) & (xx >= 0) & (xx < Wc)
+            yc = np.clip(yy, 0, Hc - 1)
+            xc = np.clip(xx, 0, Wc - 1)
+            tap = raw[i][:, yc, xc].T * w[:, None].astype(F32)
+            d += np.where(ok[:, None], tap, F32(0)).astype(F32)
+        out.append(normalize_descriptors(d, scale, normalize))
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# a8  mutual nearest neighbour matching  (core/modules/matchers/MNN.py:11-140)
+# --------------------------------------------------------------------------- #
+def find_nn(sim, ratio_thresh=None, distance_thresh=None):
+    """First-index argmax per row with optional ratio / distance tests (MNN.py:11-22)."""
+    n, m = sim.shape
+    ind = np.argmax(sim, axis=1).astype(np.int64)  # first occurrence, like topk(1)
+    best = sim[np.arange(n), ind]
+    ok = np.ones(n, dtype=bool)
+    d0 = F32(2) * (F32(1) - best)
+    if ratio_thresh:
+        tmp = sim.copy()
+        tmp[np.arange(n), ind] = -np.inf
+        second = tmp.max(axis=1)
+        d1 = F32(2) * (F32(1) - second)
+        ok &= d0 <= F32(ratio_thresh ** 2) * d1
+    if distance_thresh:
+        ok &= d0 <= F32(distance_thresh ** 2)
+    return np.where(ok, ind, -1).astype(np.int64)
+
+
+def mutual_check(m0, m1):
+    """Keep i<->j only when each is the other's nearest neighbour (MNN.py:25-32)."""
+    i0 = np.arange(m0.size)
+    i1 = np.arange(m1.size)
+    loop0 = m1[np.where(m0 > -1, m0, 0)] if m1.size else np.zeros_like(m0)
+    loop1 = m0[np.where(m1 > -1, m1, 0)] if m0.size else np.zeros_like(m1)
+    m0n = np.where((m0 > -1) & (i0 == loop0), m0, -1)
+    m1n = np.where((m1 > -1) & (i1 == loop1), m1, -1)
+    return m0n.astype(np.int64), m1n.astype(np.int64)
+
+
+def mnn_match(desc0, desc1, kpts0=None, kpts1=None, ratio_thresh=None, distance_thresh=None,
+              mutual=True, return_dense=False, sim_dtype=np.float32):
+    """One pair of NearestNeighborMatcher.forward (MNN.py:88-129).
+
+    desc0 (N, D), desc1 (M, D).  ``sim_dtype=np.float64`` gives the tie-free
+    adjudicator used for near-tie rows (MNN index parity).
+    """
+    d0 = np.asarray(desc0, dtype=sim_dtype)
+    d1 = np.asarray(desc1, dtype=sim_dtype)
+    sim = d0 @ d1.T
+    m0 = find_nn(sim, ratio_thresh, distance_thresh)
+    m1 = find_nn(sim.T, ratio_thresh, distance_thresh)
+    if mutual:
+        m0, m1 = mutual_check(m0, m1)
+    out = {
+        "matches0": m0, "matches1": m1,
+        "matching_scores0": (m0 > -1).astype(F32), "matching_scores1": (m1 > -1).astype(F32),
+    }
+    if kpts0 is not None:
+        keep = m0 > -1
+        out["matched_kpts0"] = np.asarray(kpts0)[keep]
+        out["matched_kpts1"] = np.asarray(kpts1)[m0[keep]]
+    if return_dense:
+        out["similarity"] = sim
+        n, m = sim.shape
+        la = np.zeros((n + 1, m + 1), dtype=sim.dtype)
+        s64 = sim.astype(np.float64)
+        lr = s64.max(1, keepdims=True) + np.log(np.exp(s64 - s64.max(1, keepdims=True)).sum(1, keepdims=True))
+        lc = s64.max(0, keepdims=True) + np.log(np.exp(s64 - s64.max(0, keepdims=True)).sum(0, keepdims=True))
+        la[:n, :m] = (2 * s64 - lr - lc).astype(sim.dtype)
+        out["log_assignment"] = la
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# whole path for one event-image pair (the unit bench.py counts)
+# --------------------------------------------------------------------------- #
+def extract_side(score, raw, kind, nms_dist, border, top_k, prob_thresh, scale):
+    """detect -> positions -> sample for one side; score (1,H,W) is border-zeroed in place."""
+    nms = prob_map_to_points_map(score, prob_thresh, nms_dist, border, top_k)
+    pos = prob_map_to_positions_with_prob(nms)
+    if kind == "full":
+        desc = sparsify_full_resolution_descriptors(raw, pos, scale, True)
+    else:
+        desc = sparsify_low_resolution_descriptors(raw, pos, score.shape[-2:], scale, True)
+    return pos, desc
+
+
+def pair_pipeline(ev, bins, H, W, score0, raw0, score1, raw1, kind, top_k, scale,
+                  nms_dist=4, border=4, prob_thresh=1.0):
+    """voxelise -> [detect -> sample] x2 -> MNN for ONE pair (SURVEY.md section 8 d)."""
+    grid = events_to_voxel_grid(ev["x"], ev["y"], ev["t"], ev["p"], bins, H, W, True)
+    p0, d0 = extract_side(score0, raw0, kind, nms_dist, border, top_k, prob_thresh, scale)
+    p1, d1 = extract_side(score1, raw1, kind, nms_dist, border, top_k, prob_thresh, scale)
+    m = mnn_match(d0[0], d1[0], p0[0], p1[0])
+    return grid, p0[0], p1[0], m
