@@ -1,0 +1,442 @@
+#!/usr/bin/env python
+"""Headline benchmark: pairs/sec of voxelise -> [detect -> sample] x2 -> MNN on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl einx|reference] [--config c2_ec_superpoint]
+
+One "step" is one pass of the hot path over one batch of synthetic event-image pairs per GPU
+(default: BASELINE.json configs[1] -- EC 240x180, SuperPoint-MNN, 1024 keypoints, 256-d, batch 64).
+Prints ONE JSON line on stdout (rank 0); everything else goes to stderr.
+
+  value        pairs/s, all N GPUs, inputs resident in HBM, K steps timed with CUDA events
+  e2e          same metric through the public Python API with pinned HOST buffers: every step copies
+               its events and maps host->device and reads the matches back device->host
+  roofline     dominant kernel of the step: algorithmic bytes (or flops) / its CUDA-event time,
+               against MEASURED_PEAKS.json
+  cpu_baseline the oracle port of the reference algorithm on this box's host cores (bounded sample)
+  --impl reference   times only that CPU port (the reference is Python and cannot travel to the
+               GPU box; oracle/einx_oracle.py restates it and is pinned to reference-made goldens)
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+DEFAULT_BATCH = {"c1_mvsec_silk": 1, "c2_ec_superpoint": 64, "c3_mvsec_silk_b256": 32, "c4_hires": 1}
+NUM_INPUT_SETS = 3  # distinct resident batches rotated between steps (together larger than L2)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return dict(FALLBACK_PEAKS), "fallback"
+
+
+# --------------------------------------------------------------------------------------------- #
+# synthetic batches
+# --------------------------------------------------------------------------------------------- #
+def make_batch(synth, cfg_name, batch, first_sample, n_events=None):
+    """numpy inputs of `batch` pairs: list of event dicts + stacked score / raw maps for both sides."""
+    evs, s0, r0, s1, r1 = [], [], [], [], []
+    for i in range(batch):
+        ev, sides = synth.pair_inputs(cfg_name, first_sample + i, n_events)
+        evs.append(ev)
+        s0.append(sides[0][0]); r0.append(sides[0][1]); s1.append(sides[1][0]); r1.append(sides[1][1])
+    return evs, np.concatenate(s0), np.concatenate(r0), np.concatenate(s1), np.concatenate(r1)
+
+
+# --------------------------------------------------------------------------------------------- #
+# CPU arm: the oracle port over all host cores
+# --------------------------------------------------------------------------------------------- #
+def _cpu_pair(args):
+    from oracle import einx_oracle as O
+
+    cfg, ev, s0, r0, s1, r1 = args
+    try:
+        from threadpoolctl import threadpool_limits
+        ctxm = threadpool_limits(limits=1)
+    except Exception:  # pragma: no cover
+        import contextlib
+        ctxm = contextlib.nullcontext()
+    with ctxm:
+        _, p0, p1, m = O.pair_pipeline(ev, cfg["bins"], cfg["H"], cfg["W"], s0.copy(), r0, s1.copy(), r1,
+                                       "full" if cfg["kind"] == "gather" else "low", cfg["top_k"], cfg["scale"])
+    return int((m["matches0"] > -1).sum())
+
+
+def cpu_pairs_per_sec(synth, cfg_name, pairs, repeats=1, workers=None):
+    """Run the oracle pipeline on `pairs` pairs spread over all host cores; returns (pairs/s, cores, secs)."""
+    import multiprocessing as mp
+
+    cfg = synth.CONFIGS[cfg_name]
+    cores = workers or os.cpu_count() or 1
+    cores = max(1, min(cores, pairs))
+    evs, s0, r0, s1, r1 = make_batch(synth, cfg_name, pairs, 0)
+    jobs = [(cfg, evs[i], s0[i:i + 1], r0[i:i + 1], s1[i:i + 1], r1[i:i + 1]) for i in range(pairs)]
+    ctx = mp.get_context("fork")
+    best = None
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_pair, jobs[:cores])  # warm the workers (imports, page faults)
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            pool.map(_cpu_pair, jobs, chunksize=1)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return pairs / best, cores, best
+
+
+def run_reference(args, synth):
+    """--impl reference: the CPU port of the reference path, all host cores, same metric / config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg_name = args.config
+    cores = os.cpu_count() or 1
+    pairs = max(cores, min(args.batch, 2 * cores))  # a bounded sample of the batch per step
+    cfg = synth.CONFIGS[cfg_name]
+    import multiprocessing as mp
+
+    evs, s0, r0, s1, r1 = make_batch(synth, cfg_name, pairs, 0)
+    jobs = [(cfg, evs[i], s0[i:i + 1], r0[i:i + 1], s1[i:i + 1], r1[i:i + 1]) for i in range(pairs)]
+    times = []
+    with mp.get_context("fork").Pool(min(cores, pairs)) as pool:
+        for step in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            pool.map(_cpu_pair, jobs, chunksize=1)
+            dt = time.perf_counter() - t0
+            if step >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    value = pairs * len(times) / total
+    line = {
+        "impl": "reference", "metric": "pairs/sec (voxel+detect+MNN)", "value": value, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, synth),
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": min(cores, pairs), "kind": "port",
+                         "sample": f"{pairs} pairs of the workload per step, one oracle process per core"},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, synth):
+    c = synth.CONFIGS[args.config]
+    Hp, Wp, _ = synth.padded_size(c["H"], c["W"], c["cell"])
+    return {
+        "workload": f"{args.config}: {c['W']}x{c['H']} sensor, {c['events']} events/window ({c['style']} style), "
+                    f"{c['bins']}-bin voxel grid, {'SuperPoint' if c['kind'] == 'bilinear' else 'SiLK'}-type maps "
+                    f"{Wp}x{Hp}, top-{c['top_k']} keypoints, {c['D']}-d descriptors, MNN",
+        "batch_per_gpu": args.batch, "global_batch": args.batch * args.gpus, "parallelism": f"dp{args.gpus}",
+        "mnn_precision": args.precision,
+        "l2_policy": f"{NUM_INPUT_SETS} distinct resident input batches rotated between steps (inputs larger than L2)",
+    }
+
+
+# --------------------------------------------------------------------------------------------- #
+# clocks
+# --------------------------------------------------------------------------------------------- #
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+        self.window = [None, None]
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception as e:  # pragma: no cover
+            log("clock sampler unavailable:", e)
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), sm, reasons))
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self):
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        nv = self.nv
+        t0, t1 = self.window
+        inside = [s for s in self.samples if t0 is not None and t0 <= s[0] <= t1] or self.samples
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        seen = set()
+        for _, _, r in inside:
+            for bit, name in names.items():
+                if r & bit:
+                    seen.add(name)
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
+        return {"sm_mhz": statistics.median(s[1] for s in inside), "sm_max_mhz": mx, "reasons": sorted(seen),
+                "samples": len(inside)}
+
+
+# --------------------------------------------------------------------------------------------- #
+# GPU arm
+# --------------------------------------------------------------------------------------------- #
+def stage_bytes(c, synth, batch):
+    """Algorithmic bytes / flops per STEP for each stage (SURVEY.md section 8 d)."""
+    Hp, Wp, _ = synth.padded_size(c["H"], c["W"], c["cell"])
+    K, D = c["top_k"], c["D"]
+    Hd, Wd = Hp // c["cell"], Wp // c["cell"]
+    vox = 20 * c["events"] + 4 * c["bins"] * c["H"] * c["W"]            # x,y,p fp32 + t fp64 in, grid out
+    det = 2 * (4 * Hp * Wp + 12 * K)                                    # two sides: map in, keypoints out
+    if c["kind"] == "gather":
+        smp = 2 * (4 * K * D + 4 * K * D)
+    else:
+        smp = 2 * (min(4 * D * Hd * Wd, 16 * K * D) + 4 * K * D)
+    mnn_bytes = 4 * D * 2 * K + 12 * 2 * K
+    mnn_flops = 2.0 * K * K * D
+    return {"voxel": vox * batch, "detect": det * batch, "sample": smp * batch, "mnn": mnn_bytes * batch,
+            "mnn_flops": mnn_flops * batch}
+
+
+def run_einx(args, synth):
+    import torch
+    import torch.distributed as dist
+
+    import einx
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        log(f"WORLD_SIZE={world} but --gpus {args.gpus}: using WORLD_SIZE")
+        args.gpus = world
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = einx.context_for(dev)  # raises without libeinx.so / sm_100a: no fallback
+
+    c = synth.CONFIGS[args.config]
+    B = args.batch
+    Hp, Wp, _ = synth.padded_size(c["H"], c["W"], c["cell"])
+    cfg = einx.PathConfig(bins=c["bins"], height=c["H"], width=c["W"], top_k=c["top_k"], descriptor_mode=c["kind"],
+                          descriptor_scale=c["scale"], precision=args.precision)
+    pipe = einx.ExtractMatchPipeline(cfg)
+
+    # ---- inputs: pinned host copies (e2e arm) and NUM_INPUT_SETS resident copies (device arm) ----
+    t_gen = time.time()
+    host_sets, dev_sets = [], []
+    for s in range(NUM_INPUT_SETS):
+        first = (rank * NUM_INPUT_SETS + s) * B
+        evs, s0, r0, s1, r1 = make_batch(synth, args.config, B, first)
+        ev = einx.pack_events(evs, pin=True)
+        maps = [torch.from_numpy(a).pin_memory() for a in (s0, r0, s1, r1)]
+        host_sets.append((ev, maps))
+        dev_sets.append((tuple(t.to(dev) for t in ev), [m.to(dev) for m in maps]))
+    log(f"[rank {rank}] generated {NUM_INPUT_SETS} x {B} pairs in {time.time() - t_gen:.1f}s")
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host_sets[0][0]) + \
+        sum(m.numel() * m.element_size() for m in host_sets[0][1])
+
+    def step_device(i):
+        ev, (s0, r0, s1, r1) = dev_sets[i % NUM_INPUT_SETS]
+        return pipe(ev, s0, r0, s1, r1)
+
+    # staging buffers of the e2e arm
+    stage_ev = tuple(torch.empty_like(t, device=dev) for t in host_sets[0][0])
+    stage_maps = [torch.empty_like(m, device=dev) for m in host_sets[0][1]]
+    K = c["top_k"]
+    out_host = {"matches0": torch.empty((B, K), dtype=torch.int64).pin_memory(),
+                "matching_scores0": torch.empty((B, K), dtype=torch.float32).pin_memory(),
+                "num_matches": torch.empty((B,), dtype=torch.int32).pin_memory(),
+                "matched_kpts0": torch.empty((B, K, 3), dtype=torch.float32).pin_memory(),
+                "matched_kpts1": torch.empty((B, K, 3), dtype=torch.float32).pin_memory()}
+    d2h_bytes = sum(t.numel() * t.element_size() for t in out_host.values())
+
+    def step_e2e(i):
+        ev, maps = host_sets[i % NUM_INPUT_SETS]
+        for d, h in zip(stage_ev, ev):
+            d.copy_(h, non_blocking=True)
+        for d, h in zip(stage_maps, maps):
+            d.copy_(h, non_blocking=True)
+        out = pipe(stage_ev, stage_maps[0], stage_maps[1], stage_maps[2], stage_maps[3])
+        for k, h in out_host.items():
+            h.copy_(out[k], non_blocking=True)
+        return out
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warmup, stage_times=None):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_start = time.perf_counter()
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        t_end = time.perf_counter()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, (t_start, t_end)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.launches
+    ms, window = timed(step_device, args.steps, args.warmup)
+    launches = (ctx.launches - launches0) * args.steps // (args.steps + args.warmup)
+    sampler.window = list(window)
+    ms_e2e, _ = timed(step_e2e, args.steps, max(3, args.warmup))
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- per-stage CUDA-event timing (same resident inputs, same rotation) for the roofline ----
+    stage_ms = {"voxel": 0.0, "detect": 0.0, "sample": 0.0, "mnn": 0.0}
+    det, desc, mt = (importlib.import_module(f"ei-nexus_official_b200.{m}") for m in ("detection", "describe", "match"))
+    nprof = max(3, min(args.steps, 20))
+    for i in range(3 + nprof):
+        ev, (s0, r0, s1, r1) = dev_sets[i % NUM_INPUT_SETS]
+        evts = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        mode = desc.BILINEAR if cfg.descriptor_mode == "bilinear" else desc.GATHER
+        torch.cuda.synchronize(dev)
+        evts[0].record()
+        pipe.voxelize(*ev)
+        evts[1].record()
+        _, kp0, cn0 = det.detect(s0, cfg.detection_threshold, cfg.nms_radius, cfg.remove_borders, cfg.top_k)
+        _, kp1, cn1 = det.detect(s1, cfg.detection_threshold, cfg.nms_radius, cfg.remove_borders, cfg.top_k)
+        evts[2].record()
+        d0 = desc.sample(r0, kp0, cn0, mode, (Hp, Wp), cfg.descriptor_scale, True)
+        d1 = desc.sample(r1, kp1, cn1, mode, (Hp, Wp), cfg.descriptor_scale, True)
+        evts[3].record()
+        mt.mnn(d0, d1, cn0, cn1, kp0, kp1, None, None, True, cfg.precision)
+        evts[4].record()
+        torch.cuda.synchronize(dev)
+        if i >= 3:
+            for j, k in enumerate(stage_ms):
+                stage_ms[k] += evts[j].elapsed_time(evts[j + 1]) / nprof
+
+    # one NCCL gather of the packed matches, outside the hot path (SURVEY.md section 8 e)
+    gather_ms = None
+    if world > 1:
+        out = step_device(0)
+        packed = einx.pack_matches(out["matches0"], out["num_matches"])
+        torch.cuda.synchronize(dev)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        full = einx.gather_matches(packed, B)
+        g1.record()
+        torch.cuda.synchronize(dev)
+        gather_ms = g0.elapsed_time(g1)
+        assert full.shape[0] == B * world
+
+    if rank == 0:
+        peaks, peak_kind = load_peaks()
+        pairs = B * world * args.steps
+        value = pairs / (ms * 1e-3)
+        e2e_value = pairs / (ms_e2e * 1e-3)
+        sb = stage_bytes(c, synth, B)
+        stages = {}
+        for k, t in stage_ms.items():
+            gbs = sb[k] / (t * 1e-3) / 1e9 if t > 0 else 0.0
+            stages[k] = {"ms": round(t, 4), "algorithmic_GBps": round(gbs, 1), "frac_hbm": round(gbs / peaks["hbm_gbs"], 4)}
+        tfs = sb["mnn_flops"] / (stage_ms["mnn"] * 1e-3) / 1e12 if stage_ms["mnn"] > 0 else 0.0
+        tensor_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        stages["mnn"].update({"TFLOPs": round(tfs, 2), "frac_tensor": round(tfs / tensor_peak, 4)})
+        dominant = max(stage_ms, key=stage_ms.get)
+        if dominant == "mnn":
+            roof = {"kernel": "mnn similarity tiles + fused argmax", "bound": "tensor", "achieved": tfs,
+                    "peak": tensor_peak, "unit": "TFLOP/s", "frac": tfs / tensor_peak, "traffic": None}
+        else:
+            gbs = stages[dominant]["algorithmic_GBps"]
+            roof = {"kernel": dominant, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": gbs / peaks["hbm_gbs"], "traffic": None}
+        roof["peak_source"] = f"MEASURED_PEAKS.json ({peak_kind})"
+        log("timing the CPU baseline (oracle port) ...")
+        cores = os.cpu_count() or 1
+        cpu_pairs = max(cores, min(2 * cores, 64))
+        cpu_val, cpu_cores, cpu_secs = cpu_pairs_per_sec(synth, args.config, cpu_pairs) if world == 1 else (None, None, None)
+        line = {
+            "metric": "pairs/sec (voxel+detect+MNN)", "value": value, "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "tf32x3", "bf16": "bf16"}[args.precision],
+            "data": "synthetic", "config": workload_config(args, synth),
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "stages": stages,
+            "cpu_baseline": ({"value": cpu_val, "unit": "pairs/s", "cores": cpu_cores, "kind": "port",
+                              "sample": f"{cpu_pairs} pairs of the workload in {cpu_secs:.1f}s, one oracle process per core"}
+                             if cpu_val is not None else None),
+            "gather_ms": gather_ms,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="einx", choices=["einx", "reference"])
+    ap.add_argument("--config", default="c2_ec_superpoint")
+    ap.add_argument("--batch", type=int, default=None, help="pairs per GPU per step")
+    ap.add_argument("--precision", default=os.environ.get("EINX_MNN_PRECISION", "fp32"), choices=["fp32", "tf32x3", "bf16"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "einx" else args.warmup
+    synth = importlib.import_module("ei-nexus_official_b200.synth")
+    if args.batch is None:
+        args.batch = DEFAULT_BATCH[args.config]
+    if args.impl == "reference":
+        run_reference(args, synth)
+    else:
+        run_einx(args, synth)
+
+
+if __name__ == "__main__":
+    main()

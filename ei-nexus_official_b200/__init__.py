@@ -1,0 +1,24 @@
+"""einx -- B200-native (sm_100a) extraction-and-matching hot path of EI-Nexus.
+
+Event voxelisation, detection post-processing (NMS + top-k), descriptor sampling and MNN matching as
+hand-written CUDA behind the C ABI of ``include/einx.h``; this package is the thin host layer that
+keeps the reference's Python call surface.  No CPU fallback: everything raises without libeinx.so or
+without an sm_100a device.
+"""
+from . import _lib
+from ._lib import EinxError, context_for
+from .describe import sample, sparsify_full_resolution_descriptors, sparsify_low_resolution_descriptors
+from .detection import detect, prob_map_to_points_map, prob_map_to_positions_with_prob
+from .dist import gather_matches, pack_matches, shard_range
+from .match import NearestNeighborMatcher, mnn, mnn_dense
+from .patch import patch_reference
+from .pipeline import ExtractMatchPipeline, PathConfig
+from .voxel import events_to_voxel_grid, pack_events, time_normalization, voxelize_batch, voxelize_device
+
+__all__ = [
+    "EinxError", "context_for", "events_to_voxel_grid", "time_normalization", "pack_events", "voxelize_batch",
+    "voxelize_device", "detect", "prob_map_to_points_map", "prob_map_to_positions_with_prob", "sample",
+    "sparsify_full_resolution_descriptors", "sparsify_low_resolution_descriptors", "NearestNeighborMatcher",
+    "mnn", "mnn_dense", "ExtractMatchPipeline", "PathConfig", "patch_reference", "shard_range", "pack_matches",
+    "gather_matches",
+]

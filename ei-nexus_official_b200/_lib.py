@@ -1,0 +1,115 @@
+"""ctypes binding of the C ABI in include/einx.h.  There is no fallback: a missing library or a
+missing sm_100a device raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libeinx.so")
+
+c_ctx = C.c_void_p
+_P = C.c_void_p
+
+# name -> (restype, argtypes); mirrors include/einx.h one to one
+SIGNATURES = {
+    "einx_version": (C.c_int, []),
+    "einx_create": (C.c_int, [C.c_int, C.POINTER(c_ctx)]),
+    "einx_destroy": (None, [c_ctx]),
+    "einx_last_error": (C.c_char_p, [c_ctx]),
+    "einx_launch_count": (C.c_int64, [c_ctx]),
+    "einx_voxelize": (C.c_int, [c_ctx, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "einx_detect": (C.c_int, [c_ctx, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                              _P, _P, C.c_int, _P, _P]),
+    "einx_sample": (C.c_int, [c_ctx, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P,
+                              C.c_int, C.c_float, C.c_int, _P, _P]),
+    "einx_mnn": (C.c_int, [c_ctx, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                           C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "einx_mnn_dense": (C.c_int, [c_ctx, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class EinxError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen libeinx.so and declare every prototype of include/einx.h."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise EinxError(
+                f"{LIB_PATH} is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(needs nvcc 12.9). There is no CPU or PyTorch fallback for this path.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError here = header / library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+class Context:
+    """One einx_ctx per CUDA device (workspace owner).  Not thread-safe, like the C object."""
+
+    def __init__(self, device: int):
+        self.lib = load()
+        self.device = int(device)
+        h = c_ctx()
+        rc = self.lib.einx_create(self.device, C.byref(h))
+        if rc != 0:
+            msg = self.lib.einx_last_error(None)
+            raise EinxError(f"einx_create({device}) failed ({rc}): {msg.decode() if msg else ''}")
+        self.handle = h
+
+    def check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self.lib.einx_last_error(self.handle)
+            raise EinxError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.einx_launch_count(self.handle))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.einx_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+_contexts = {}
+
+
+def context_for(device) -> Context:
+    """Context of a torch device / ordinal (created on first use)."""
+    import torch
+
+    dev = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
+    if dev.type != "cuda":
+        raise EinxError(f"einx kernels run on CUDA sm_100a only; got device '{dev}'. There is no CPU fallback.")
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    ctx = _contexts.get(idx)
+    if ctx is None:
+        ctx = _contexts[idx] = Context(idx)
+    return ctx
+
+
+def ptr(t):
+    """Device pointer of a tensor (or NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_of(device):
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

@@ -1,0 +1,66 @@
+// Shared declarations of libeinx (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "einx.h"
+
+struct einx_ctx {
+    int device;
+    int num_sms;
+    int max_smem_optin;   // bytes of dynamic shared memory a CTA may opt in to
+    void* ws;             // grow-only device workspace
+    size_t ws_bytes;
+    int64_t launches;
+    char err[512];
+};
+
+// Grow the workspace to at least `bytes` (synchronising cudaFree/cudaMalloc only on growth).
+int einx_ws_reserve(einx_ctx* ctx, size_t bytes);
+int einx_fail(einx_ctx* ctx, int code, const char* fmt, ...);
+
+#define EINX_CUDA(ctx, call)                                                                   \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return einx_fail((ctx), EINX_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, \
+                             cudaGetErrorString(e_));                                          \
+    } while (0)
+
+#define EINX_CHECK_LAUNCH(ctx)                                                                   \
+    do {                                                                                         \
+        (ctx)->launches++;                                                                       \
+        cudaError_t e_ = cudaGetLastError();                                                     \
+        if (e_ != cudaSuccess)                                                                   \
+            return einx_fail((ctx), EINX_ERR_CUDA, "%s:%d kernel launch -> %s", __FILE__, __LINE__, \
+                             cudaGetErrorString(e_));                                            \
+    } while (0)
+
+struct DeviceGuard {
+    int prev;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+__host__ __device__ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// fp32 -> monotone uint32 (larger float <=> larger unsigned); -0 must be canonicalised first.
+__device__ __forceinline__ uint32_t f32_orderable(float f) {
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float f32_from_orderable(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+// (value, lowest index wins) packed so that one unsigned 64-bit max does an argmax
+__device__ __forceinline__ unsigned long long pack_best(float v, uint32_t idx) {
+    return ((unsigned long long)f32_orderable(v + 0.0f) << 32) | (unsigned long long)(0xffffffffu - idx);
+}

@@ -1,0 +1,81 @@
+// Context lifetime, workspace and error plumbing of libeinx.
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+static char g_create_err[512] = "";
+
+int einx_fail(einx_ctx* ctx, int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx ? ctx->err : g_create_err, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int einx_ws_reserve(einx_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->ws_bytes) return EINX_OK;
+    // Growth only: earlier work queued on any stream may still use the old block.
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return einx_fail(ctx, EINX_ERR_CUDA, "workspace sync: %s", cudaGetErrorString(e));
+    if (ctx->ws) cudaFree(ctx->ws);
+    ctx->ws = nullptr;
+    ctx->ws_bytes = 0;
+    size_t want = align_up(bytes + bytes / 4, 1 << 20);
+    e = cudaMalloc(&ctx->ws, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return einx_fail(ctx, EINX_ERR_NOMEM, "workspace of %zu bytes: %s", want, cudaGetErrorString(e));
+    }
+    ctx->ws_bytes = want;
+    return EINX_OK;
+}
+
+extern "C" {
+
+int einx_version(void) { return 100; }
+
+int einx_create(int device, einx_ctx** out) {
+    if (!out) return einx_fail(nullptr, EINX_ERR_INVALID, "einx_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return einx_fail(nullptr, EINX_ERR_CUDA, "einx_create: no CUDA device (%s); this library has no CPU fallback",
+                         cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= ndev)
+        return einx_fail(nullptr, EINX_ERR_INVALID, "einx_create: device %d out of range [0,%d)", device, ndev);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return einx_fail(nullptr, EINX_ERR_CUDA, "einx_create: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return einx_fail(nullptr, EINX_ERR_ARCH,
+                         "einx_create: device %d is sm_%d%d; libeinx is built for sm_100a (B200) only", device,
+                         prop.major, prop.minor);
+    einx_ctx* ctx = (einx_ctx*)calloc(1, sizeof(einx_ctx));
+    if (!ctx) return einx_fail(nullptr, EINX_ERR_NOMEM, "einx_create: out of host memory");
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    *out = ctx;
+    return EINX_OK;
+}
+
+void einx_destroy(einx_ctx* ctx) {
+    if (!ctx) return;
+    DeviceGuard g(ctx->device);
+    if (ctx->ws) {
+        cudaDeviceSynchronize();
+        cudaFree(ctx->ws);
+    }
+    free(ctx);
+}
+
+const char* einx_last_error(const einx_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
+
+int64_t einx_launch_count(const einx_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,614 @@
+// Detection post-processing: border removal -> iterative NMS fixpoint -> top-k threshold ->
+// raster-ordered keypoint rows.  Semantics: reference core/modules/utils/detector_util.py:80-135,
+// :138-164, :243-337, :451-484 (see include/einx.h); bit-exact for non-negative maps.
+//
+// One thread-block CLUSTER per image.  Each CTA owns a band of rows of the score map in shared
+// memory (with an R-row halo refreshed from the neighbouring CTAs' shared memory over DSMEM every
+// round), so an NMS round never touches HBM: the map is read once and the keypoints written once.
+//
+// A round (detector_util.py:286-335 restated):
+//   lm(p)  = v(p) > 0  and  v(p) >= every window value  and  no equal value earlier in raster order
+//   v(p)   = 0 for every p that has a local maximum in its window and is not one itself
+// Local maxima are monotone (values only decrease), so segments with no undecided pixel are
+// skipped in later rounds, and the loop ends when no pixel is undecided -- the same fixpoint the
+// reference reaches when its batch-wide count of maxima stops changing.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int kThreads = 1024;
+constexpr int kWarps = kThreads / 32;
+constexpr int kSegRows = 24;  // rows per (strip, segment) work item of the fused row/column pass
+constexpr int kMaxCluster = 8;
+
+struct DetectParams {
+    float* score;
+    const uint8_t* mask;
+    float* nms_map;
+    float* kpts;
+    int32_t* counts;
+    int B, Hp, Wp, border, kcap;
+    int CS;      // CTAs per image (cluster size)
+    int S;       // 32-column strips per row
+    int WS;      // padded row stride of V in floats: 32*S + 2R
+    int RBmax;   // max own rows of a band
+    float prob_thresh;
+    int use_topk;  // 1: threshold from order statistics rank_lo / rank_hi; 2: top_k >= n (thr_k = 0)
+    int rank_lo, rank_hi;
+    int scap;  // survivor list capacity per image
+    float* surv_val;
+    int32_t* surv_idx;
+    // global-memory variant (maps too large for a cluster's shared memory)
+    float* gV;
+    uint32_t* gLM;
+    uint32_t* gRD;
+};
+
+struct Shared {
+    int flags[2];
+    int xcnt[2];
+    int warp_scan[kWarps + 1];
+    unsigned int hist[256];
+    unsigned int sel_prefix, sel_rank, sel_min, sel_cnt;
+    float thr;
+};
+
+__device__ __forceinline__ int block_excl_scan(int v, int* scratch, int& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    __syncthreads();  // protect scratch from the previous call
+    if (lane == 31) scratch[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = scratch[lane];
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int n = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += n;
+        }
+        scratch[lane] = winc - w;
+        if (lane == 31) scratch[kWarps] = winc;
+    }
+    __syncthreads();
+    total = scratch[kWarps];
+    return inc - v + scratch[warp];
+}
+
+// j-th smallest (0-based) of the positive floats in list[0..n) via 4 radix passes on their bit
+// patterns, then the next order statistic; every thread returns the same (a, b).
+__device__ void select_two(const float* __restrict__ list, int n, int j, bool need_next, Shared& sh, float& a_out,
+                           float& b_out) {
+    if (threadIdx.x == 0) { sh.sel_prefix = 0; sh.sel_rank = (unsigned)j; }
+    unsigned mask = 0;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int i = threadIdx.x; i < 256; i += kThreads) sh.hist[i] = 0;
+        __syncthreads();
+        const unsigned prefix = sh.sel_prefix;
+        for (int i = threadIdx.x; i < n; i += kThreads) {
+            const unsigned e = __float_as_uint(__ldcg(list + i));
+            if ((e & mask) == prefix) atomicAdd(&sh.hist[(e >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned r = sh.sel_rank, cum = 0;
+            int bin = 0;
+            for (; bin < 256; ++bin) {
+                const unsigned c = sh.hist[bin];
+                if (cum + c > r) break;
+                cum += c;
+            }
+            sh.sel_rank = r - cum;
+            sh.sel_prefix = prefix | ((unsigned)bin << shift);
+        }
+        mask |= 255u << shift;
+        __syncthreads();
+    }
+    const unsigned abits = sh.sel_prefix;
+    float a = __uint_as_float(abits), b = a;
+    if (need_next) {
+        if (threadIdx.x == 0) { sh.sel_min = 0xffffffffu; sh.sel_cnt = 0; }
+        __syncthreads();
+        unsigned cnt = 0, mn = 0xffffffffu;
+        for (int i = threadIdx.x; i < n; i += kThreads) {
+            const unsigned e = __float_as_uint(__ldcg(list + i));
+            if (e <= abits) cnt++;
+            else mn = min(mn, e);
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        mn = __reduce_min_sync(0xffffffffu, mn);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&sh.sel_cnt, cnt);
+            atomicMin(&sh.sel_min, mn);
+        }
+        __syncthreads();
+        // the (j+1)-th smallest equals a when a is duplicated past position j
+        b = (sh.sel_cnt > (unsigned)j + 1u) ? a : __uint_as_float(sh.sel_min);
+    }
+    __syncthreads();
+    a_out = a;
+    b_out = b;
+}
+
+template <int R, bool SMEM>
+__global__ void __launch_bounds__(kThreads, 1) detect_kernel(const DetectParams P) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int CS = P.CS;
+    const int b = blockIdx.x / CS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int S = P.S, WS = P.WS, Hp = P.Hp, Wp = P.Wp;
+
+    // balanced row bands
+    const int base_rows = Hp / CS, rem = Hp % CS;
+    const int nrows = base_rows + (rank < rem ? 1 : 0);
+    const int ys = rank * base_rows + min(rank, rem);
+    const int nprev = base_rows + ((rank - 1) < rem ? 1 : 0);  // rows of the band above
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
+    float* V;
+    uint32_t *LM, *RD;
+    unsigned char* item_active;
+    const int lrows = P.RBmax + 2 * R;  // local rows incl. halo
+    const int nseg = (P.RBmax + kSegRows - 1) / kSegRows;
+    if (SMEM) {
+        size_t o = align_up(sizeof(Shared), 16);
+        V = reinterpret_cast<float*>(smem_raw + o);
+        o += sizeof(float) * (size_t)lrows * WS;
+        LM = reinterpret_cast<uint32_t*>(smem_raw + o);
+        o += sizeof(uint32_t) * (size_t)lrows * S;
+        RD = reinterpret_cast<uint32_t*>(smem_raw + o);
+        o += sizeof(uint32_t) * (size_t)lrows * S;
+        item_active = smem_raw + o;
+    } else {
+        // global variant: one padded image per batch entry; a CTA indexes its band so that local row
+        // lr maps to padded row ys + lr, neighbours' rows are simply adjacent (no halo copies)
+        const size_t img_rows = (size_t)Hp + 2 * R;
+        V = P.gV + ((size_t)b * img_rows + ys) * WS;
+        LM = P.gLM + ((size_t)b * img_rows + ys) * S;
+        RD = P.gRD + ((size_t)b * img_rows + ys) * S;
+        item_active = smem_raw + align_up(sizeof(Shared), 16);
+    }
+    const int nitems = S * nseg;
+
+    // ---- load the band: border + mask zeroing (in place on `score`), zero padding ---------- //
+    if (SMEM) {
+        for (int i = tid; i < lrows * WS; i += kThreads) V[i] = 0.0f;
+        for (int i = tid; i < lrows * S; i += kThreads) { LM[i] = 0u; RD[i] = 0u; }
+    }
+    for (int i = tid; i < nitems; i += kThreads) item_active[i] = 1;
+    if (tid == 0) { sh.flags[0] = sh.flags[1] = 0; sh.xcnt[0] = sh.xcnt[1] = 0; }
+    __syncthreads();
+    {
+        float* simg = P.score + (size_t)b * Hp * Wp;
+        const uint8_t* mimg = P.mask ? P.mask + (size_t)b * Hp * Wp : nullptr;
+        const int bd = P.border;
+        for (int e = tid; e < nrows * Wp; e += kThreads) {
+            const int lr = e / Wp, x = e - lr * Wp, y = ys + lr;
+            const size_t gi = (size_t)y * Wp + x;
+            float v = simg[gi];
+            bool kill = (y < bd) | (y >= Hp - bd) | (x < bd) | (x >= Wp - bd);
+            if (mimg) kill |= (mimg[gi] == 0);
+            if (kill) {
+                if (v != 0.0f) simg[gi] = 0.0f;
+                v = 0.0f;
+            }
+            V[(size_t)(lr + R) * WS + x + R] = v;
+        }
+    }
+    if (!SMEM) __threadfence();
+
+    // ---- NMS rounds ------------------------------------------------------------------------ //
+    if constexpr (R > 0) {
+        for (int round = 0;; ++round) {
+            cluster.sync();  // S1: every band's V (and the previous round's flag) is final
+            if (round > 0) {
+                int any = 0;
+                for (int r = 0; r < CS; ++r) any |= *cluster.map_shared_rank(&sh.flags[(round - 1) & 1], r);
+                if (!any) break;
+            }
+            if (SMEM) {
+                if (rank > 0) {
+                    const float* src = cluster.map_shared_rank(V, rank - 1) + (size_t)nprev * WS;
+                    for (int i = tid; i < R * WS; i += kThreads) V[i] = src[i];
+                }
+                if (rank < CS - 1) {
+                    const float* src = cluster.map_shared_rank(V, rank + 1) + (size_t)R * WS;
+                    float* dst = V + (size_t)(R + nrows) * WS;
+                    for (int i = tid; i < R * WS; i += kThreads) dst[i] = src[i];
+                }
+                __syncthreads();
+            }
+            // fused row/column window pass: one warp walks a 32-column strip down a row segment,
+            // keeping the last 2R+1 full-width row maxima in registers
+            for (int item = warp; item < nitems; item += kWarps) {
+                if (!item_active[item]) continue;
+                const int s = item % S, g = item / S;
+                const int r0 = g * kSegRows;
+                const int r1 = min(r0 + kSegRows, nrows);
+                if (r0 >= r1) continue;
+                const int lc = 32 * s + lane + R;
+                float F[2 * R + 1], C[R + 1];
+#pragma unroll
+                for (int k = 0; k < 2 * R + 1; ++k) F[k] = 0.0f;
+#pragma unroll
+                for (int k = 0; k < R + 1; ++k) C[k] = 0.0f;
+                const int nsteps = (r1 - r0) + 2 * R;
+                for (int i = 0; i < nsteps; ++i) {
+                    const float* row = V + (size_t)(r0 + i) * WS + lc;
+                    float f = row[0];
+                    const float centre = f;
+#pragma unroll
+                    for (int d = 1; d <= R; ++d) f = fmaxf(f, fmaxf(row[-d], row[d]));
+#pragma unroll
+                    for (int k = 0; k < 2 * R; ++k) F[k] = F[k + 1];
+                    F[2 * R] = f;
+#pragma unroll
+                    for (int k = 0; k < R; ++k) C[k] = C[k + 1];
+                    C[R] = centre;
+                    if (i >= 2 * R) {
+                        const int c = r0 + i - 2 * R;  // own row being decided
+                        const float vc = C[0];
+                        float above = F[0], below = F[R + 1];
+#pragma unroll
+                        for (int k = 1; k < R; ++k) { above = fmaxf(above, F[k]); below = fmaxf(below, F[R + 1 + k]); }
+                        const float m = fmaxf(fmaxf(above, below), F[R]);
+                        bool lm = (vc > 0.0f) && (vc == m) && (above < vc);
+                        if (lm) {  // an equal value to the left in the same row wins the argmax
+                            const float* crow = V + (size_t)(c + R) * WS + lc;
+                            float left = crow[-1];
+#pragma unroll
+                            for (int d = 2; d <= R; ++d) left = fmaxf(left, crow[-d]);
+                            lm = left < vc;
+                        }
+                        const unsigned bits = __ballot_sync(0xffffffffu, lm);
+                        if (lane == 0) LM[(size_t)(c + R) * S + s] = bits;
+                    }
+                }
+            }
+            if (!SMEM) __threadfence();
+            cluster.sync();  // S2: own-row maxima bits are ready in every band
+            if (SMEM) {
+                if (rank > 0) {
+                    const uint32_t* src = cluster.map_shared_rank(LM, rank - 1) + (size_t)nprev * S;
+                    for (int i = tid; i < R * S; i += kThreads) LM[i] = src[i];
+                }
+                if (rank < CS - 1) {
+                    const uint32_t* src = cluster.map_shared_rank(LM, rank + 1) + (size_t)R * S;
+                    uint32_t* dst = LM + (size_t)(R + nrows) * S;
+                    for (int i = tid; i < R * S; i += kThreads) dst[i] = src[i];
+                }
+                __syncthreads();
+            }
+            // horizontal dilation of the maxima bits, on words.  In the global variant each CTA
+            // also covers its halo rows (cheap) so no third barrier is needed.
+            for (int i = tid; i < (nrows + 2 * R) * S; i += kThreads) {
+                const int row = i / S, s = i - row * S;
+                const int yy = ys - R + row;
+                uint32_t acc = 0;
+                if (yy >= 0 && yy < Hp) {
+                    const uint32_t w = LM[i];
+                    const uint32_t wl = s > 0 ? LM[i - 1] : 0u;
+                    const uint32_t wr = s < S - 1 ? LM[i + 1] : 0u;
+                    acc = w;
+#pragma unroll
+                    for (int d = 1; d <= R; ++d)
+                        acc |= (w >> d) | (wr << (32 - d)) | (w << d) | (wl >> (32 - d));
+                }
+                if (SMEM) RD[i] = acc;
+                else if (row >= R && row < R + nrows) RD[i] = acc;  // own rows only are stored ...
+                // ... halo rows of the global variant are recomputed by the consumer below
+            }
+            __syncthreads();
+            // suppression + undecided census
+            int und = 0;
+            for (int wi = warp; wi < nrows * S; wi += kWarps) {
+                const int lr = wi / S, s = wi - lr * S;
+                uint32_t part = 0;
+                if (lane <= 2 * R) {
+                    const int row = lr + lane;  // local rows lr .. lr+2R  (centre lr+R)
+                    if (SMEM || (row >= R && row < R + nrows)) {
+                        part = RD[(size_t)row * S + s];
+                    } else {
+                        const int yy = ys - R + row;
+                        if (yy >= 0 && yy < Hp) {
+                            const size_t i = (size_t)row * S + s;
+                            const uint32_t w = LM[i];
+                            const uint32_t wl = s > 0 ? LM[i - 1] : 0u;
+                            const uint32_t wr = s < S - 1 ? LM[i + 1] : 0u;
+                            part = w;
+#pragma unroll
+                            for (int d = 1; d <= R; ++d)
+                                part |= (w >> d) | (wr << (32 - d)) | (w << d) | (wl >> (32 - d));
+                        }
+                    }
+                }
+                const uint32_t dil = __reduce_or_sync(0xffffffffu, part);
+                const uint32_t lmw = LM[(size_t)(lr + R) * S + s];
+                const uint32_t sup = dil & ~lmw;
+                float* cell = V + (size_t)(lr + R) * WS + 32 * s + lane + R;
+                const float v = *cell;
+                const bool is_sup = (sup >> lane) & 1u;
+                if (is_sup && v != 0.0f) *cell = 0.0f;
+                const bool u = (v > 0.0f) && !is_sup && !((lmw >> lane) & 1u);
+                const unsigned ub = __ballot_sync(0xffffffffu, u);
+                if (lane == 0) {
+                    // a still-undecided pixel keeps its (strip, segment) item alive for the next round
+                    if (ub) {
+                        und = 1;
+                        item_active[(lr / kSegRows) * S + s] = 2;
+                    }
+                }
+            }
+            und = __syncthreads_or(und);
+            // 2 = touched this round, 1 = stale from the previous round
+            for (int i = tid; i < nitems; i += kThreads) item_active[i] = item_active[i] == 2 ? 1 : 0;
+            if (tid == 0) sh.flags[round & 1] = und;
+            if (!SMEM) __threadfence();
+        }
+    } else {
+        // no NMS: survivors are simply the positive pixels
+        __syncthreads();
+        for (int wi = warp; wi < nrows * S; wi += kWarps) {
+            const int lr = wi / S, s = wi - lr * S;
+            const float v = V[(size_t)(lr + R) * WS + 32 * s + lane + R];
+            const unsigned bits = __ballot_sync(0xffffffffu, v > 0.0f);
+            if (lane == 0) LM[(size_t)(lr + R) * S + s] = bits;
+        }
+        __syncthreads();
+    }
+
+    // ---- survivors -> ordered per-image list (global workspace) ------------------------------ //
+    // At the fixpoint every positive pixel is a local maximum, so the maxima bits of the last
+    // round are exactly the survivors.
+    float* slist = P.surv_val + (size_t)b * P.scap;
+    int32_t* sidx = P.surv_idx + (size_t)b * P.scap;
+    const int nwords = nrows * S;
+    int own = 0;
+    {
+        int c = 0;
+        for (int wi = tid; wi < nwords; wi += kThreads) c += __popc(LM[(size_t)R * S + wi]);
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (lane == 0 && c) atomicAdd(&sh.xcnt[0], c);
+    }
+    cluster.sync();
+    int offset = 0, total = 0;
+    for (int r = 0; r < CS; ++r) {
+        const int c = *cluster.map_shared_rank(&sh.xcnt[0], r);
+        if (r < rank) offset += c;
+        total += c;
+    }
+    own = sh.xcnt[0];
+    {
+        int run = offset;
+        for (int base = 0; base < nwords; base += kThreads) {
+            const int wi = base + tid;
+            const uint32_t w = wi < nwords ? LM[(size_t)R * S + wi] : 0u;
+            int tot;
+            int pos = run + block_excl_scan(__popc(w), sh.warp_scan, tot);
+            if (w) {
+                const int lr = wi / S, s = wi - lr * S;
+                uint32_t bits = w;
+                while (bits) {
+                    const int bit = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const int x = 32 * s + bit;
+                    if (pos < P.scap) {
+                        slist[pos] = V[(size_t)(lr + R) * WS + x + R];
+                        sidx[pos] = (ys + lr) * Wp + x;
+                    }
+                    ++pos;
+                }
+            }
+            run += tot;
+        }
+    }
+    __threadfence();
+    cluster.sync();  // the whole image's list is visible
+
+    // ---- threshold (detector_util.py:108-133), computed redundantly by every CTA ------------ //
+    float thr = P.prob_thresh;
+    if (P.use_topk == 2) {
+        thr = fminf(0.0f, P.prob_thresh);
+    } else if (P.use_topk == 1) {
+        const int n = Hp * Wp;
+        const int zeros = n - total;  // ascending order: the zeros come first
+        float a = 0.0f, bq = 0.0f;
+        if (P.rank_hi >= zeros) {
+            if (P.rank_lo >= zeros) {
+                select_two(slist, total, P.rank_lo - zeros, P.rank_hi != P.rank_lo, sh, a, bq);
+            } else {  // lo falls on a zero, hi on the smallest survivor
+                float dummy;
+                select_two(slist, total, 0, false, sh, bq, dummy);
+            }
+        }
+        // torch.lerp(a, b, 0.5) takes the `b - (b - a) * (1 - w)` branch
+        const float thr_k = __fsub_rn(bq, __fmul_rn(__fsub_rn(bq, a), 0.5f));
+        thr = fminf(thr_k, P.prob_thresh);
+    }
+
+    // ---- keypoint rows in raster order + optional dense map ---------------------------------- //
+    {
+        int c = 0;
+        for (int i = tid; i < own; i += kThreads) c += (__ldcg(slist + offset + i) > thr) ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (lane == 0 && c) atomicAdd(&sh.xcnt[1], c);
+    }
+    cluster.sync();
+    int koff = 0, ktotal = 0;
+    for (int r = 0; r < CS; ++r) {
+        const int c = *cluster.map_shared_rank(&sh.xcnt[1], r);
+        if (r < rank) koff += c;
+        ktotal += c;
+    }
+    if (rank == 0 && tid == 0) P.counts[b] = ktotal;
+    {
+        float* krows = P.kpts + (size_t)b * P.kcap * 3;
+        int run = koff;
+        for (int base = 0; base < own; base += kThreads) {
+            const int i = base + tid;
+            float v = 0.0f;
+            int idx = 0;
+            bool keep = false;
+            if (i < own) {
+                v = __ldcg(slist + offset + i);
+                idx = __ldcg(sidx + offset + i);
+                keep = v > thr;
+            }
+            int tot;
+            const int pos = run + block_excl_scan(keep ? 1 : 0, sh.warp_scan, tot);
+            if (keep && pos < P.kcap) {
+                const int y = idx / Wp, x = idx - y * Wp;
+                krows[(size_t)pos * 3 + 0] = (float)y + 0.5f;
+                krows[(size_t)pos * 3 + 1] = (float)x + 0.5f;
+                krows[(size_t)pos * 3 + 2] = v;
+            }
+            run += tot;
+        }
+    }
+    if (P.nms_map) {
+        float* out = P.nms_map + (size_t)b * Hp * Wp;
+        for (int e = tid; e < nrows * Wp; e += kThreads) {
+            const int lr = e / Wp, x = e - lr * Wp;
+            const float v = V[(size_t)(lr + R) * WS + x + R];
+            out[(size_t)(ys + lr) * Wp + x] = v > thr ? v : 0.0f;
+        }
+    }
+    cluster.sync();  // nobody leaves while a neighbour may still read its shared memory
+}
+
+template <int R, bool SMEM>
+int launch_detect(einx_ctx* ctx, const DetectParams& P, size_t smem, cudaStream_t stream) {
+    auto kern = detect_kernel<R, SMEM>;
+    EINX_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(P.B * P.CS);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = P.CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    EINX_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, P));
+    ctx->launches++;
+    return EINX_OK;
+}
+
+template <bool SMEM>
+int dispatch_radius(einx_ctx* ctx, int R, const DetectParams& P, size_t smem, cudaStream_t stream) {
+    switch (R) {
+        case 0: return launch_detect<0, SMEM>(ctx, P, smem, stream);
+        case 1: return launch_detect<1, SMEM>(ctx, P, smem, stream);
+        case 2: return launch_detect<2, SMEM>(ctx, P, smem, stream);
+        case 3: return launch_detect<3, SMEM>(ctx, P, smem, stream);
+        case 4: return launch_detect<4, SMEM>(ctx, P, smem, stream);
+        case 5: return launch_detect<5, SMEM>(ctx, P, smem, stream);
+        case 6: return launch_detect<6, SMEM>(ctx, P, smem, stream);
+        case 7: return launch_detect<7, SMEM>(ctx, P, smem, stream);
+        case 8: return launch_detect<8, SMEM>(ctx, P, smem, stream);
+    }
+    return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_detect: nms_radius %d not in [0, 8]", R);
+}
+
+// fp32 emulation of q = (n-k)/n, rank = q*(n-1) (detector_util.py:113-124; torch divides an
+// int64 tensor by a Python int in fp32 and quantile scales q in the input dtype)
+void topk_ranks(int n, int k, int* lo, int* hi) {
+    volatile float q = (float)(n - k) / (float)n;
+    volatile float rank = q * (float)(n - 1);
+    *lo = (int)floorf(rank);
+    *hi = (int)ceilf(rank);
+}
+
+}  // namespace
+
+extern "C" int einx_detect(einx_ctx* ctx, float* score, const uint8_t* mask, int B, int Hp, int Wp, int nms_radius,
+                           int border, float prob_thresh, int top_k, float* nms_map, float* kpts, int kcap,
+                           int32_t* counts, einx_stream stream_) {
+    if (!ctx) return EINX_ERR_INVALID;
+    if (B < 0 || Hp <= 0 || Wp <= 0 || nms_radius < 0 || border < 0 || kcap < 0)
+        return einx_fail(ctx, EINX_ERR_INVALID, "einx_detect: bad argument B=%d Hp=%d Wp=%d r=%d border=%d kcap=%d", B,
+                         Hp, Wp, nms_radius, border, kcap);
+    if (B == 0) return EINX_OK;
+    if (!score || !kpts || !counts) return einx_fail(ctx, EINX_ERR_INVALID, "einx_detect: NULL pointer argument");
+    if ((long long)Hp * Wp > (1ll << 30)) return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_detect: map too large");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int R = nms_radius;
+
+    DetectParams P = {};
+    P.score = score; P.mask = mask; P.nms_map = nms_map; P.kpts = kpts; P.counts = counts;
+    P.B = B; P.Hp = Hp; P.Wp = Wp; P.border = border; P.kcap = kcap;
+    P.S = (Wp + 31) / 32;
+    P.WS = 32 * P.S + 2 * R;
+    P.prob_thresh = prob_thresh;
+    const int n = Hp * Wp;
+    if (top_k > 0) {
+        if (top_k >= n) P.use_topk = 2;
+        else { P.use_topk = 1; topk_ranks(n, top_k, &P.rank_lo, &P.rank_hi); }
+    }
+    P.scap = R == 0 ? n : ((Hp + R) / (R + 1)) * ((Wp + R) / (R + 1));
+
+    // pick the cluster size: smallest that fits the band in shared memory, then widen while the
+    // machine would otherwise sit idle
+    const size_t fixed = align_up(sizeof(Shared), 16);
+    const size_t row_bytes = (size_t)P.WS * 4 + (size_t)P.S * 8;
+    auto smem_for = [&](int rb) {
+        const int nseg = (rb + kSegRows - 1) / kSegRows;
+        return fixed + row_bytes * (size_t)(rb + 2 * R) + align_up((size_t)P.S * nseg, 16);
+    };
+    const size_t budget = (size_t)ctx->max_smem_optin;
+    int CS = 0;
+    for (int c = 1; c <= kMaxCluster; ++c) {
+        const int rb = (Hp + c - 1) / c;
+        if (c > 1 && Hp / c < (R > 0 ? R : 1)) break;
+        if (smem_for(rb) <= budget) { CS = c; break; }
+    }
+    bool use_smem = CS > 0;
+    if (use_smem) {
+        while (CS * 2 <= kMaxCluster && (long long)B * CS * 2 <= ctx->num_sms && Hp / (CS * 2) >= 2 * (R > 0 ? R : 1) + 8) CS *= 2;
+    } else {
+        CS = kMaxCluster;
+        while (CS > 1 && Hp / CS < (R > 0 ? R : 1)) CS /= 2;
+    }
+    P.CS = CS;
+    P.RBmax = (Hp + CS - 1) / CS;
+
+    // workspace: survivor lists (+ padded global image for the large-map variant)
+    const size_t list_bytes = align_up((size_t)B * P.scap * 4, 256);
+    size_t ws_bytes = 2 * list_bytes;
+    const size_t img_rows = (size_t)Hp + 2 * R;
+    const size_t gv_bytes = align_up((size_t)B * img_rows * P.WS * 4, 256);
+    const size_t gw_bytes = align_up((size_t)B * img_rows * P.S * 4, 256);
+    if (!use_smem) ws_bytes += gv_bytes + 2 * gw_bytes;
+    int rc = einx_ws_reserve(ctx, ws_bytes);
+    if (rc) return rc;
+    unsigned char* ws = (unsigned char*)ctx->ws;
+    P.surv_val = (float*)ws;
+    P.surv_idx = (int32_t*)(ws + list_bytes);
+    size_t smem;
+    if (use_smem) {
+        smem = smem_for(P.RBmax);
+        return dispatch_radius<true>(ctx, R, P, smem, stream);
+    }
+    P.gV = (float*)(ws + 2 * list_bytes);
+    P.gLM = (uint32_t*)(ws + 2 * list_bytes + gv_bytes);
+    P.gRD = (uint32_t*)(ws + 2 * list_bytes + gv_bytes + gw_bytes);
+    EINX_CUDA(ctx, cudaMemsetAsync(P.gV, 0, gv_bytes + 2 * gw_bytes, stream));
+    const int nseg = (P.RBmax + kSegRows - 1) / kSegRows;
+    smem = fixed + align_up((size_t)P.S * nseg, 16);
+    return dispatch_radius<false>(ctx, R, P, smem, stream);
+}

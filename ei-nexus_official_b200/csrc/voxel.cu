@@ -1,0 +1,236 @@
+// Event voxelisation: trilinear scatter + non-zero mean/std normalisation.
+// Semantics: reference datasets/representations.py:8-22 and :66-124 (see include/einx.h).
+//
+// Layout in HBM: SoA events (x, y, p fp32; t fp64) for the whole ragged batch, grid
+// (B, bins, H, W) fp32.  The grid of a batch is L2-resident on B200 (C2: 64 x 0.86 MB), so the
+// zero / scatter / stats / apply passes hit L2, and DRAM sees the events once and the grid once.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kScatterThreads = 256;
+constexpr int kEventsPerThread = 4;
+
+__device__ __forceinline__ void red_add(float* addr, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_add2(float* addr, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+struct TimeBase {
+    double t0;     // first timestamp of the window
+    double denom;  // (t[-1] - t[0]) + 1e-8                  representations.py:19-20
+    float tf0;     // fp32 of the normalised first timestamp  (:76, :81)
+    float span;    // t_norm[-1] - t_norm[0] in fp32          (:81)
+};
+
+__device__ __forceinline__ TimeBase make_time_base(const double* __restrict__ t, int64_t beg, int64_t end) {
+    TimeBase tb;
+    tb.t0 = t[beg];
+    double tl = t[end - 1];
+    tb.denom = (tl - tb.t0) + 1e-8;
+    tb.tf0 = (float)((tb.t0 - tb.t0) / tb.denom);
+    float tfN = (float)((tl - tb.t0) / tb.denom);
+    tb.span = __fsub_rn(tfN, tb.tf0);
+    return tb;
+}
+
+// One event -> up to 8 corner contributions.  x-adjacent corners go out as one 8-byte vector
+// reduction when the pair is 8-byte aligned; exact-zero weights (integer-pixel EC events) are
+// skipped, which cannot change any cell (0 + 0) nor the `!= 0` normalisation mask.
+__device__ __forceinline__ void splat_event(float* __restrict__ g, float xf, float yf, float tn, float pf,
+                                            int bins, int H, int W) {
+    if (tn != tn) return;  // 0/0 time span: the reference's NaN bin index is out of range
+    const float pol = pf < 1.0f ? -1.0f : pf;  // value[value < 1] = -1   (:88-89)
+    const int x0 = (int)xf, y0 = (int)yf, t0 = (int)tn;  // .int() truncates (:83-85)
+    const float wx0 = __fmul_rn(pol, __fsub_rn(1.0f, fabsf(__fsub_rn((float)x0, xf))));
+    const float wx1 = __fmul_rn(pol, __fsub_rn(1.0f, fabsf(__fsub_rn((float)(x0 + 1), xf))));
+    const bool vx0 = (x0 >= 0) & (x0 < W);
+    const bool vx1 = (x0 + 1 >= 0) & (x0 + 1 < W);
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+        const int yl = y0 + dy;
+        if (yl < 0 || yl >= H) continue;
+        const float wy = __fsub_rn(1.0f, fabsf(__fsub_rn((float)yl, yf)));
+        const float a0 = __fmul_rn(wx0, wy), a1 = __fmul_rn(wx1, wy);
+#pragma unroll
+        for (int dt = 0; dt < 2; ++dt) {
+            const int tl = t0 + dt;
+            if (tl < 0 || tl >= bins) continue;
+            const float wt = __fsub_rn(1.0f, fabsf(__fsub_rn((float)tl, tn)));
+            const float w0 = vx0 ? __fmul_rn(a0, wt) : 0.0f;
+            const float w1 = vx1 ? __fmul_rn(a1, wt) : 0.0f;
+            if (w0 == 0.0f && w1 == 0.0f) continue;
+            float* cell = g + ((size_t)tl * H + yl) * W + x0;
+            if (vx0 && vx1 && ((reinterpret_cast<uintptr_t>(cell) & 7u) == 0)) {
+                red_add2(cell, w0, w1);
+            } else {
+                if (w0 != 0.0f) red_add(cell, w0);
+                if (w1 != 0.0f) red_add(cell + 1, w1);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kScatterThreads)
+voxel_scatter_kernel(const float* __restrict__ x, const float* __restrict__ y, const double* __restrict__ t,
+                     const float* __restrict__ p, const int64_t* __restrict__ off, int bins, int H, int W,
+                     float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int64_t beg = off[b], end = off[b + 1];
+    if (end - beg <= 0) return;
+    const TimeBase tb = make_time_base(t, beg, end);
+    const float bm1 = (float)(bins - 1);
+    float* g = out + (size_t)b * bins * H * W;
+    const int64_t stride = (int64_t)gridDim.x * kScatterThreads * kEventsPerThread;
+    for (int64_t base = beg + (int64_t)blockIdx.x * kScatterThreads * kEventsPerThread; base < end; base += stride) {
+        float xf[kEventsPerThread], yf[kEventsPerThread], pf[kEventsPerThread];
+        double td[kEventsPerThread];
+        // issue all loads of this thread's events before any dependent math (coalesced per warp)
+#pragma unroll
+        for (int k = 0; k < kEventsPerThread; ++k) {
+            const int64_t i = base + k * kScatterThreads + threadIdx.x;
+            const bool ok = i < end;
+            xf[k] = ok ? __ldg(x + i) : 0.f;
+            yf[k] = ok ? __ldg(y + i) : 0.f;
+            pf[k] = ok ? __ldg(p + i) : 0.f;
+            td[k] = ok ? __ldg(t + i) : tb.t0;
+        }
+#pragma unroll
+        for (int k = 0; k < kEventsPerThread; ++k) {
+            const int64_t i = base + k * kScatterThreads + threadIdx.x;
+            if (i >= end) continue;
+            const float tf = (float)((td[k] - tb.t0) / tb.denom);                          // :19-20, :76
+            const float tn = __fdiv_rn(__fmul_rn(bm1, __fsub_rn(tf, tb.tf0)), tb.span);  // :81
+            splat_event(g, xf[k], yf[k], tn, pf[k], bins, H, W);
+        }
+    }
+}
+
+// ---- normalisation: statistics over cells != 0, then apply -------------------------------- //
+struct Stats {
+    double n, sum, sumsq;
+};
+
+__global__ void __launch_bounds__(256)
+voxel_stats_kernel(const float* __restrict__ grid, size_t ncell, double* __restrict__ stats) {
+    const int b = blockIdx.y;
+    const float* g = grid + (size_t)b * ncell;
+    double n = 0, s = 0, ss = 0;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nthr = (size_t)gridDim.x * blockDim.x;
+    if (((ncell & 3) == 0) && ((reinterpret_cast<uintptr_t>(g) & 15u) == 0)) {
+        const float4* g4 = reinterpret_cast<const float4*>(g);
+        for (size_t i = tid; i < ncell / 4; i += nthr) {
+            const float4 v = g4[i];
+            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (e[k] != 0.0f) { n += 1.0; s += (double)e[k]; ss += (double)e[k] * (double)e[k]; }
+        }
+    } else {
+        for (size_t i = tid; i < ncell; i += nthr) {
+            const float e = g[i];
+            if (e != 0.0f) { n += 1.0; s += (double)e; ss += (double)e * (double)e; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n += __shfl_xor_sync(0xffffffffu, n, o);
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    __shared__ double sh[3][8];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sh[0][w] = n; sh[1][w] = s; sh[2][w] = ss; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double a = 0;
+        for (int k = 0; k < 8; ++k) a += sh[threadIdx.x][k];
+        if (a != 0.0) atomicAdd(stats + 3 * b + threadIdx.x, a);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+voxel_apply_kernel(float* __restrict__ grid, size_t ncell, const double* __restrict__ stats) {
+    const int b = blockIdx.y;
+    const double n = stats[3 * b], s = stats[3 * b + 1], ss = stats[3 * b + 2];
+    if (n <= 0.0) return;
+    const double mean_d = s / n;
+    const float mean = (float)mean_d;
+    // unbiased std (torch.Tensor.std); a single cell gives nan, which fails `std > 0` (:118-121)
+    float sd = nanf("");
+    if (n > 1.0) {
+        double var = (ss - n * mean_d * mean_d) / (n - 1.0);
+        sd = (float)sqrt(var > 0.0 ? var : 0.0);
+    }
+    const bool divide = sd > 0.0f;
+    float* g = grid + (size_t)b * ncell;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nthr = (size_t)gridDim.x * blockDim.x;
+    if (((ncell & 3) == 0) && ((reinterpret_cast<uintptr_t>(g) & 15u) == 0)) {
+        float4* g4 = reinterpret_cast<float4*>(g);
+        for (size_t i = tid; i < ncell / 4; i += nthr) {
+            float4 v = g4[i];
+            float e[4] = {v.x, v.y, v.z, v.w};
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (e[k] != 0.0f) {
+                    const float c = __fsub_rn(e[k], mean);
+                    e[k] = divide ? __fdiv_rn(c, sd) : c;
+                    any = true;
+                }
+            if (any) g4[i] = make_float4(e[0], e[1], e[2], e[3]);
+        }
+    } else {
+        for (size_t i = tid; i < ncell; i += nthr) {
+            const float e = g[i];
+            if (e != 0.0f) {
+                const float c = __fsub_rn(e, mean);
+                g[i] = divide ? __fdiv_rn(c, sd) : c;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int einx_voxelize(einx_ctx* ctx, const float* x, const float* y, const double* t, const float* p,
+                             const int64_t* ev_offsets, int B, int bins, int H, int W, int normalize,
+                             float* out, einx_stream stream_) {
+    if (!ctx) return EINX_ERR_INVALID;
+    if (B < 0 || bins <= 0 || H <= 0 || W <= 0)
+        return einx_fail(ctx, EINX_ERR_INVALID, "einx_voxelize: bad shape B=%d bins=%d H=%d W=%d", B, bins, H, W);
+    if (B == 0) return EINX_OK;
+    if (!x || !y || !t || !p || !ev_offsets || !out)
+        return einx_fail(ctx, EINX_ERR_INVALID, "einx_voxelize: NULL pointer argument");
+    if (B > 65535) return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_voxelize: B=%d > 65535", B);
+    DeviceGuard guard(ctx->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t ncell = (size_t)bins * H * W;
+    EINX_CUDA(ctx, cudaMemsetAsync(out, 0, sizeof(float) * ncell * B, stream));
+    // enough CTAs per window to cover the machine a few times over; windows are ragged, so a
+    // CTA grid-strides over its own window only
+    int per_window = (ctx->num_sms * 8 + B - 1) / B;
+    if (per_window < 1) per_window = 1;
+    if (per_window > 1024) per_window = 1024;
+    voxel_scatter_kernel<<<dim3(per_window, B), kScatterThreads, 0, stream>>>(x, y, t, p, ev_offsets, bins, H, W, out);
+    EINX_CHECK_LAUNCH(ctx);
+    if (normalize) {
+        int rc = einx_ws_reserve(ctx, sizeof(double) * 3 * B);
+        if (rc) return rc;
+        double* stats = (double*)ctx->ws;
+        EINX_CUDA(ctx, cudaMemsetAsync(stats, 0, sizeof(double) * 3 * B, stream));
+        int chunks = (int)((ncell / 4 + 255) / 256);
+        int cap = (ctx->num_sms * 8 + B - 1) / B;
+        if (chunks > cap) chunks = cap;
+        if (chunks < 1) chunks = 1;
+        voxel_stats_kernel<<<dim3(chunks, B), 256, 0, stream>>>(out, ncell, stats);
+        EINX_CHECK_LAUNCH(ctx);
+        voxel_apply_kernel<<<dim3(chunks, B), 256, 0, stream>>>(out, ncell, stats);
+        EINX_CHECK_LAUNCH(ctx);
+    }
+    return EINX_OK;
+}

@@ -1,0 +1,119 @@
+"""Mutual-nearest-neighbour matcher -- host side of einx_mnn.
+
+``NearestNeighborMatcher`` keeps the constructor and the forward contract of the reference's
+``core/modules/matchers/MNN.py:35-140``.  ``similarity`` / ``log_assignment`` are only
+materialised when ``return_dense=True`` (no live consumer in the reference);
+otherwise the keys are present with value ``None`` so ``core/modules/Matchers.py:180-203`` keeps working.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+FP32, TF32X3, BF16 = 0, 1, 2
+_PRECISION = {"fp32": FP32, "tf32x3": TF32X3, "bf16": BF16}
+
+
+@torch.no_grad()
+def mnn(desc0: torch.Tensor, desc1: torch.Tensor, n0: Optional[torch.Tensor] = None,
+        n1: Optional[torch.Tensor] = None, kpts0: Optional[torch.Tensor] = None,
+        kpts1: Optional[torch.Tensor] = None, ratio_thresh=None, distance_thresh=None, mutual: bool = True,
+        precision="fp32") -> Dict[str, torch.Tensor]:
+    """einx_mnn on padded batches: desc0 (B, N, D), desc1 (B, M, D) fp32 CUDA; n0/n1 valid-row counts.
+
+    Returns matches0/1 (int64, -1 = none), matching_scores0/1 and, when keypoints are given, the
+    compacted ``matched_kpts0/1`` (B, N, 3) with ``num_matches`` (B,) int32.
+    """
+    if desc0.dtype != torch.float32 or not desc0.is_cuda or desc1.dtype != torch.float32 or not desc1.is_cuda:
+        raise _lib.EinxError("mnn: descriptors must be float32 CUDA tensors (there is no CPU fallback)")
+    desc0, desc1 = desc0.contiguous(), desc1.contiguous()
+    B, N, D = desc0.shape
+    M = desc1.shape[1]
+    if desc1.shape[0] != B or desc1.shape[2] != D:
+        raise ValueError("mnn: desc0 / desc1 batch or feature size mismatch")
+    dev = desc0.device
+    ctx = _lib.context_for(dev)
+    prec = _PRECISION[precision] if isinstance(precision, str) else int(precision)
+    m0 = torch.empty((B, N), dtype=torch.int64, device=dev)
+    m1 = torch.empty((B, M), dtype=torch.int64, device=dev)
+    s0 = torch.empty((B, N), dtype=torch.float32, device=dev)
+    s1 = torch.empty((B, M), dtype=torch.float32, device=dev)
+    mk0 = mk1 = nm = None
+    if kpts0 is not None:
+        kpts0, kpts1 = kpts0.contiguous(), kpts1.contiguous()
+        mk0 = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
+        mk1 = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
+        nm = torch.empty((B,), dtype=torch.int32, device=dev)
+    rc = ctx.lib.einx_mnn(ctx.handle, _lib.ptr(desc0), _lib.ptr(desc1), _lib.ptr(n0), _lib.ptr(n1), B, N, M, D,
+                          float(ratio_thresh or 0.0), float(distance_thresh or 0.0), int(bool(mutual)), prec,
+                          _lib.ptr(m0), _lib.ptr(m1), _lib.ptr(s0), _lib.ptr(s1), _lib.ptr(kpts0), _lib.ptr(kpts1),
+                          _lib.ptr(mk0), _lib.ptr(mk1), _lib.ptr(nm), _lib.stream_of(dev))
+    ctx.check(rc, "einx_mnn")
+    out = {"matches0": m0, "matches1": m1, "matching_scores0": s0, "matching_scores1": s1}
+    if kpts0 is not None:
+        out.update(matched_kpts0=mk0, matched_kpts1=mk1, num_matches=nm)
+    return out
+
+
+@torch.no_grad()
+def mnn_dense(desc0: torch.Tensor, desc1: torch.Tensor):
+    """Opt-in ``similarity`` (B, N, M) and ``log_assignment`` (B, N+1, M+1) of MNN.py:88, :96-98."""
+    desc0, desc1 = desc0.contiguous(), desc1.contiguous()
+    B, N, D = desc0.shape
+    M = desc1.shape[1]
+    dev = desc0.device
+    ctx = _lib.context_for(dev)
+    sim = torch.empty((B, N, M), dtype=torch.float32, device=dev)
+    la = torch.empty((B, N + 1, M + 1), dtype=torch.float32, device=dev)
+    rc = ctx.lib.einx_mnn_dense(ctx.handle, _lib.ptr(desc0), _lib.ptr(desc1), B, N, M, D, _lib.ptr(sim),
+                                _lib.ptr(la), _lib.stream_of(dev))
+    ctx.check(rc, "einx_mnn_dense")
+    return sim, la
+
+
+class NearestNeighborMatcher(nn.Module):
+    """Drop-in for ``core/modules/matchers/MNN.py:35-140``."""
+
+    def __init__(self, ratio_thresh=None, distance_thresh=None, mutual_check=True, precision="fp32",
+                 return_dense=False):
+        super().__init__()
+        self.ratio_thresh = ratio_thresh
+        self.distance_thresh = distance_thresh
+        self.mutual_check = mutual_check
+        self.precision = precision
+        self.return_dense = return_dense
+
+    @torch.no_grad()
+    def forward(self, feats0: Dict[str, torch.Tensor], feats1: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        desc0, desc1 = feats0["sparse_descriptors"], feats1["sparse_descriptors"]
+        kpts0, kpts1 = feats0["sparse_positions"], feats1["sparse_positions"]
+        b, n, m = desc0.shape[0], desc0.shape[1], desc1.shape[1]
+        dense = self.return_dense
+        if kpts0.numel() == 0 or kpts1.numel() == 0:  # MNN.py:63-86
+            print("No keypoints found in either image")
+            empty0 = [kpts0.new_zeros((kpts0.shape[1], 3))] * b if b > 1 else kpts0.new_zeros((0, 3))
+            empty1 = [kpts1.new_zeros((kpts1.shape[1], 3))] * b if b > 1 else kpts1.new_zeros((0, 3))
+            return {
+                "matches0": desc0.new_full((b, n), -1), "matches1": desc1.new_full((b, m), -1),
+                "matching_scores0": desc0.new_zeros((b, n)), "matching_scores1": desc1.new_zeros((b, m)),
+                "matched_kpts0": empty0, "matched_kpts1": empty1,
+                "similarity": desc0.new_zeros((b, n, m)) if dense else None,
+                "log_assignment": desc0.new_zeros((b, n + 1, m + 1)) if dense else None,
+            }
+        out = mnn(desc0, desc1, None, None, kpts0[..., :3].float(), kpts1[..., :3].float(), self.ratio_thresh,
+                  self.distance_thresh, self.mutual_check, self.precision)
+        if self.mutual_check:
+            assert (out["matches0"] > -1).sum() == (out["matches1"] > -1).sum()  # MNN.py:95
+        nm = out.pop("num_matches").tolist()
+        mk0, mk1 = out["matched_kpts0"], out["matched_kpts1"]
+        if b > 1:
+            out["matched_kpts0"] = [mk0[i, : nm[i]] for i in range(b)]
+            out["matched_kpts1"] = [mk1[i, : nm[i]] for i in range(b)]
+        else:
+            out["matched_kpts0"], out["matched_kpts1"] = mk0[0, : nm[0]], mk1[0, : nm[0]]
+        out["similarity"], out["log_assignment"] = mnn_dense(desc0, desc1) if dense else (None, None)
+        return out

@@ -1,0 +1,97 @@
+"""Event representation builder -- host side of einx_voxelize.
+
+Keeps the call surface of the reference's ``datasets/representations.py``:
+``events_to_voxel_grid(events, input_size, normalize=True)`` (:66-124) takes a dict of four
+equal-length numpy arrays and returns a CPU fp32 ``(bins, H, W)`` tensor, with the same side
+effects on ``events``.  ``voxelize_batch`` is the batched, device-resident form the pipeline uses.
+"""
+from __future__ import annotations
+
+from typing import Dict, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def time_normalization(events: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+    """Reference ``time_normalization`` (representations.py:8-22), same in-place dict update."""
+    events["t"] = events["t"] - events["t"][0]
+    events["t"] = events["t"] / (events["t"][-1] + 1e-8)
+    return events
+
+
+def pack_events(batch: Sequence[Dict[str, np.ndarray]], pin: bool = False):
+    """Concatenate event windows into the SoA layout of the C ABI.
+
+    Returns CPU tensors (x, y, t, p, offsets): x/y/p fp32 (the cast of representations.py:73-75),
+    t fp64 (left untouched for the on-device fp64 offset subtraction), offsets int64 (B+1).
+    """
+    counts = [len(ev["t"]) for ev in batch]
+    for ev, n in zip(batch, counts):
+        if n == 0:
+            raise IndexError("index 0 is out of bounds: empty event window (reference raises here too)")
+        if not (len(ev["x"]) == len(ev["y"]) == len(ev["p"]) == n):
+            raise ValueError("events x, y, t, p must have equal length")
+    off = np.zeros(len(batch) + 1, dtype=np.int64)
+    np.cumsum(counts, out=off[1:])
+    total = int(off[-1])
+
+    def alloc(dtype):
+        t = torch.empty(total, dtype=dtype)
+        return t.pin_memory() if pin else t
+
+    x, y, p, t = alloc(torch.float32), alloc(torch.float32), alloc(torch.float32), alloc(torch.float64)
+    xn, yn, pn, tn = x.numpy(), y.numpy(), p.numpy(), t.numpy()
+    for ev, a, b in zip(batch, off[:-1], off[1:]):
+        xn[a:b] = ev["x"]  # numpy casts to float32 exactly like .astype("float32")
+        yn[a:b] = ev["y"]
+        pn[a:b] = ev["p"]
+        tn[a:b] = ev["t"]
+    return x, y, t, p, torch.from_numpy(off)
+
+
+def voxelize_device(x, y, t, p, offsets, input_size: Tuple[int, int, int], normalize: bool = True,
+                    out: torch.Tensor | None = None) -> torch.Tensor:
+    """einx_voxelize on device-resident SoA events; returns (B, bins, H, W) fp32 on the same device."""
+    bins, H, W = (int(v) for v in input_size)
+    dev = x.device
+    ctx = _lib.context_for(dev)
+    for name, ten, dt in (("x", x, torch.float32), ("y", y, torch.float32), ("p", p, torch.float32),
+                          ("t", t, torch.float64), ("offsets", offsets, torch.int64)):
+        if ten.dtype != dt or not ten.is_contiguous() or ten.device != dev:
+            raise ValueError(f"{name}: expected contiguous {dt} on {dev}")
+    B = offsets.numel() - 1
+    if out is None:
+        out = torch.empty((B, bins, H, W), dtype=torch.float32, device=dev)
+    rc = ctx.lib.einx_voxelize(ctx.handle, _lib.ptr(x), _lib.ptr(y), _lib.ptr(t), _lib.ptr(p), _lib.ptr(offsets),
+                               B, bins, H, W, int(bool(normalize)), _lib.ptr(out), _lib.stream_of(dev))
+    ctx.check(rc, "einx_voxelize")
+    return out
+
+
+def voxelize_batch(batch: Sequence[Dict[str, np.ndarray]], input_size, normalize: bool = True,
+                   device="cuda") -> torch.Tensor:
+    """Ragged batch of event dicts -> (B, bins, H, W) voxel grids on ``device``."""
+    x, y, t, p, off = pack_events(batch)
+    dev = torch.device(device)
+    return voxelize_device(x.to(dev), y.to(dev), t.to(dev), p.to(dev), off.to(dev), input_size, normalize)
+
+
+@torch.no_grad()
+def events_to_voxel_grid(events: Dict, input_size: Tuple, normalize: bool = True, device="cuda") -> torch.Tensor:
+    """Drop-in for ``datasets/representations.py:66-124``.
+
+    Same inputs, same CPU fp32 result, same observable side effects: afterwards ``events`` holds
+    fp32 torch tensors, ``t`` normalised to [0, 1) and ``p`` with every value < 1 set to -1.
+    """
+    grid = voxelize_batch([events], input_size, normalize, device)[0].cpu()
+    # side effects of :72-76 and :88-89 (cheap host work; the kernel recomputes them on device)
+    events = time_normalization(events)
+    events["x"] = torch.from_numpy(events["x"].astype("float32"))
+    events["y"] = torch.from_numpy(events["y"].astype("float32"))
+    events["p"] = torch.from_numpy(events["p"].astype("float32"))
+    events["t"] = torch.from_numpy(events["t"].astype("float32"))
+    events["p"][events["p"] < 1] = -1
+    return grid

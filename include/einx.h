@@ -1,0 +1,134 @@
+/*
+ * einx.h -- C ABI of the B200-native (sm_100a) extraction-and-matching path of EI-Nexus.
+ *
+ * The reference (ZhonghuaYi/EI-Nexus_official) is pure Python/PyTorch and has no FFI; the
+ * boundary it exposes for this path is four groups of Python callables.  Each entry point
+ * below replaces the ATen op sequence behind one of them (paths relative to the reference
+ * root); the Python host layer in ei-nexus_official_b200/ keeps the reference signatures and
+ * binds these symbols with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer owned by the caller (outputs included);
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*) and never
+ *     synchronise with the host;
+ *   - return value: 0 (EINX_OK) or a negative EINX_ERR_*; text via einx_last_error();
+ *   - no C++ exception crosses the ABI; one context is not thread-safe, distinct contexts are;
+ *   - sm_100a only: einx_create() fails with EINX_ERR_ARCH on any other device.  There is no
+ *     CPU or generic-GPU fallback anywhere behind this header.
+ */
+#ifndef EINX_H_
+#define EINX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EINX_OK 0
+#define EINX_ERR_INVALID (-1)     /* bad argument                                   */
+#define EINX_ERR_CUDA (-2)        /* a CUDA runtime call failed                     */
+#define EINX_ERR_ARCH (-3)        /* device is not compute capability 10.0 (B200)   */
+#define EINX_ERR_NOMEM (-4)       /* workspace allocation failed                    */
+#define EINX_ERR_UNSUPPORTED (-5) /* shape outside what the kernels were built for  */
+
+#define EINX_SAMPLE_GATHER 0   /* sparsify_full_resolution_descriptors */
+#define EINX_SAMPLE_BILINEAR 1 /* sparsify_low_resolution_descriptors  */
+
+#define EINX_MNN_FP32 0  /* FFMA tiles, fp32 accumulate: index-exact reference path */
+#define EINX_MNN_TF32X3 1 /* tcgen05 kind::tf32, 3-term split (hi*hi + hi*lo + lo*hi) */
+#define EINX_MNN_BF16 2  /* tcgen05 kind::f16 on bf16-rounded descriptors             */
+
+typedef struct einx_ctx einx_ctx;
+typedef void* einx_stream; /* cudaStream_t */
+
+/* ABI version of this header (major*100 + minor). */
+int einx_version(void);
+
+/* Context: owns the per-device workspace (NMS survivor lists, radix-select histograms,
+ * voxel statistics, MNN row/column best keys).  `device` is a CUDA ordinal. */
+int einx_create(int device, einx_ctx** out);
+void einx_destroy(einx_ctx* ctx);
+/* Last error text of `ctx`; pass NULL for the error of a failed einx_create(). */
+const char* einx_last_error(const einx_ctx* ctx);
+
+/*
+ * Event voxelisation.  Replaces datasets/representations.py:8-22 (time_normalization) and
+ * :66-124 (events_to_voxel_grid) for a ragged batch of B event windows.
+ *   x, y, p   : (N_total) fp32 -- the reference casts to float32 at :73-75
+ *   t         : (N_total) fp64 -- stays double across the ABI: the offset subtraction of :19-20
+ *               happens in fp64 before the fp32 cast of :76 (epoch-scale timestamps)
+ *   ev_offsets: (B+1) int64, window b owns events [ev_offsets[b], ev_offsets[b+1]), time-sorted
+ *   out       : (B, bins, H, W) fp32, fully overwritten
+ *   normalize : non-zero -> mean / unbiased-std normalisation over cells != 0 (:114-122)
+ * A window with a single event yields an all-zero grid (the reference's 0/0 time maps to an
+ * out-of-range bin); empty windows yield zeros (the reference raises IndexError -- the host
+ * layer keeps that behaviour).
+ */
+int einx_voxelize(einx_ctx* ctx, const float* x, const float* y, const double* t, const float* p,
+                  const int64_t* ev_offsets, int B, int bins, int H, int W, int normalize,
+                  float* out, einx_stream stream);
+
+/*
+ * Detection post-processing.  Replaces core/modules/utils/detector_util.py:80-135
+ * (prob_map_to_points_map: remove_border_points :138-164, fast_nms :243-337, the quantile
+ * top-k threshold :108-133) and :451-484 (prob_map_to_positions_with_prob, ordering 'yx').
+ *   score     : (B, Hp, Wp) fp32 >= 0, border frame zeroed IN PLACE like the reference
+ *   mask      : optional (B, Hp, Wp) uint8; where 0 the score is zeroed first (in place), i.e.
+ *               `score[~mask] = 0` of EventExtractors.py:374-375 fused in; NULL to skip
+ *   top_k     : <= 0 means None; prob_thresh as in the reference (1.0 in every shipped config)
+ *   nms_map   : optional (B, Hp, Wp) fp32 dense result (the `nms` tensor); NULL to skip
+ *   kpts      : (B, kcap, 3) fp32 rows (y+0.5, x+0.5, prob) in raster order; rows >= count
+ *               are left untouched
+ *   counts    : (B) int32 number of keypoints found (may exceed kcap: only kcap rows written)
+ * Bit-exact with the reference for non-negative, NaN-free maps.
+ */
+int einx_detect(einx_ctx* ctx, float* score, const uint8_t* mask, int B, int Hp, int Wp,
+                int nms_radius, int border, float prob_thresh, int top_k, float* nms_map,
+                float* kpts, int kcap, int32_t* counts, einx_stream stream);
+
+/*
+ * Descriptor sampling + L2 normalisation.  Replaces core/modules/utils/descriptor_util.py:21-28
+ * (normalize_descriptors), :50-71 (gather, SiLK type) and :74-128 (bilinear grid_sample with
+ * align_corners=False on the padded-image grid, SuperPoint type).
+ *   raw   : (B, C, Hd, Wd) fp32 descriptor map (Hd, Wd = padded image for gather; coarse map
+ *           for bilinear)
+ *   Hp,Wp : padded image size the positions refer to (bilinear mode only)
+ *   kpts  : (B, kcap, 3) as written by einx_detect; counts (B) int32 (clamped to kcap)
+ *   desc  : (B, kcap, C) fp32; rows >= count are zero-filled
+ */
+int einx_sample(einx_ctx* ctx, const float* raw, int B, int C, int Hd, int Wd, int mode, int Hp,
+                int Wp, const float* kpts, const int32_t* counts, int kcap, float scale,
+                int normalize, float* desc, einx_stream stream);
+
+/*
+ * Mutual-nearest-neighbour matching.  Replaces core/modules/matchers/MNN.py:11-22 (find_nn),
+ * :25-32 (mutual_check) and :88-129 of NearestNeighborMatcher.forward.  The similarity matrix
+ * is never written to memory: row/column argmax are fused into the tile epilogue.
+ *   d0 (B, ncap, D), d1 (B, mcap, D) fp32; n0, n1 (B) int32 valid rows (NULL = all)
+ *   ratio_thresh / distance_thresh <= 0 disable the test (None/False in the reference)
+ *   m0 (B, ncap), m1 (B, mcap) int64, -1 = unmatched; s0, s1 fp32 (m > -1)
+ *   kpts0/kpts1 (B, cap, 3) + mk0/mk1 (B, ncap, 3) + nmatch (B): optional compaction of the
+ *   matched keypoint rows in ascending i (:103-129); pass NULL kpts0 to skip
+ * Ties resolve to the lowest index like topk(1).
+ */
+int einx_mnn(einx_ctx* ctx, const float* d0, const float* d1, const int32_t* n0,
+             const int32_t* n1, int B, int ncap, int mcap, int D, float ratio_thresh,
+             float distance_thresh, int mutual, int precision, int64_t* m0, int64_t* m1,
+             float* s0, float* s1, const float* kpts0, const float* kpts1, float* mk0,
+             float* mk1, int32_t* nmatch, einx_stream stream);
+
+/*
+ * Opt-in dense by-products of MNN.py:88,96-98 for callers that really want them
+ * (`similarity` (B,N,M) and `log_assignment` (B,N+1,M+1)); fp32 FFMA path.
+ */
+int einx_mnn_dense(einx_ctx* ctx, const float* d0, const float* d1, int B, int N, int M, int D,
+                   float* similarity, float* log_assignment, einx_stream stream);
+
+/* Number of kernel launches issued through `ctx` so far (bench.py's gpu_launches). */
+int64_t einx_launch_count(const einx_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EINX_H_ */

@@ -1,0 +1,130 @@
+"""CPU-side checks: the C-ABI library loads and exports what include/einx.h declares, the product
+path refuses to run without a GPU (no fallback), and the host-side helpers behave."""
+import ctypes
+import importlib
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def einx():
+    import einx as m
+
+    return m
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    build = importlib.import_module("ei-nexus_official_b200.build")
+    return build.build_library()
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "einx.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(einx_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_header_symbol(built_lib):
+    lib = ctypes.CDLL(built_lib)
+    syms = header_symbols()
+    assert {"einx_create", "einx_destroy", "einx_voxelize", "einx_detect", "einx_sample", "einx_mnn"} <= set(syms)
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/einx.h but not exported"
+    lib.einx_version.restype = ctypes.c_int
+    assert lib.einx_version() == 100
+
+
+def test_ctypes_table_matches_header(einx):
+    assert sorted(einx._lib.SIGNATURES) == header_symbols()
+
+
+def test_library_is_sm100a_only(built_lib):
+    out = subprocess.run(["cuobjdump", "--list-elf", built_lib], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_\d+a?", out.stdout))
+    assert archs == {"sm_100a"}, archs
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback(einx):
+    ev = {"x": np.array([1.0, 2.0]), "y": np.array([1.0, 2.0]), "t": np.array([0.0, 1.0]), "p": np.array([1.0, 0.0])}
+    with pytest.raises(Exception):
+        einx.events_to_voxel_grid(ev, (3, 8, 8))
+    with pytest.raises(einx.EinxError):
+        einx.detect(torch.rand(1, 1, 16, 16), 1.0, 4, 4, 10)
+    with pytest.raises(einx.EinxError):
+        einx.mnn(torch.rand(1, 4, 8), torch.rand(1, 4, 8))
+    with pytest.raises(einx.EinxError):
+        einx.sample(torch.rand(1, 8, 4, 4), torch.zeros(1, 2, 3), torch.zeros(1, dtype=torch.int32), 0)
+    with pytest.raises(einx.EinxError):
+        einx._lib.Context(0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "ei-nexus_official_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"(^|\n)\s*(from|import)\s+oracle|einx_oracle|oracle/", text), f"{f} uses oracle/"
+
+
+def test_pack_events_layout(einx):
+    rng = np.random.default_rng(0)
+    batch = [{"x": rng.random(n) * 10, "y": rng.random(n) * 10, "t": np.sort(rng.random(n)) + 1.5e9,
+              "p": rng.integers(0, 2, n).astype(np.float64)} for n in (5, 1, 9)]
+    x, y, t, p, off = einx.pack_events(batch)
+    assert off.tolist() == [0, 5, 6, 15] and off.dtype == torch.int64
+    assert x.dtype == torch.float32 and t.dtype == torch.float64
+    assert np.array_equal(x[5:6].numpy(), batch[1]["x"].astype("float32"))
+    assert np.array_equal(t[6:].numpy(), batch[2]["t"])
+    with pytest.raises(IndexError):
+        einx.pack_events([{k: np.zeros(0) for k in "xytp"}])
+
+
+def test_time_normalization_matches_oracle(einx):
+    from oracle import einx_oracle as O
+
+    t = np.sort(np.random.default_rng(1).uniform(1.5e9, 1.5e9 + 0.4, 100))
+    ev = einx.time_normalization({"t": t.copy()})
+    assert np.array_equal(ev["t"], O.time_normalization(t))
+
+
+def test_shard_range_partitions(einx):
+    for total in (0, 1, 7, 64, 256):
+        for world in (1, 2, 3, 8):
+            spans = [einx.shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_padded_size_and_seed():
+    synth = importlib.import_module("ei-nexus_official_b200.synth")
+    from oracle import einx_oracle as O
+
+    assert synth.padded_size(260, 346, 8) == (264, 352, (3, 3, 2, 2))
+    assert synth.padded_size(180, 240, 8) == (184, 240, (0, 0, 2, 2))
+    assert synth.padded_size(180, 240, 8)[2] == O.padder_sizes(180, 240, 8)
+    assert synth.seed_for(2, 5) == 1234 + 2000 + 5
+
+
+def test_max_keypoints_bound():
+    det = importlib.import_module("ei-nexus_official_b200.detection")
+    from oracle import einx_oracle as O
+
+    rng = np.random.default_rng(4)
+    for r in (1, 2, 4):
+        v = O.fast_nms(rng.random((2, 40, 56)).astype(np.float32), r)
+        assert (v > 0).reshape(2, -1).sum(1).max() <= det.max_keypoints(40, 56, r)
