@@ -47,8 +47,10 @@ def detect(score: torch.Tensor, prob_thresh: float, nms_dist: int, border_dist: 
     ctx = _lib.context_for(dev)
     k = int(top_k) if top_k else 0
     if kcap is None:
+        # the top-k threshold only bounds the count by k when prob_thresh cannot undercut it
+        # (thr = min(thr_k, prob_thresh)); probabilities never exceed 1
         bound = max_keypoints(Hp, Wp, nms_dist)
-        kcap = min(k, bound) if k > 0 else bound
+        kcap = min(k, bound) if (k > 0 and prob_thresh >= 1.0) else bound
     kcap = max(int(kcap), 1)
     kpts = torch.empty((B, kcap, 3), dtype=torch.float32, device=dev)
     counts = torch.empty((B,), dtype=torch.int32, device=dev)
