@@ -7,9 +7,9 @@
 //   warp 0   TMA producer   -- A tile 128 rows x 128 B, B tile 256 rows x 128 B per k-block
 //   warp 1   MMA issuer     -- one lane issues tcgen05.mma (M=128, N=256, K=32 bytes) x4 per k-block
 //   warp 2   TMEM allocator -- 512 columns = two 128x256 fp32 accumulators (double buffered)
-//   warps 4-7 epilogue      -- tcgen05.ld 32 columns at a time; per-row running max in registers,
-//                              per-column max over the warp's 32 rows with redux.sync, then one
-//                              64-bit atomicMax per row / column into the global key arrays
+//   warps 4-11 epilogue     -- tcgen05.ld 32 columns at a time; per-row running max in registers,
+//                              per-column max through a padded 32x32 shared-memory transpose, then
+//                              one 64-bit atomicMax per row / column into the global key arrays
 // The similarity matrix therefore never leaves the SM.
 //
 // Precision modes (include/einx.h): BF16 rounds the descriptors to bf16 (kind::f16); TF32X3 splits
@@ -29,9 +29,11 @@ constexpr int TILE_N = 256;          // rows of d1 per tile  (UMMA N, TMEM colum
 constexpr int KBLOCK_BYTES = 128;    // one swizzle-128B row per k-block
 constexpr int A_BYTES = TILE_M * KBLOCK_BYTES;  // 16 KB
 constexpr int B_BYTES = TILE_N * KBLOCK_BYTES;  // 32 KB
-constexpr int STAGES = 4;
-constexpr int kThreads = 256;
+constexpr int STAGES = 3;
 constexpr int kEpilogueWarp0 = 4;
+constexpr int kEpilogueWarps = 8;   // two warps per TMEM lane quarter, each takes half of the columns
+constexpr int kThreads = 32 * (kEpilogueWarp0 + kEpilogueWarps);
+constexpr int kScratchPitch = 33;   // floats; 32x32 transpose tile per epilogue warp, conflict-free both ways
 constexpr uint32_t kTmemCols = 512;
 
 struct TcParams {
@@ -146,6 +148,7 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
     unsigned char* tiles = (unsigned char*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
     Barriers* bars = reinterpret_cast<Barriers*>(tiles + (size_t)STAGES * (A_BYTES + B_BYTES));
     unsigned long long* colpart = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(bars) + 128);
+    float* scratch_all = reinterpret_cast<float*>(colpart + 4 * TILE_N);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_pair = P.tiles_m * P.tiles_n;
@@ -161,7 +164,7 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], kEpilogueWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -250,8 +253,12 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
         }
     } else if (warp >= kEpilogueWarp0) {
         // ===== epilogue: TMEM -> registers -> row / column best keys =====
-        const int q = warp & 3;               // TMEM lane quarter this warp may access
-        const int ew = warp - kEpilogueWarp0;  // 0..3, slot in the column-merge buffer
+        // Rows: the thread that owns TMEM lane r scans its 128 columns with a strict '>' (lowest
+        // column wins ties).  Columns: the 32x32 chunk goes through a padded shared-memory tile so
+        // that lane c then owns column c and scans the 32 rows the same way (lowest row wins).
+        const int q = warp & 3;                          // TMEM lane quarter this warp may access
+        const int half = (warp - kEpilogueWarp0) >> 2;   // which 128 columns of the tile
+        float* scratch = scratch_all + (size_t)(warp - kEpilogueWarp0) * 32 * kScratchPitch;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -263,54 +270,57 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
             const int M = P.n1 ? min(P.n1[b], P.mcap) : P.mcap;
             const int row = i0 + 32 * q + lane;  // this thread's row of d0
             const bool row_ok = row < N;
+            const int rows_here = min(max(N - (i0 + 32 * q), 0), 32);  // valid rows of this warp's quarter
             const bool full_tile = (i0 + TILE_M <= N) && (j0 + TILE_N <= M);
             mbar_wait(&bars->tmem_full[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)acc * TILE_N;
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * TILE_N + 128 * half);
             float best = -INFINITY;
             int best_j = 0;
-            for (int c = 0; c < TILE_N / 32; ++c) {
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
                 uint32_t v[32];
                 tc_ld32(taddr + 32 * c, v);
-                const int jc = j0 + 32 * c;
-                if (jc >= M) break;  // warp-uniform: the rest of the tile is padding
-                // -- rows: strict '>' keeps the lowest column on ties
+                const int jc = j0 + 128 * half + 32 * c;
+                if (jc < M) {  // warp-uniform; beyond M the tile is padding
 #pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    const float f = __uint_as_float(v[k]);
-                    const bool ok = full_tile || (jc + k < M);
-                    if (ok && f > best) { best = f; best_j = jc + k; }
-                }
-                // -- columns: max over this warp's 32 rows, first row on ties; lane k keeps column k
-                int cmax = 0, crow = 0;
+                    for (int k = 0; k < 32; ++k) {
+                        const float f = __uint_as_float(v[k]);
+                        const bool ok = full_tile || (jc + k < M);
+                        if (ok && f > best) { best = f; best_j = jc + k; }
+                        scratch[lane * kScratchPitch + k] = f;
+                    }
+                    __syncwarp();
+                    // two independent scan chains (rows 0-15, 16-31) keep the compare latency hidden
+                    float c0 = -INFINITY, c1 = -INFINITY;
+                    int r0 = 0, r1 = 16;
 #pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    int key = f32_skey(v[k]);
-                    if (!full_tile && !row_ok) key = INT_MIN;
-                    const int mx = __reduce_max_sync(0xffffffffu, key);
-                    const unsigned eq = __ballot_sync(0xffffffffu, key == mx);
-                    if (lane == k) { cmax = mx; crow = __ffs(eq) - 1; }
+                    for (int r = 0; r < 16; ++r) {
+                        const float x0 = scratch[r * kScratchPitch + lane];
+                        const float x1 = scratch[(r + 16) * kScratchPitch + lane];
+                        if ((full_tile || r < rows_here) && x0 > c0) { c0 = x0; r0 = r; }
+                        if ((full_tile || r + 16 < rows_here) && x1 > c1) { c1 = x1; r1 = r + 16; }
+                    }
+                    if (c1 > c0) { c0 = c1; r0 = r1; }
+                    const bool col_ok = (jc + lane < M) && (c0 > -INFINITY);
+                    colpart[q * TILE_N + 128 * half + 32 * c + lane] =
+                        col_ok ? (((unsigned long long)f32_orderable(c0 + 0.0f) << 32) |
+                                  (0xffffffffu - (uint32_t)(i0 + 32 * q + r0)))
+                               : 0ull;
+                    __syncwarp();  // the tile is rewritten by the next chunk
                 }
-                // rows beyond N can only win a column when the whole 32-row group is padding
-                const bool col_ok = (jc + lane < M) && (i0 + 32 * q + crow < N);
-                const uint32_t ob = (uint32_t)cmax ^ 0x80000000u;  // signed key -> unsigned orderable
-                colpart[ew * TILE_N + 32 * c + lane] =
-                    col_ok ? (((unsigned long long)ob << 32) | (0xffffffffu - (uint32_t)(i0 + 32 * q + crow))) : 0ull;
             }
-            // TMEM accumulator fully read: hand it back to the MMA warp
+            // TMEM accumulator fully read by this warp: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
-            if (row_ok && best > -INFINITY) {
-                const uint32_t ob = f32_orderable(best);
-                atomicMax(P.rowkey + (size_t)b * P.ncap + row, ((unsigned long long)ob << 32) | (0xffffffffu - (uint32_t)best_j));
-            }
-            // merge the 4 warps' column keys (128 epilogue threads only: named barrier 1)
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            const int et = threadIdx.x - kEpilogueWarp0 * 32;
-#pragma unroll
-            for (int h = 0; h < TILE_N / 128; ++h) {
-                const int cidx = et + 128 * h;
+            if (row_ok && best > -INFINITY)
+                atomicMax(P.rowkey + (size_t)b * P.ncap + row,
+                          ((unsigned long long)f32_orderable(best + 0.0f) << 32) | (0xffffffffu - (uint32_t)best_j));
+            // merge the 4 lane quarters' column keys: 256 epilogue threads, one column each
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            {
+                const int cidx = threadIdx.x - kEpilogueWarp0 * 32;
                 const int j = j0 + cidx;
                 if (j < M) {
                     unsigned long long m = colpart[cidx];
@@ -319,7 +329,7 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
                     if (m) atomicMax(P.colkey + (size_t)b * P.mcap + j, m);
                 }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // colpart is reused by the next tile
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // colpart is reused by the next tile
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
@@ -451,7 +461,8 @@ int einx_mnn_tc(einx_ctx* ctx, const float* d0, const float* d1, const int32_t* 
         P.passes = 3;
         P.idesc = make_idesc(1);
     }
-    const size_t smem = 1024 + (size_t)STAGES * (A_BYTES + B_BYTES) + 128 + 4 * TILE_N * sizeof(unsigned long long);
+    const size_t smem = 1024 + (size_t)STAGES * (A_BYTES + B_BYTES) + 128 + 4 * TILE_N * sizeof(unsigned long long) +
+                        (size_t)kEpilogueWarps * 32 * kScratchPitch * sizeof(float);
     const int total_tiles = B * P.tiles_m * P.tiles_n;
     int grid = ctx->num_sms < total_tiles ? ctx->num_sms : total_tiles;
     if (grid < 1) grid = 1;

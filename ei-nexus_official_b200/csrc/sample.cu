@@ -73,16 +73,163 @@ sample_kernel(const float* __restrict__ raw, int C, int Hd, int Wd, float Hp, fl
     }
 #pragma unroll
     for (int j = 0; j < kMaxPerLane; ++j) ss = fmaf(v[j], v[j], ss);
-    float mul = scale, den = 1.0f;
+    float mul = scale;
     if (normalize) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        den = fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps
+        mul = __fdiv_rn(scale, fmaxf(sqrtf(ss), 1e-12f));  // scale / max(||v||, eps): one division per keypoint
     }
 #pragma unroll
     for (int j = 0; j < kMaxPerLane; ++j) {
         const int c = lane + 32 * j;
-        if (c < C) out[c] = __fmul_rn(mul, normalize ? __fdiv_rn(v[j], den) : v[j]);
+        if (c < C) out[c] = v[j] * mul;
+    }
+}
+
+
+// ---- bilinear mode, coarse map staged in shared memory --------------------------------------- //
+// The generic kernel above reads one 32-byte sector per 4-byte tap (channel stride = Hd*Wd floats).
+// For SuperPoint-type maps (C=256, 23x30 cells) the two coarse rows a keypoint touches are only
+// C * 2 * Wd floats, so one CTA per (image, coarse row pair) stages them with coalesced loads and
+// serves every keypoint whose upper tap row is that pair's first row: the descriptor map is read
+// about twice from L2/HBM instead of ~8x in sectors, and every tap becomes a conflict-free LDS.
+constexpr int kSlabThreads = 256;
+constexpr int kSlabWarps = kSlabThreads / 32;
+
+struct Tap {  // one keypoint's bilinear footprint, computed once and shared by the 32 channel lanes
+    int k, xa, xb;
+    float w00, w01, w10, w11;
+};
+
+__device__ __forceinline__ float bilinear_unnormalize(float p, float size_padded, int size_in) {
+    // pos - 0.5 -> [-1, 1] on the padded image -> grid_sample index ((g + 1) * size_in - 1) / 2
+    const float g = __fsub_rn(__fmul_rn(2.0f, __fdiv_rn(__fsub_rn(p, 0.5f), __fsub_rn(size_padded, 1.0f))), 1.0f);
+    return __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.0f), (float)size_in), 1.0f), 2.0f);
+}
+
+template <int NJ>  // channel groups of 32 held per lane: C == 32 * NJ exactly, or NJ == kMaxPerLane with guards
+__global__ void __launch_bounds__(kSlabThreads, 2)
+sample_bilinear_slab_kernel(const float* __restrict__ raw, int C, int Hd, int Wd, float Hp, float Wp,
+                            const float* __restrict__ kpts, const int32_t* __restrict__ counts, int kcap, float scale,
+                            int normalize, float* __restrict__ desc, int SP) {
+    extern __shared__ __align__(16) float slab[];  // [C][SP]: rows y0, y0+1 of every channel
+    __shared__ Tap taps[kSlabThreads];
+    __shared__ int s_first[kSlabWarps], s_last[kSlabWarps];
+    const int b = blockIdx.y;
+    const int y0 = (int)blockIdx.x - 1;  // upper tap row of this CTA's keypoints, -1 .. Hd-1
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int cnt = counts[b];
+    if (cnt > kcap) cnt = kcap;
+    if (blockIdx.x == 0) {  // padding rows are defined (zero)
+        float* z = desc + ((size_t)b * kcap + cnt) * C;
+        for (size_t i = tid; i < (size_t)(kcap - cnt) * C; i += kSlabThreads) z[i] = 0.0f;
+    }
+    const float* kp = kpts + (size_t)b * kcap * 3;
+    // keypoints are in raster order, so this CTA's keypoints form one contiguous run [first, last]
+    int first = cnt, last = -1;
+    for (int k = tid; k < cnt; k += kSlabThreads) {
+        const float iy = bilinear_unnormalize(kp[3 * k], Hp, Hd);
+        if ((int)floorf(iy) == y0) { first = min(first, k); last = max(last, k); }
+    }
+    first = __reduce_min_sync(0xffffffffu, first);
+    last = __reduce_max_sync(0xffffffffu, last);
+    if (lane == 0) { s_first[warp] = first; s_last[warp] = last; }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < kSlabWarps; ++w) { first = min(first, s_first[w]); last = max(last, s_last[w]); }
+    if (last < first) return;
+
+    // stage rows y0, y0+1 of every channel: one warp per channel, lanes along the 2*Wd floats
+    const float* img = raw + (size_t)b * C * Hd * Wd;
+    const int row_elems = 2 * Wd;
+    const bool oy0 = (y0 >= 0) & (y0 < Hd), oy1 = (y0 + 1 >= 0) & (y0 + 1 < Hd);
+    // (cp.async: every element is in flight at once, no register staging -- the loop would
+    // otherwise expose one L2/HBM round trip per channel).  Per-lane element offsets and their
+    // validity are hoisted: row_elems <= 128, so a lane owns at most 4 elements of a channel.
+    {
+        int roff[4];
+        bool rok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            roff[u] = lane + 32 * u;
+            rok[u] = roff[u] < row_elems && (roff[u] < Wd ? oy0 : oy1);
+            if (roff[u] < row_elems && !rok[u])  // out-of-map row: zero once per channel below
+                rok[u] = false;
+        }
+        const bool zero_any = !(oy0 && oy1);
+        const float* src = img + ((ptrdiff_t)warp * Hd + y0) * Wd;  // rows y0 and y0+1 are adjacent in memory
+        const size_t cstep = (size_t)kSlabWarps * Hd * Wd;
+        uint32_t dst = (uint32_t)__cvta_generic_to_shared(slab + warp * SP);
+        const uint32_t dstep = (uint32_t)(kSlabWarps * SP * sizeof(float));
+        for (int c = warp; c < C; c += kSlabWarps, src += cstep, dst += dstep) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (rok[u])
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * roff[u]), "l"(src + roff[u]) : "memory");
+                else if (zero_any && roff[u] < row_elems)
+                    slab[c * SP + roff[u]] = 0.0f;
+            }
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+
+    for (int base = first; base <= last; base += kSlabThreads) {
+        __syncthreads();  // slab staged (first pass) / taps consumed (later passes)
+        const int k = base + tid;
+        if (k <= last) {
+            const float iy = bilinear_unnormalize(kp[3 * k], Hp, Hd);
+            const float ix = bilinear_unnormalize(kp[3 * k + 1], Wp, Wd);
+            const float fy = floorf(iy), fx = floorf(ix);
+            const int x0 = (int)fx;
+            const float wy1 = __fsub_rn(iy, fy), wx1 = __fsub_rn(ix, fx);
+            const float wy0 = __fsub_rn(__fadd_rn(fy, 1.0f), iy), wx0 = __fsub_rn(__fadd_rn(fx, 1.0f), ix);
+            const bool ox0 = (x0 >= 0) & (x0 < Wd), ox1 = (x0 + 1 >= 0) & (x0 + 1 < Wd);
+            Tap t;
+            t.k = ((int)fy == y0) ? k : -1;
+            t.xa = ox0 ? x0 : 0;
+            t.xb = ox1 ? x0 + 1 : 0;
+            // out-of-map taps get weight 0 (grid_sample zeros padding); out-of-map rows are zero in the slab
+            t.w00 = ox0 ? __fmul_rn(wx0, wy0) : 0.0f;
+            t.w01 = ox1 ? __fmul_rn(wx1, wy0) : 0.0f;
+            t.w10 = ox0 ? __fmul_rn(wx0, wy1) : 0.0f;
+            t.w11 = ox1 ? __fmul_rn(wx1, wy1) : 0.0f;
+            taps[tid] = t;
+        }
+        __syncthreads();
+        const int n = min(kSlabThreads, last - base + 1);
+        for (int e = warp; e < n; e += kSlabWarps) {
+            const Tap t = taps[e];
+            if (t.k < 0) continue;
+            float v[NJ];
+            float ss = 0.0f;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int c = lane + 32 * j;
+                float acc = 0.0f;
+                if (NJ != kMaxPerLane || c < C) {
+                    const float* s = slab + c * SP;  // odd pitch: the 32 channel lanes hit 32 banks
+                    acc = __fmul_rn(s[t.xa], t.w00);
+                    acc = fmaf(s[t.xb], t.w01, acc);
+                    acc = fmaf(s[Wd + t.xa], t.w10, acc);
+                    acc = fmaf(s[Wd + t.xb], t.w11, acc);
+                }
+                v[j] = acc;
+                ss = fmaf(acc, acc, ss);
+            }
+            float mul = scale;
+            if (normalize) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                mul = __fdiv_rn(scale, fmaxf(sqrtf(ss), 1e-12f));
+            }
+            float* out = desc + ((size_t)b * kcap + t.k) * C;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int c = lane + 32 * j;
+                if (NJ != kMaxPerLane || c < C) out[c] = v[j] * mul;
+            }
+        }
     }
 }
 
@@ -106,6 +253,28 @@ extern "C" int einx_sample(einx_ctx* ctx, const float* raw, int B, int C, int Hd
             raw, C, Hd, Wd, (float)Hp, (float)Wp, kpts, counts, kcap, scale, normalize, desc);
     } else if (mode == EINX_SAMPLE_BILINEAR) {
         if (Hp <= 1 || Wp <= 1) return einx_fail(ctx, EINX_ERR_INVALID, "einx_sample: bilinear needs Hp, Wp > 1");
+        // shared-memory slab variant when two coarse rows of every channel fit (odd pitch: lanes are
+        // channels, so an odd channel pitch makes every tap conflict-free)
+        const int SP = (2 * Wd) | 1;
+        const size_t slab_bytes = (size_t)C * SP * sizeof(float);
+        if (slab_bytes <= 100 * 1024 && Hd + 1 <= 65535 && 2 * Wd <= 128) {
+            auto launch = [&](auto kern) -> cudaError_t {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slab_bytes);
+                if (e != cudaSuccess) return e;
+                kern<<<dim3(Hd + 1, B), kSlabThreads, slab_bytes, stream>>>(raw, C, Hd, Wd, (float)Hp, (float)Wp, kpts,
+                                                                          counts, kcap, scale, normalize, desc, SP);
+                return cudaSuccess;
+            };
+            switch (C) {
+                case 32: EINX_CUDA(ctx, launch(sample_bilinear_slab_kernel<1>)); break;
+                case 64: EINX_CUDA(ctx, launch(sample_bilinear_slab_kernel<2>)); break;
+                case 128: EINX_CUDA(ctx, launch(sample_bilinear_slab_kernel<4>)); break;
+                case 256: EINX_CUDA(ctx, launch(sample_bilinear_slab_kernel<8>)); break;
+                default: EINX_CUDA(ctx, launch(sample_bilinear_slab_kernel<kMaxPerLane>)); break;
+            }
+            EINX_CHECK_LAUNCH(ctx);
+            return EINX_OK;
+        }
         sample_kernel<EINX_SAMPLE_BILINEAR><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
             raw, C, Hd, Wd, (float)Hp, (float)Wp, kpts, counts, kcap, scale, normalize, desc);
     } else {
