@@ -83,8 +83,9 @@ def _cpu_pair(args):
     return int((m["matches0"] > -1).sum())
 
 
-def cpu_pairs_per_sec(synth, cfg_name, pairs, repeats=1, workers=None):
-    """Run the oracle pipeline on `pairs` pairs spread over all host cores; returns (pairs/s, cores, secs)."""
+def cpu_pairs_per_sec(synth, cfg_name, pairs, budget_s=12.0, workers=None):
+    """Run the oracle pipeline over all host cores for about `budget_s` seconds of wall time (a bounded
+    sample: the same `pairs` inputs are re-run); returns (pairs/s, cores, secs, pairs_done)."""
     import multiprocessing as mp
 
     cfg = synth.CONFIGS[cfg_name]
@@ -93,15 +94,15 @@ def cpu_pairs_per_sec(synth, cfg_name, pairs, repeats=1, workers=None):
     evs, s0, r0, s1, r1 = make_batch(synth, cfg_name, pairs, 0)
     jobs = [(cfg, evs[i], s0[i:i + 1], r0[i:i + 1], s1[i:i + 1], r1[i:i + 1]) for i in range(pairs)]
     ctx = mp.get_context("fork")
-    best = None
+    done, total = 0, 0.0
     with ctx.Pool(cores) as pool:
         pool.map(_cpu_pair, jobs[:cores])  # warm the workers (imports, page faults)
-        for _ in range(repeats):
+        while total < budget_s:
             t0 = time.perf_counter()
             pool.map(_cpu_pair, jobs, chunksize=1)
-            dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
-    return pairs / best, cores, best
+            total += time.perf_counter() - t0
+            done += pairs
+    return done / total, cores, total, done
 
 
 def run_reference(args, synth):
@@ -152,6 +153,16 @@ def workload_config(args, synth):
     }
 
 
+def load_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the profiled kernels, copied from
+    the ncu --set full capture summarised in profiles/ (null when a kernel has not been captured)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
+
+
 # --------------------------------------------------------------------------------------------- #
 # clocks
 # --------------------------------------------------------------------------------------------- #
@@ -185,7 +196,7 @@ class ClockSampler(threading.Thread):
                 self.samples.append((time.perf_counter(), sm, reasons))
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.004)
 
     def summary(self):
         if self.nv is None or not self.samples:
@@ -334,10 +345,15 @@ def run_einx(args, synth):
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    # ---- per-stage CUDA-event timing (same resident inputs, same rotation) for the roofline ----
+    # ---- per-stage and per-kernel CUDA-event timing (same resident inputs, same rotation) ----
+    # stage: torch events around each stage of the step; kernel: the C ABI's own events around the
+    # dominant kernel of each entry point (einx_profile_enable / einx_profile_read), recorded on the
+    # stream the kernels are launched on.
     stage_ms = {"voxel": 0.0, "detect": 0.0, "sample": 0.0, "mnn": 0.0}
+    kern_ms = {"voxel_scatter": 0.0, "detect": 0.0, "sample": 0.0, "mnn_similarity": 0.0}
     det, desc, mt = (importlib.import_module(f"ei-nexus_official_b200.{m}") for m in ("detection", "describe", "match"))
     nprof = max(3, min(args.steps, 20))
+    ctx.profile(True)
     for i in range(3 + nprof):
         ev, (s0, r0, s1, r1) = dev_sets[i % NUM_INPUT_SETS]
         evts = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
@@ -346,18 +362,26 @@ def run_einx(args, synth):
         evts[0].record()
         pipe.voxelize(*ev)
         evts[1].record()
-        _, kp0, cn0 = det.detect(s0, cfg.detection_threshold, cfg.nms_radius, cfg.remove_borders, cfg.top_k)
-        _, kp1, cn1 = det.detect(s1, cfg.detection_threshold, cfg.nms_radius, cfg.remove_borders, cfg.top_k)
+        _, kp0, cn0 = det.detect(s0, cfg.detection_threshold, cfg.nms_radius, cfg.remove_borders, cfg.top_k, kcap=cfg.top_k)
+        k_det0 = ctx.profile_read()[1]
+        _, kp1, cn1 = det.detect(s1, cfg.detection_threshold, cfg.nms_radius, cfg.remove_borders, cfg.top_k, kcap=cfg.top_k)
         evts[2].record()
         d0 = desc.sample(r0, kp0, cn0, mode, (Hp, Wp), cfg.descriptor_scale, True)
+        k_smp0 = ctx.profile_read()[2]
         d1 = desc.sample(r1, kp1, cn1, mode, (Hp, Wp), cfg.descriptor_scale, True)
         evts[3].record()
         mt.mnn(d0, d1, cn0, cn1, kp0, kp1, None, None, True, cfg.precision)
         evts[4].record()
         torch.cuda.synchronize(dev)
+        k = ctx.profile_read()
         if i >= 3:
-            for j, k in enumerate(stage_ms):
-                stage_ms[k] += evts[j].elapsed_time(evts[j + 1]) / nprof
+            for j, name in enumerate(stage_ms):
+                stage_ms[name] += evts[j].elapsed_time(evts[j + 1]) / nprof
+            kern_ms["voxel_scatter"] += k[0] / nprof
+            kern_ms["detect"] += (k_det0 + k[1]) / nprof      # two launches (both sides) per step
+            kern_ms["sample"] += (k_smp0 + k[2]) / nprof
+            kern_ms["mnn_similarity"] += k[3] / nprof
+    ctx.profile(False)
 
     # one NCCL gather of the packed matches, outside the hot path (SURVEY.md section 8 e)
     gather_ms = None
@@ -379,26 +403,38 @@ def run_einx(args, synth):
         value = pairs / (ms * 1e-3)
         e2e_value = pairs / (ms_e2e * 1e-3)
         sb = stage_bytes(c, synth, B)
+        traffic = load_traffic()
         stages = {}
         for k, t in stage_ms.items():
             gbs = sb[k] / (t * 1e-3) / 1e9 if t > 0 else 0.0
             stages[k] = {"ms": round(t, 4), "algorithmic_GBps": round(gbs, 1), "frac_hbm": round(gbs / peaks["hbm_gbs"], 4)}
-        tfs = sb["mnn_flops"] / (stage_ms["mnn"] * 1e-3) / 1e12 if stage_ms["mnn"] > 0 else 0.0
         tensor_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-        stages["mnn"].update({"TFLOPs": round(tfs, 2), "frac_tensor": round(tfs / tensor_peak, 4)})
-        dominant = max(stage_ms, key=stage_ms.get)
-        if dominant == "mnn":
-            roof = {"kernel": "mnn similarity tiles + fused argmax", "bound": "tensor", "achieved": tfs,
-                    "peak": tensor_peak, "unit": "TFLOP/s", "frac": tfs / tensor_peak, "traffic": None}
-        else:
-            gbs = stages[dominant]["algorithmic_GBps"]
-            roof = {"kernel": dominant, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": gbs / peaks["hbm_gbs"], "traffic": None}
-        roof["peak_source"] = f"MEASURED_PEAKS.json ({peak_kind})"
+        # per-kernel rooflines: launches per step, algorithmic work per launch, CUDA-event ms per launch
+        launches_per_step = {"voxel_scatter": 1, "detect": 2, "sample": 2, "mnn_similarity": 1}
+        work = {"voxel_scatter": sb["voxel"], "detect": sb["detect"] / 2, "sample": sb["sample"] / 2}
+        kernels = {}
+        for name, tot in kern_ms.items():
+            per = tot / launches_per_step[name]
+            if name == "mnn_similarity":
+                tfs = sb["mnn_flops"] / (per * 1e-3) / 1e12 if per > 0 else 0.0
+                kernels[name] = {"ms_per_launch": round(per, 4), "launches_per_step": 1, "bound": "tensor",
+                                 "achieved": round(tfs, 2), "peak": tensor_peak, "unit": "TFLOP/s",
+                                 "frac": round(tfs / tensor_peak, 4), "traffic": traffic.get(f"{name}_{args.precision}")}
+            else:
+                gbs = work[name] / (per * 1e-3) / 1e9 if per > 0 else 0.0
+                kernels[name] = {"ms_per_launch": round(per, 4), "launches_per_step": launches_per_step[name],
+                                 "bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                 "frac": round(gbs / peaks["hbm_gbs"], 4), "traffic": traffic.get(name)}
+        dominant = max(kern_ms, key=kern_ms.get)  # largest share of the step
+        roof = dict(kernels[dominant])
+        roof["kernel"] = dominant
+        roof["share_of_step"] = round(kern_ms[dominant] / (ms / args.steps), 3)
+        roof["peak_source"] = f"MEASURED_PEAKS.json ({peak_kind}; HBM copy GB/s, cuBLAS bf16 sustained TF/s)"
         log("timing the CPU baseline (oracle port) ...")
         cores = os.cpu_count() or 1
         cpu_pairs = max(cores, min(2 * cores, 64))
-        cpu_val, cpu_cores, cpu_secs = cpu_pairs_per_sec(synth, args.config, cpu_pairs) if world == 1 else (None, None, None)
+        cpu_val, cpu_cores, cpu_secs, cpu_done = (cpu_pairs_per_sec(synth, args.config, cpu_pairs) if world == 1
+                                                  else (None, None, None, None))
         line = {
             "metric": "pairs/sec (voxel+detect+MNN)", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -406,9 +442,10 @@ def run_einx(args, synth):
             "data": "synthetic", "config": workload_config(args, synth),
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "stages": stages,
+            "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "kernels": kernels,
+            "stages": stages,
             "cpu_baseline": ({"value": cpu_val, "unit": "pairs/s", "cores": cpu_cores, "kind": "port",
-                              "sample": f"{cpu_pairs} pairs of the workload in {cpu_secs:.1f}s, one oracle process per core"}
+                              "sample": f"{cpu_done} pairs ({cpu_pairs} distinct) of the workload in {cpu_secs:.1f}s, one oracle process per core"}
                              if cpu_val is not None else None),
             "gather_ms": gather_ms,
         }
@@ -421,12 +458,13 @@ def run_einx(args, synth):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="einx", choices=["einx", "reference"])
     ap.add_argument("--config", default="c2_ec_superpoint")
     ap.add_argument("--batch", type=int, default=None, help="pairs per GPU per step")
-    ap.add_argument("--precision", default=os.environ.get("EINX_MNN_PRECISION", "fp32"), choices=["fp32", "tf32x3", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("EINX_MNN_PRECISION", "tf32x3"), choices=["fp32", "tf32x3", "bf16"],
+                    help="MNN arithmetic: tf32x3 (default; fp32-accurate on the tensor pipe), fp32 (FFMA), bf16")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "einx" else args.warmup
     synth = importlib.import_module("ei-nexus_official_b200.synth")

@@ -19,6 +19,8 @@ SIGNATURES = {
     "einx_destroy": (None, [c_ctx]),
     "einx_last_error": (C.c_char_p, [c_ctx]),
     "einx_launch_count": (C.c_int64, [c_ctx]),
+    "einx_profile_enable": (C.c_int, [c_ctx, C.c_int]),
+    "einx_profile_read": (C.c_int, [c_ctx, C.POINTER(C.c_float)]),
     "einx_voxelize": (C.c_int, [c_ctx, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "einx_detect": (C.c_int, [c_ctx, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                               _P, _P, C.c_int, _P, _P]),
@@ -73,6 +75,16 @@ class Context:
         if rc != 0:
             msg = self.lib.einx_last_error(self.handle)
             raise EinxError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def profile(self, on: bool):
+        """Bracket each entry point's dominant kernel with CUDA events on the caller's stream."""
+        self.check(self.lib.einx_profile_enable(self.handle, int(on)), "einx_profile_enable")
+
+    def profile_read(self):
+        """ms of the last (voxel scatter, detect, sample, MNN similarity) kernel; synchronises."""
+        out = (C.c_float * 4)()
+        self.check(self.lib.einx_profile_read(self.handle, out), "einx_profile_read")
+        return [float(v) for v in out]
 
     @property
     def launches(self) -> int:

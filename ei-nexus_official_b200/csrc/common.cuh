@@ -14,8 +14,16 @@ struct einx_ctx {
     void* ws;             // grow-only device workspace
     size_t ws_bytes;
     int64_t launches;
+    int profile;                    // einx_profile_enable
+    cudaEvent_t prof_ev[4][2];      // [slot][begin/end], created lazily
+    int prof_set[4];
     char err[512];
 };
+
+// Bracket the dominant kernel of an entry point with events on the caller's stream (no-op unless
+// profiling is enabled).
+void einx_prof_begin(einx_ctx* ctx, int slot, cudaStream_t stream);
+void einx_prof_end(einx_ctx* ctx, int slot, cudaStream_t stream);
 
 // Grow the workspace to at least `bytes` (synchronising cudaFree/cudaMalloc only on growth).
 int einx_ws_reserve(einx_ctx* ctx, size_t bytes);

@@ -32,7 +32,38 @@ int einx_ws_reserve(einx_ctx* ctx, size_t bytes) {
     return EINX_OK;
 }
 
+void einx_prof_begin(einx_ctx* ctx, int slot, cudaStream_t stream) {
+    if (!ctx->profile) return;
+    for (int k = 0; k < 2; ++k)
+        if (!ctx->prof_ev[slot][k]) cudaEventCreate(&ctx->prof_ev[slot][k]);
+    cudaEventRecord(ctx->prof_ev[slot][0], stream);
+}
+void einx_prof_end(einx_ctx* ctx, int slot, cudaStream_t stream) {
+    if (!ctx->profile) return;
+    cudaEventRecord(ctx->prof_ev[slot][1], stream);
+    ctx->prof_set[slot] = 1;
+}
+
 extern "C" {
+
+int einx_profile_enable(einx_ctx* ctx, int on) {
+    if (!ctx) return EINX_ERR_INVALID;
+    ctx->profile = on != 0;
+    for (int s = 0; s < EINX_PROFILE_SLOTS; ++s) ctx->prof_set[s] = 0;
+    return EINX_OK;
+}
+
+int einx_profile_read(einx_ctx* ctx, float* ms_out) {
+    if (!ctx || !ms_out) return EINX_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    for (int s = 0; s < EINX_PROFILE_SLOTS; ++s) {
+        ms_out[s] = -1.0f;
+        if (!ctx->prof_set[s]) continue;
+        EINX_CUDA(ctx, cudaEventSynchronize(ctx->prof_ev[s][1]));
+        EINX_CUDA(ctx, cudaEventElapsedTime(&ms_out[s], ctx->prof_ev[s][0], ctx->prof_ev[s][1]));
+    }
+    return EINX_OK;
+}
 
 int einx_version(void) { return 100; }
 
@@ -71,6 +102,9 @@ void einx_destroy(einx_ctx* ctx) {
         cudaDeviceSynchronize();
         cudaFree(ctx->ws);
     }
+    for (int s = 0; s < EINX_PROFILE_SLOTS; ++s)
+        for (int k = 0; k < 2; ++k)
+            if (ctx->prof_ev[s][k]) cudaEventDestroy(ctx->prof_ev[s][k]);
     free(ctx);
 }
 

@@ -24,6 +24,7 @@ constexpr int kThreads = 1024;
 constexpr int kWarps = kThreads / 32;
 constexpr int kSegRows = 24;  // rows per (strip, segment) work item of the fused row/column pass
 constexpr int kMaxCluster = 8;
+constexpr int kWorklistCap = 4096;  // late NMS rounds visit only the still-undecided pixels (per CTA)
 
 struct DetectParams {
     float* score;
@@ -42,6 +43,7 @@ struct DetectParams {
     int scap;  // survivor list capacity per image
     float* surv_val;
     int32_t* surv_idx;
+    unsigned int* worklists;  // [B * CS][2][kWorklistCap] entries (local row << 16 | x), L2-resident
     // global-memory variant (maps too large for a cluster's shared memory)
     float* gV;
     uint32_t* gLM;
@@ -55,6 +57,7 @@ struct Shared {
     unsigned int hist[256];
     unsigned int sel_prefix, sel_rank, sel_min, sel_cnt;
     float thr;
+    int wl_n[2];  // undecided pixels found by the last suppression pass (list valid while <= kWorklistCap)
 };
 
 __device__ __forceinline__ int block_excl_scan(int v, int* scratch, int& total) {
@@ -99,16 +102,31 @@ __device__ void select_two(const float* __restrict__ list, int n, int j, bool ne
             if ((e & mask) == prefix) atomicAdd(&sh.hist[(e >> shift) & 255u], 1u);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned r = sh.sel_rank, cum = 0;
-            int bin = 0;
-            for (; bin < 256; ++bin) {
-                const unsigned c = sh.hist[bin];
-                if (cum + c > r) break;
-                cum += c;
+        if (threadIdx.x < 32) {
+            // warp 0 locates the bin holding rank r: 8 bins per lane, warp prefix, then a short scan
+            const unsigned r = sh.sel_rank;
+            unsigned c[8], mine = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { c[k] = sh.hist[threadIdx.x * 8 + k]; mine += c[k]; }
+            unsigned inc = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned n = __shfl_up_sync(0xffffffffu, inc, o);
+                if ((int)threadIdx.x >= o) inc += n;
             }
-            sh.sel_rank = r - cum;
-            sh.sel_prefix = prefix | ((unsigned)bin << shift);
+            const unsigned before = inc - mine;
+            const bool here = (before <= r) && (r < inc);  // exactly one lane (r < total count)
+            if (here) {
+                unsigned cum = before;
+                int bin = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (cum + c[k] <= r) { cum += c[k]; bin = k + 1; }
+                    else break;
+                }
+                sh.sel_rank = r - cum;
+                sh.sel_prefix = prefix | ((unsigned)(threadIdx.x * 8 + bin) << shift);
+            }
         }
         mask |= 255u << shift;
         __syncthreads();
@@ -210,6 +228,11 @@ __global__ void __launch_bounds__(kThreads, 1) detect_kernel(const DetectParams 
 
     // ---- NMS rounds ------------------------------------------------------------------------ //
     if constexpr (R > 0) {
+        constexpr int P2 = 2 * R + 1;
+        unsigned int* const wl0 = P.worklists + (size_t)blockIdx.x * 2 * kWorklistCap;
+        int wl_cur = 0;         // list buffer holding the current undecided set
+        bool wl_mode = false;   // CTA-uniform: this round runs on the worklist instead of full passes
+        if (tid == 0) sh.wl_n[0] = sh.wl_n[1] = 0;
         for (int round = 0;; ++round) {
             cluster.sync();  // S1: every band's V (and the previous round's flag) is final
             if (round > 0) {
@@ -229,50 +252,79 @@ __global__ void __launch_bounds__(kThreads, 1) detect_kernel(const DetectParams 
                 }
                 __syncthreads();
             }
-            // fused row/column window pass: one warp walks a 32-column strip down a row segment,
-            // keeping the last 2R+1 full-width row maxima in registers
-            for (int item = warp; item < nitems; item += kWarps) {
-                if (!item_active[item]) continue;
-                const int s = item % S, g = item / S;
-                const int r0 = g * kSegRows;
-                const int r1 = min(r0 + kSegRows, nrows);
-                if (r0 >= r1) continue;
-                const int lc = 32 * s + lane + R;
-                float F[2 * R + 1], C[R + 1];
+            if (!wl_mode) {
+                // fused row/column window pass: one warp walks a 32-column strip down a row segment.
+                // The last 2R+1 full-width row maxima (F) and centre values (C) live in registers as
+                // a ring addressed with compile-time slots (the row loop is unrolled by 2R+1).
+                for (int item = warp; item < nitems; item += kWarps) {
+                    if (!item_active[item]) continue;
+                    const int s = item % S, g = item / S;
+                    const int r0 = g * kSegRows;
+                    const int r1 = min(r0 + kSegRows, nrows);
+                    if (r0 >= r1) continue;
+                    const int lc = 32 * s + lane + R;
+                    float F[P2], C[P2];
 #pragma unroll
-                for (int k = 0; k < 2 * R + 1; ++k) F[k] = 0.0f;
+                    for (int k = 0; k < P2; ++k) { F[k] = 0.0f; C[k] = 0.0f; }
+                    const int nsteps = (r1 - r0) + 2 * R;
+                    for (int base = 0; base < nsteps; base += P2) {
 #pragma unroll
-                for (int k = 0; k < R + 1; ++k) C[k] = 0.0f;
-                const int nsteps = (r1 - r0) + 2 * R;
-                for (int i = 0; i < nsteps; ++i) {
-                    const float* row = V + (size_t)(r0 + i) * WS + lc;
-                    float f = row[0];
-                    const float centre = f;
+                        for (int u = 0; u < P2; ++u) {
+                            const int i = base + u;
+                            if (i < nsteps) {
+                                const float* row = V + (size_t)(r0 + i) * WS + lc;
+                                float f = row[0];
+                                C[u] = f;
 #pragma unroll
-                    for (int d = 1; d <= R; ++d) f = fmaxf(f, fmaxf(row[-d], row[d]));
+                                for (int d = 1; d <= R; ++d) f = fmaxf(f, fmaxf(row[-d], row[d]));
+                                F[u] = f;
+                                if (i >= 2 * R) {
+                                    const int c = r0 + i - 2 * R;        // own row being decided
+                                    const float vc = C[(u + R + 1) % P2];  // row i-R
+                                    float above = F[(u + 1) % P2], below = F[(u + R + 2) % P2];
 #pragma unroll
-                    for (int k = 0; k < 2 * R; ++k) F[k] = F[k + 1];
-                    F[2 * R] = f;
+                                    for (int k = 1; k < R; ++k) {
+                                        above = fmaxf(above, F[(u + 1 + k) % P2]);
+                                        below = fmaxf(below, F[(u + R + 2 + k) % P2]);
+                                    }
+                                    const float m = fmaxf(fmaxf(above, below), F[(u + R + 1) % P2]);
+                                    bool lm = (vc > 0.0f) && (vc == m) && (above < vc);
+                                    if (lm) {  // an equal value to the left in the same row wins the argmax
+                                        const float* crow = V + (size_t)(c + R) * WS + lc;
+                                        float left = crow[-1];
 #pragma unroll
-                    for (int k = 0; k < R; ++k) C[k] = C[k + 1];
-                    C[R] = centre;
-                    if (i >= 2 * R) {
-                        const int c = r0 + i - 2 * R;  // own row being decided
-                        const float vc = C[0];
-                        float above = F[0], below = F[R + 1];
-#pragma unroll
-                        for (int k = 1; k < R; ++k) { above = fmaxf(above, F[k]); below = fmaxf(below, F[R + 1 + k]); }
-                        const float m = fmaxf(fmaxf(above, below), F[R]);
-                        bool lm = (vc > 0.0f) && (vc == m) && (above < vc);
-                        if (lm) {  // an equal value to the left in the same row wins the argmax
-                            const float* crow = V + (size_t)(c + R) * WS + lc;
-                            float left = crow[-1];
-#pragma unroll
-                            for (int d = 2; d <= R; ++d) left = fmaxf(left, crow[-d]);
-                            lm = left < vc;
+                                        for (int d = 2; d <= R; ++d) left = fmaxf(left, crow[-d]);
+                                        lm = left < vc;
+                                    }
+                                    const unsigned bits = __ballot_sync(0xffffffffu, lm);
+                                    if (lane == 0) LM[(size_t)(c + R) * S + s] = bits;
+                                }
+                            }
                         }
-                        const unsigned bits = __ballot_sync(0xffffffffu, lm);
-                        if (lane == 0) LM[(size_t)(c + R) * S + s] = bits;
+                    }
+                }
+            } else {
+                // worklist round, phase 1: each undecided pixel scans its own window
+                const int n = sh.wl_n[wl_cur];
+                for (int e = tid; e < n; e += kThreads) {
+                    const unsigned ent = wl0[wl_cur * kWorklistCap + e];
+                    const int lr = (int)(ent >> 16), x = (int)(ent & 0xffffu);
+                    const float* crow = V + (size_t)(lr + R) * WS + x + R;
+                    const float vc = crow[0];
+                    float emax = 0.0f, lmax = 0.0f;  // raster-earlier / raster-later halves of the window
+#pragma unroll
+                    for (int dy = 1; dy <= R; ++dy) {
+#pragma unroll
+                        for (int dx = -R; dx <= R; ++dx) {
+                            emax = fmaxf(emax, crow[-dy * WS + dx]);
+                            lmax = fmaxf(lmax, crow[dy * WS + dx]);
+                        }
+                    }
+#pragma unroll
+                    for (int d = 1; d <= R; ++d) { emax = fmaxf(emax, crow[-d]); lmax = fmaxf(lmax, crow[d]); }
+                    if (vc > emax && vc >= lmax) {
+                        atomicOr(&LM[(size_t)(lr + R) * S + (x >> 5)], 1u << (x & 31));
+                        wl0[wl_cur * kWorklistCap + e] = ent | 0x80000000u;  // decided: a local maximum (rows < 32768)
                     }
                 }
             }
@@ -288,71 +340,109 @@ __global__ void __launch_bounds__(kThreads, 1) detect_kernel(const DetectParams 
                     uint32_t* dst = LM + (size_t)(R + nrows) * S;
                     for (int i = tid; i < R * S; i += kThreads) dst[i] = src[i];
                 }
-                __syncthreads();
             }
-            // horizontal dilation of the maxima bits, on words.  In the global variant each CTA
-            // also covers its halo rows (cheap) so no third barrier is needed.
-            for (int i = tid; i < (nrows + 2 * R) * S; i += kThreads) {
-                const int row = i / S, s = i - row * S;
-                const int yy = ys - R + row;
-                uint32_t acc = 0;
-                if (yy >= 0 && yy < Hp) {
-                    const uint32_t w = LM[i];
-                    const uint32_t wl = s > 0 ? LM[i - 1] : 0u;
-                    const uint32_t wr = s < S - 1 ? LM[i + 1] : 0u;
-                    acc = w;
-#pragma unroll
-                    for (int d = 1; d <= R; ++d)
-                        acc |= (w >> d) | (wr << (32 - d)) | (w << d) | (wl >> (32 - d));
-                }
-                if (SMEM) RD[i] = acc;
-                else if (row >= R && row < R + nrows) RD[i] = acc;  // own rows only are stored ...
-                // ... halo rows of the global variant are recomputed by the consumer below
-            }
+            const int wl_next = wl_cur ^ 1;
+            if (tid == 0) sh.wl_n[wl_next] = 0;
             __syncthreads();
-            // suppression + undecided census
             int und = 0;
-            for (int wi = warp; wi < nrows * S; wi += kWarps) {
-                const int lr = wi / S, s = wi - lr * S;
-                uint32_t part = 0;
-                if (lane <= 2 * R) {
-                    const int row = lr + lane;  // local rows lr .. lr+2R  (centre lr+R)
-                    if (SMEM || (row >= R && row < R + nrows)) {
-                        part = RD[(size_t)row * S + s];
-                    } else {
-                        const int yy = ys - R + row;
-                        if (yy >= 0 && yy < Hp) {
-                            const size_t i = (size_t)row * S + s;
-                            const uint32_t w = LM[i];
-                            const uint32_t wl = s > 0 ? LM[i - 1] : 0u;
-                            const uint32_t wr = s < S - 1 ? LM[i + 1] : 0u;
-                            part = w;
+            if (!wl_mode) {
+                // horizontal dilation of the maxima bits, on words.  In the global variant only own
+                // rows are stored; halo rows are recomputed by the consumer below.
+                for (int i = tid; i < (nrows + 2 * R) * S; i += kThreads) {
+                    const int row = i / S, s = i - row * S;
+                    const int yy = ys - R + row;
+                    uint32_t acc = 0;
+                    if (yy >= 0 && yy < Hp) {
+                        const uint32_t w = LM[i];
+                        const uint32_t wl = s > 0 ? LM[i - 1] : 0u;
+                        const uint32_t wr = s < S - 1 ? LM[i + 1] : 0u;
+                        acc = w;
 #pragma unroll
-                            for (int d = 1; d <= R; ++d)
-                                part |= (w >> d) | (wr << (32 - d)) | (w << d) | (wl >> (32 - d));
+                        for (int d = 1; d <= R; ++d) acc |= (w >> d) | (wr << (32 - d)) | (w << d) | (wl >> (32 - d));
+                    }
+                    if (SMEM || (row >= R && row < R + nrows)) RD[i] = acc;
+                }
+                __syncthreads();
+                // suppression + undecided census (the undecided pixels also go to the next worklist)
+                for (int wi = warp, lr = warp / S, s = warp - (warp / S) * S; wi < nrows * S; wi += kWarps) {
+                    if (wi != warp) {  // advance (lr, s) by kWarps words without dividing
+                        s += kWarps;
+                        while (s >= S) { s -= S; ++lr; }
+                    }
+                    uint32_t part = 0;
+                    if (lane <= 2 * R) {
+                        const int row = lr + lane;  // local rows lr .. lr+2R  (centre lr+R)
+                        if (SMEM || (row >= R && row < R + nrows)) {
+                            part = RD[(size_t)row * S + s];
+                        } else {
+                            const int yy = ys - R + row;
+                            if (yy >= 0 && yy < Hp) {
+                                const size_t i = (size_t)row * S + s;
+                                const uint32_t w = LM[i];
+                                const uint32_t wl = s > 0 ? LM[i - 1] : 0u;
+                                const uint32_t wr = s < S - 1 ? LM[i + 1] : 0u;
+                                part = w;
+#pragma unroll
+                                for (int d = 1; d <= R; ++d)
+                                    part |= (w >> d) | (wr << (32 - d)) | (w << d) | (wl >> (32 - d));
+                            }
                         }
                     }
-                }
-                const uint32_t dil = __reduce_or_sync(0xffffffffu, part);
-                const uint32_t lmw = LM[(size_t)(lr + R) * S + s];
-                const uint32_t sup = dil & ~lmw;
-                float* cell = V + (size_t)(lr + R) * WS + 32 * s + lane + R;
-                const float v = *cell;
-                const bool is_sup = (sup >> lane) & 1u;
-                if (is_sup && v != 0.0f) *cell = 0.0f;
-                const bool u = (v > 0.0f) && !is_sup && !((lmw >> lane) & 1u);
-                const unsigned ub = __ballot_sync(0xffffffffu, u);
-                if (lane == 0) {
-                    // a still-undecided pixel keeps its (strip, segment) item alive for the next round
+                    const uint32_t dil = __reduce_or_sync(0xffffffffu, part);
+                    const uint32_t lmw = LM[(size_t)(lr + R) * S + s];
+                    const uint32_t sup = dil & ~lmw;
+                    float* cell = V + (size_t)(lr + R) * WS + 32 * s + lane + R;
+                    const float v = *cell;
+                    const bool is_sup = (sup >> lane) & 1u;
+                    if (is_sup && v != 0.0f) *cell = 0.0f;
+                    const bool u = (v > 0.0f) && !is_sup && !((lmw >> lane) & 1u);
+                    const unsigned ub = __ballot_sync(0xffffffffu, u);
                     if (ub) {
                         und = 1;
-                        item_active[(lr / kSegRows) * S + s] = 2;
+                        int basei = 0;
+                        if (lane == 0) {
+                            // a still-undecided pixel keeps its (strip, segment) item alive
+                            item_active[(lr / kSegRows) * S + s] = 2;
+                            basei = atomicAdd(&sh.wl_n[wl_next], __popc(ub));
+                        }
+                        basei = __shfl_sync(0xffffffffu, basei, 0);
+                        const int pos = basei + __popc(ub & ((1u << lane) - 1u));
+                        if (u && pos < kWorklistCap) wl0[wl_next * kWorklistCap + pos] = ((unsigned)lr << 16) | (unsigned)(32 * s + lane);
+                    }
+                }
+            } else {
+                // worklist round, phase 2: drop pixels that now have a local maximum in their window
+                const int n = sh.wl_n[wl_cur];
+                for (int e = tid; e < n; e += kThreads) {
+                    const unsigned ent = wl0[wl_cur * kWorklistCap + e];
+                    if (ent & 0x80000000u) continue;  // became a local maximum in phase 1
+                    const int lr = (int)(ent >> 16), x = (int)(ent & 0xffffu);
+                    const int xl = x - R;
+                    const int wi = xl >> 5;  // arithmetic: -1 for the left border
+                    const int sh_ = xl - 32 * wi;
+                    uint32_t any = 0;
+#pragma unroll
+                    for (int dy = -R; dy <= R; ++dy) {
+                        const uint32_t* rowp = LM + (size_t)(lr + R + dy) * S;
+                        const uint32_t w0 = (wi >= 0 && wi < S) ? rowp[wi] : 0u;
+                        const uint32_t w1 = (wi + 1 >= 0 && wi + 1 < S) ? rowp[wi + 1] : 0u;
+                        const unsigned long long both = (unsigned long long)w0 | ((unsigned long long)w1 << 32);
+                        any |= (uint32_t)(both >> sh_) & ((1u << P2) - 1u);
+                    }
+                    if (any) {
+                        V[(size_t)(lr + R) * WS + x + R] = 0.0f;
+                    } else {
+                        const int pos = atomicAdd(&sh.wl_n[wl_next], 1);
+                        wl0[wl_next * kWorklistCap + pos] = ent;  // pos < n <= kWorklistCap
+                        und = 1;
                     }
                 }
             }
             und = __syncthreads_or(und);
             // 2 = touched this round, 1 = stale from the previous round
             for (int i = tid; i < nitems; i += kThreads) item_active[i] = item_active[i] == 2 ? 1 : 0;
+            wl_mode = (round >= 1) && (sh.wl_n[wl_next] <= kWorklistCap);
+            wl_cur = wl_next;
             if (tid == 0) sh.flags[round & 1] = und;
             if (!SMEM) __threadfence();
         }
@@ -503,7 +593,10 @@ int launch_detect(einx_ctx* ctx, const DetectParams& P, size_t smem, cudaStream_
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    EINX_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, P));
+    einx_prof_begin(ctx, 1, stream);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, P);
+    einx_prof_end(ctx, 1, stream);
+    EINX_CUDA(ctx, le);
     ctx->launches++;
     return EINX_OK;
 }
@@ -589,7 +682,8 @@ extern "C" int einx_detect(einx_ctx* ctx, float* score, const uint8_t* mask, int
 
     // workspace: survivor lists (+ padded global image for the large-map variant)
     const size_t list_bytes = align_up((size_t)B * P.scap * 4, 256);
-    size_t ws_bytes = 2 * list_bytes;
+    const size_t wl_bytes = align_up((size_t)B * CS * 2 * kWorklistCap * 4, 256);
+    size_t ws_bytes = 2 * list_bytes + wl_bytes;
     const size_t img_rows = (size_t)Hp + 2 * R;
     const size_t gv_bytes = align_up((size_t)B * img_rows * P.WS * 4, 256);
     const size_t gw_bytes = align_up((size_t)B * img_rows * P.S * 4, 256);
@@ -599,14 +693,15 @@ extern "C" int einx_detect(einx_ctx* ctx, float* score, const uint8_t* mask, int
     unsigned char* ws = (unsigned char*)ctx->ws;
     P.surv_val = (float*)ws;
     P.surv_idx = (int32_t*)(ws + list_bytes);
+    P.worklists = (unsigned int*)(ws + 2 * list_bytes);
     size_t smem;
     if (use_smem) {
         smem = smem_for(P.RBmax);
         return dispatch_radius<true>(ctx, R, P, smem, stream);
     }
-    P.gV = (float*)(ws + 2 * list_bytes);
-    P.gLM = (uint32_t*)(ws + 2 * list_bytes + gv_bytes);
-    P.gRD = (uint32_t*)(ws + 2 * list_bytes + gv_bytes + gw_bytes);
+    P.gV = (float*)(ws + 2 * list_bytes + wl_bytes);
+    P.gLM = (uint32_t*)(ws + 2 * list_bytes + wl_bytes + gv_bytes);
+    P.gRD = (uint32_t*)(ws + 2 * list_bytes + wl_bytes + gv_bytes + gw_bytes);
     EINX_CUDA(ctx, cudaMemsetAsync(P.gV, 0, gv_bytes + 2 * gw_bytes, stream));
     const int nseg = (P.RBmax + kSegRows - 1) / kSegRows;
     smem = fixed + align_up((size_t)P.S * nseg, 16);

@@ -338,9 +338,11 @@ extern "C" int einx_mnn(einx_ctx* ctx, const float* d0, const float* d1, const i
     if (ncap > 0 && mcap > 0) {
         dim3 grid((mcap + BN - 1) / BN, (ncap + BM - 1) / BM, B);
         if (precision == EINX_MNN_FP32 || use_ratio) {
+            einx_prof_begin(ctx, 3, stream);
             // the ratio test needs exact second-best values: it always runs on the fp32 path
             mnn_fp32_kernel<0><<<grid, kGemmThreads, 0, stream>>>(d0, d1, n0, n1, ncap, mcap, D, rowkey, colkey,
                                                                   nullptr, nullptr, nullptr);
+            einx_prof_end(ctx, 3, stream);
             EINX_CHECK_LAUNCH(ctx);
             if (use_ratio) {
                 mnn_fp32_kernel<1><<<grid, kGemmThreads, 0, stream>>>(d0, d1, n0, n1, ncap, mcap, D, row2, col2,

@@ -468,11 +468,14 @@ int einx_mnn_tc(einx_ctx* ctx, const float* d0, const float* d1, const int32_t* 
     if (grid < 1) grid = 1;
     if (precision == EINX_MNN_BF16) {
         EINX_CUDA(ctx, cudaFuncSetAttribute(mnn_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        einx_prof_begin(ctx, 3, stream);
         mnn_tc_kernel<0><<<grid, kThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], P);
     } else {
         EINX_CUDA(ctx, cudaFuncSetAttribute(mnn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        einx_prof_begin(ctx, 3, stream);
         mnn_tc_kernel<1><<<grid, kThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], P);
     }
+    einx_prof_end(ctx, 3, stream);
     EINX_CHECK_LAUNCH(ctx);
     (void)scratch_bytes;
     return EINX_OK;

@@ -248,6 +248,11 @@ extern "C" int einx_sample(einx_ctx* ctx, const float* raw, int B, int C, int Hd
     DeviceGuard guard(ctx->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     dim3 grid((kcap + kWarpsPerBlock - 1) / kWarpsPerBlock, B);
+    struct ProfScope {  // brackets whichever sampling kernel runs below
+        einx_ctx* c; cudaStream_t s;
+        ProfScope(einx_ctx* c_, cudaStream_t s_) : c(c_), s(s_) { einx_prof_begin(c, 2, s); }
+        ~ProfScope() { einx_prof_end(c, 2, s); }
+    } prof_scope(ctx, stream);
     if (mode == EINX_SAMPLE_GATHER) {
         sample_kernel<EINX_SAMPLE_GATHER><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
             raw, C, Hd, Wd, (float)Hp, (float)Wp, kpts, counts, kcap, scale, normalize, desc);

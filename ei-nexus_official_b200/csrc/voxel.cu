@@ -216,7 +216,9 @@ extern "C" int einx_voxelize(einx_ctx* ctx, const float* x, const float* y, cons
     int per_window = (ctx->num_sms * 8 + B - 1) / B;
     if (per_window < 1) per_window = 1;
     if (per_window > 1024) per_window = 1024;
+    einx_prof_begin(ctx, 0, stream);
     voxel_scatter_kernel<<<dim3(per_window, B), kScatterThreads, 0, stream>>>(x, y, t, p, ev_offsets, bins, H, W, out);
+    einx_prof_end(ctx, 0, stream);
     EINX_CHECK_LAUNCH(ctx);
     if (normalize) {
         int rc = einx_ws_reserve(ctx, sizeof(double) * 3 * B);

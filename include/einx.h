@@ -128,6 +128,17 @@ int einx_mnn_dense(einx_ctx* ctx, const float* d0, const float* d1, int B, int N
 /* Number of kernel launches issued through `ctx` so far (bench.py's gpu_launches). */
 int64_t einx_launch_count(const einx_ctx* ctx);
 
+/*
+ * Measurement hook.  With profiling on, every entry point brackets its dominant kernel with CUDA
+ * events recorded on the caller's stream (slot 0: voxel scatter, 1: detect, 2: sample, 3: MNN
+ * similarity tiles).  einx_profile_read() waits for those events and returns the elapsed
+ * milliseconds of the most recent launch per slot (-1 if none); it is the only call in this
+ * header that synchronises with the host.
+ */
+#define EINX_PROFILE_SLOTS 4
+int einx_profile_enable(einx_ctx* ctx, int on);
+int einx_profile_read(einx_ctx* ctx, float* ms_out /* [EINX_PROFILE_SLOTS] */);
+
 #ifdef __cplusplus
 }
 #endif
