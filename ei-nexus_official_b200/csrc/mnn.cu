@@ -300,7 +300,7 @@ int einx_mnn_tc(einx_ctx* ctx, const float* d0, const float* d1, const int32_t* 
                 int mcap, int D, int precision, unsigned long long* rowkey, unsigned long long* colkey,
                 unsigned char* scratch, size_t scratch_bytes, cudaStream_t stream);
 size_t einx_mnn_tc_scratch_bytes(int B, int ncap, int mcap, int D, int precision);
-bool einx_mnn_tc_supported(int D, int precision);
+bool einx_mnn_tc_supported(const float* d0, const float* d1, int D, int precision);
 
 extern "C" int einx_mnn(einx_ctx* ctx, const float* d0, const float* d1, const int32_t* n0, const int32_t* n1, int B,
                         int ncap, int mcap, int D, float ratio_thresh, float distance_thresh, int mutual,
@@ -321,7 +321,7 @@ extern "C" int einx_mnn(einx_ctx* ctx, const float* d0, const float* d1, const i
     cudaStream_t stream = (cudaStream_t)stream_;
     const bool use_ratio = ratio_thresh > 0.0f;
     // TMA needs 16-byte row pitches; other feature sizes take the (more exact) FFMA path
-    if (precision != EINX_MNN_FP32 && !einx_mnn_tc_supported(D, precision)) precision = EINX_MNN_FP32;
+    if (precision != EINX_MNN_FP32 && !einx_mnn_tc_supported(d0, d1, D, precision)) precision = EINX_MNN_FP32;
 
     const size_t rk_bytes = align_up((size_t)B * ncap * 8, 256), ck_bytes = align_up((size_t)B * mcap * 8, 256);
     const size_t key_bytes = (rk_bytes + ck_bytes) * (use_ratio ? 2 : 1);

@@ -18,6 +18,7 @@
 // a few 1e-7 while staying on the tensor pipe.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "mnn_keys.cuh"
@@ -26,31 +27,51 @@ namespace {
 
 constexpr int TILE_M = 128;          // rows of d0 per tile  (UMMA M, TMEM lanes)
 constexpr int TILE_N = 256;          // rows of d1 per tile  (UMMA N, TMEM columns)
-constexpr int KBLOCK_BYTES = 128;    // one swizzle-128B row per k-block
-constexpr int A_BYTES = TILE_M * KBLOCK_BYTES;  // 16 KB
-constexpr int B_BYTES = TILE_N * KBLOCK_BYTES;  // 32 KB
-constexpr int STAGES = 3;
 constexpr int kEpilogueWarp0 = 4;
-constexpr int kEpilogueWarps = 8;   // two warps per TMEM lane quarter, each takes half of the columns
-constexpr int kThreads = 32 * (kEpilogueWarp0 + kEpilogueWarps);
-constexpr int kScratchPitch = 33;   // floats; 32x32 transpose tile per epilogue warp, conflict-free both ways
+constexpr int kThreads = 384;        // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4.. epilogue (+ converters)
+constexpr int kScratchPitch = 33;    // floats; 32x32 transpose tile per epilogue warp, conflict-free both ways
 constexpr uint32_t kTmemCols = 512;
+
+// Per-precision shape of the pipeline.
+//   BF16   : 3 stages of (A 16 KB | B 32 KB), 8 epilogue warps (the epilogue is the critical path).
+//   TF32X3 : every stage also holds the low-order tiles (A lo | B lo) that 4 converter warps derive
+//            from the raw fp32 tiles in shared memory, so each descriptor byte crosses L2 -> SM once
+//            per tile and no split copy of the descriptors ever exists in HBM.  The MMA work is 6x
+//            the bf16 one, so 4 epilogue warps keep up.
+template <int KIND, int KB>
+struct Cfg {
+    static constexpr int kElt = KIND == 0 ? 2 : 4;
+    static constexpr int kKB = KB;                       // bytes of K per stage row (= swizzle span)
+    static constexpr int kABytes = TILE_M * KB;
+    static constexpr int kBBytes = TILE_N * KB;
+    static constexpr bool kConvert = KIND == 1;
+    static constexpr int kStageBytes = (kABytes + kBBytes) * (kConvert ? 2 : 1);
+    static constexpr int kStages = KIND == 0 ? 3 : (192 * 1024) / kStageBytes;
+    static constexpr int kEpiWarps = KIND == 0 ? 8 : 4;
+    static constexpr int kConvWarps = kConvert ? 4 : 0;
+    static constexpr int kConvWarp0 = kEpilogueWarp0 + kEpiWarps;
+    static constexpr int kColsPerWarp = TILE_N / (kEpiWarps / 4);
+    static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + 256 + 4 * TILE_N * sizeof(unsigned long long) +
+                                    (size_t)kEpiWarps * 32 * kScratchPitch * sizeof(float);
+    static_assert(kEpilogueWarp0 + kEpiWarps + kConvWarps <= kThreads / 32, "warp roles exceed the CTA");
+    static_assert(kStages <= 4, "Barriers holds 4 stages");
+};
 
 struct TcParams {
     const int32_t* n0;
     const int32_t* n1;
     int B, ncap, mcap;
     int tiles_m, tiles_n;  // per pair
-    int nkb;               // k-blocks per operand pass
-    int passes;            // 1 (bf16) or 3 (tf32x3)
+    int nkb;               // k-blocks per tile
     uint32_t idesc;
     unsigned long long* rowkey;
     unsigned long long* colkey;
 };
 
 struct __align__(8) Barriers {
-    unsigned long long full[STAGES];
-    unsigned long long empty[STAGES];
+    unsigned long long full[4];    // TMA landed the raw tiles of a stage
+    unsigned long long conv[4];    // converter warps wrote the lo tiles of a stage (TF32X3)
+    unsigned long long empty[4];   // the MMAs reading a stage have completed
     unsigned long long tmem_full[2];
     unsigned long long tmem_empty[2];
     uint32_t tmem_base;
@@ -68,18 +89,27 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Spin on the phase parity.  A pipeline bug must not hang the GPU: after ~2^31 cycles the kernel
+// traps, which surfaces as a CUDA error on the host instead of a dead device.
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    long long t0 = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if ((spins & 0xfffu) == 0xfffu) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > (1ll << 31)) __trap();
+        }
+    }
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1) {
     asm volatile(
@@ -124,30 +154,37 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups 1024 B apart (SBO), descriptor
-// version 1 (Blackwell), layout type 2.  The start address advances by 32 B per UMMA_K step.
+// K-major operand tile whose rows are one swizzle span (KB = 128 or 64 bytes) wide: 8-row groups are
+// 8*KB bytes apart (SBO), descriptor version 1 (Blackwell), layout type 2 (SWIZZLE_128B) or 4
+// (SWIZZLE_64B).  The start address advances by 32 B per UMMA_K step inside the span.
+template <int KB>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);   // start address, bits [0,14)
     d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset, bits [32,46)
+    d |= (uint64_t)((8 * KB) >> 4) << 32;          // stride byte offset, bits [32,46)
     d |= (uint64_t)1 << 46;                        // version
-    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    d |= (uint64_t)(KB == 128 ? 2 : 4) << 61;      // swizzle mode
     return d;
 }
 
-// signed-int key: larger float <=> larger int (for redux.sync.max.s32)
-__device__ __forceinline__ int f32_skey(uint32_t bits) { return (int)(bits ^ (((int)bits >> 31) & 0x7fffffff)); }
+// low-order part of an fp32 value w.r.t. its tf32 truncation: kind::tf32 reads the top 19 bits of
+// each operand word, so hi = x & 0xffffe000 is what the tensor core sees of the raw tile and
+// lo = x - hi is exact in fp32 (13 significant bits, of which the tensor core keeps 11)
+__device__ __forceinline__ float tf32_lo(float x) {
+    return __fsub_rn(x, __uint_as_float(__float_as_uint(x) & 0xffffe000u));
+}
 
-template <int KIND>
+template <int KIND, int KB>
 __global__ void __launch_bounds__(kThreads, 1)
-mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-              const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1, const TcParams P) {
+mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams P) {
+    using C = Cfg<KIND, KB>;
+    constexpr int A_BYTES = C::kABytes, B_BYTES = C::kBBytes, STAGES = C::kStages, STAGE_BYTES = C::kStageBytes;
     extern __shared__ __align__(1024) unsigned char smem[];
-    // carve: [stages x (A | B)] 1024-aligned, then barriers, then the column-merge buffer
+    // carve: [stages x (A | B [| A lo | B lo])] 1024-aligned, then barriers, then the column-merge buffer
     unsigned char* tiles = (unsigned char*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
-    Barriers* bars = reinterpret_cast<Barriers*>(tiles + (size_t)STAGES * (A_BYTES + B_BYTES));
-    unsigned long long* colpart = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(bars) + 128);
+    Barriers* bars = reinterpret_cast<Barriers*>(tiles + (size_t)STAGES * STAGE_BYTES);
+    unsigned long long* colpart = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(bars) + 256);
     float* scratch_all = reinterpret_cast<float*>(colpart + 4 * TILE_N);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -155,16 +192,16 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
     const int total_tiles = P.B * tiles_per_pair;
 
     if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB0) : "memory");
-        if (P.passes > 1) {
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA1) : "memory");
-            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB1) : "memory");
-        }
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], kEpilogueWarps); }
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&bars->full[s], 1);
+            mbar_init(&bars->conv[s], C::kConvWarps * 32);
+            mbar_init(&bars->empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], C::kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -199,20 +236,14 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
                 tile_coords(t, b, i0, j0, live);
                 if (!live) continue;
                 const int rowA = b * P.ncap + i0, rowB = b * P.mcap + j0;
-                for (int pass = 0; pass < P.passes; ++pass) {
-                    // pass 0: hi*hi   pass 1: hi*lo   pass 2: lo*hi
-                    const CUtensorMap* ma = (pass == 2) ? &mapA1 : &mapA0;
-                    const CUtensorMap* mb = (pass == 1) ? &mapB1 : &mapB0;
-                    for (int kb = 0; kb < P.nkb; ++kb) {
-                        mbar_wait(&bars->empty[stage], phase ^ 1);
-                        unsigned char* sa = tiles + (size_t)stage * (A_BYTES + B_BYTES);
-                        unsigned char* sb = sa + A_BYTES;
-                        mbar_expect_tx(&bars->full[stage], A_BYTES + B_BYTES);
-                        const int kcoord = kb * (KBLOCK_BYTES / (KIND == 0 ? 2 : 4));
-                        tma_load_2d(sa, ma, &bars->full[stage], kcoord, rowA);
-                        tma_load_2d(sb, mb, &bars->full[stage], kcoord, rowB);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                    }
+                for (int kb = 0; kb < P.nkb; ++kb) {
+                    mbar_wait(&bars->empty[stage], phase ^ 1);
+                    unsigned char* sa = tiles + (size_t)stage * STAGE_BYTES;
+                    mbar_expect_tx(&bars->full[stage], A_BYTES + B_BYTES);
+                    const int kcoord = kb * (KB / C::kElt);
+                    tma_load_2d(sa, &mapA, &bars->full[stage], kcoord, rowA);
+                    tma_load_2d(sa + A_BYTES, &mapB, &bars->full[stage], kcoord, rowB);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -231,33 +262,74 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
                 mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)acc * TILE_N;
-                const int nsteps = P.passes * P.nkb;
-                for (int step = 0; step < nsteps; ++step) {
+                for (int kb = 0; kb < P.nkb; ++kb) {
                     mbar_wait(&bars->full[stage], phase);
+                    if (C::kConvert) mbar_wait(&bars->conv[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(tiles + (size_t)stage * (A_BYTES + B_BYTES));
-                    const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + A_BYTES);
+                    const uint32_t sa = smem_u32(tiles + (size_t)stage * STAGE_BYTES);
+                    const uint64_t a_hi = make_smem_desc<KB>(sa), b_hi = make_smem_desc<KB>(sa + A_BYTES);
+                    if (C::kConvert) {
+                        // x.y ~= hi.hi + hi.lo + lo.hi  (the raw tile is its own hi part: the tensor
+                        // core drops the 13 low mantissa bits of a tf32 operand)
+                        const uint64_t a_lo = make_smem_desc<KB>(sa + A_BYTES + B_BYTES);
+                        const uint64_t b_lo = make_smem_desc<KB>(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
-                    for (int k = 0; k < KBLOCK_BYTES / 32; ++k) {
-                        // +32 B along K inside the swizzle atom = +2 in the 16-byte-unit address field
-                        tc_mma<KIND>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), P.idesc,
-                                     (step > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < KB / 32; ++k)
+                            tc_mma<KIND>(tmem_d, a_hi + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), P.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                        for (int k = 0; k < KB / 32; ++k)
+                            tc_mma<KIND>(tmem_d, a_hi + (uint64_t)(2 * k), b_lo + (uint64_t)(2 * k), P.idesc, 1u);
+#pragma unroll
+                        for (int k = 0; k < KB / 32; ++k)
+                            tc_mma<KIND>(tmem_d, a_lo + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), P.idesc, 1u);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < KB / 32; ++k) {
+                            // +32 B along K inside the swizzle span = +2 in the 16-byte-unit address field
+                            tc_mma<KIND>(tmem_d, a_hi + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), P.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        }
                     }
                     tc_commit(&bars->empty[stage]);  // smem slot free once these MMAs have read it
-                    if (step == nsteps - 1) tc_commit(&bars->tmem_full[acc]);
+                    if (kb == P.nkb - 1) tc_commit(&bars->tmem_full[acc]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
         }
-    } else if (warp >= kEpilogueWarp0) {
+    } else if (C::kConvert && warp >= C::kConvWarp0 && warp < C::kConvWarp0 + C::kConvWarps) {
+        // ===== converter: lo tiles = x - tf32_trunc(x), element-wise (so the swizzle is irrelevant) =====
+        const int ct = threadIdx.x - C::kConvWarp0 * 32;
+        constexpr int kChunks = (A_BYTES + B_BYTES) / 16;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            int b, i0, j0;
+            bool live;
+            tile_coords(t, b, i0, j0, live);
+            if (!live) continue;
+            for (int kb = 0; kb < P.nkb; ++kb) {
+                mbar_wait(&bars->full[stage], phase);
+                const float4* raw = reinterpret_cast<const float4*>(tiles + (size_t)stage * STAGE_BYTES);
+                float4* lo = reinterpret_cast<float4*>(tiles + (size_t)stage * STAGE_BYTES + A_BYTES + B_BYTES);
+#pragma unroll 8
+                for (int i = ct; i < kChunks; i += C::kConvWarps * 32) {
+                    const float4 v = raw[i];
+                    lo[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+                }
+                // generic-proxy writes must be visible to the tensor core's async-proxy reads
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&bars->conv[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= kEpilogueWarp0 && warp < kEpilogueWarp0 + C::kEpiWarps) {
         // ===== epilogue: TMEM -> registers -> row / column best keys =====
-        // Rows: the thread that owns TMEM lane r scans its 128 columns with a strict '>' (lowest
+        // Rows: the thread that owns TMEM lane r scans its columns with a strict '>' (lowest
         // column wins ties).  Columns: the 32x32 chunk goes through a padded shared-memory tile so
         // that lane c then owns column c and scans the 32 rows the same way (lowest row wins).
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
-        const int half = (warp - kEpilogueWarp0) >> 2;   // which 128 columns of the tile
+        const int part = (warp - kEpilogueWarp0) >> 2;   // which kColsPerWarp columns of the tile
         float* scratch = scratch_all + (size_t)(warp - kEpilogueWarp0) * 32 * kScratchPitch;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -274,14 +346,14 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
             const bool full_tile = (i0 + TILE_M <= N) && (j0 + TILE_N <= M);
             mbar_wait(&bars->tmem_full[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * TILE_N + 128 * half);
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * TILE_N + C::kColsPerWarp * part);
             float best = -INFINITY;
             int best_j = 0;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < C::kColsPerWarp / 32; ++c) {
                 uint32_t v[32];
                 tc_ld32(taddr + 32 * c, v);
-                const int jc = j0 + 128 * half + 32 * c;
+                const int jc = j0 + C::kColsPerWarp * part + 32 * c;
                 if (jc < M) {  // warp-uniform; beyond M the tile is padding
 #pragma unroll
                     for (int k = 0; k < 32; ++k) {
@@ -303,7 +375,7 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
                     }
                     if (c1 > c0) { c0 = c1; r0 = r1; }
                     const bool col_ok = (jc + lane < M) && (c0 > -INFINITY);
-                    colpart[q * TILE_N + 128 * half + 32 * c + lane] =
+                    colpart[q * TILE_N + C::kColsPerWarp * part + 32 * c + lane] =
                         col_ok ? (((unsigned long long)f32_orderable(c0 + 0.0f) << 32) |
                                   (0xffffffffu - (uint32_t)(i0 + 32 * q + r0)))
                                : 0ull;
@@ -317,10 +389,9 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
             if (row_ok && best > -INFINITY)
                 atomicMax(P.rowkey + (size_t)b * P.ncap + row,
                           ((unsigned long long)f32_orderable(best + 0.0f) << 32) | (0xffffffffu - (uint32_t)best_j));
-            // merge the 4 lane quarters' column keys: 256 epilogue threads, one column each
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            {
-                const int cidx = threadIdx.x - kEpilogueWarp0 * 32;
+            // merge the 4 lane quarters' column keys
+            asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiWarps * 32) : "memory");
+            for (int cidx = threadIdx.x - kEpilogueWarp0 * 32; cidx < TILE_N; cidx += C::kEpiWarps * 32) {
                 const int j = j0 + cidx;
                 if (j < M) {
                     unsigned long long m = colpart[cidx];
@@ -329,7 +400,7 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
                     if (m) atomicMax(P.colkey + (size_t)b * P.mcap + j, m);
                 }
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");  // colpart is reused by the next tile
+            asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiWarps * 32) : "memory");  // colpart is reused by the next tile
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
@@ -343,28 +414,19 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
 }
 
 // ---- operand preparation --------------------------------------------------------------------- //
-__global__ void to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
-    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i + 3 < n) {
-        const float4 v = *reinterpret_cast<const float4*>(src + i);
+__global__ void to_bf16_kernel(const float* __restrict__ src0, size_t n0, const float* __restrict__ src1, size_t n1,
+                               __nv_bfloat16* __restrict__ dst) {
+    // dst = [bf16(src0) | bf16(src1)], both sides in one launch; n0 and n1 are multiples of 8
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+    const size_t n = n0 + n1;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        const float4 v = i < n0 ? __ldg(reinterpret_cast<const float4*>(src0 + i))
+                                : __ldg(reinterpret_cast<const float4*>(src1 + (i - n0)));
         __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
         uint2 o;
         o.x = *reinterpret_cast<uint32_t*>(&a);
         o.y = *reinterpret_cast<uint32_t*>(&b);
         *reinterpret_cast<uint2*>(dst + i) = o;
-    } else {
-        for (size_t k = i; k < n; ++k) dst[k] = __float2bfloat16_rn(src[k]);
-    }
-}
-__global__ void split_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        const float x = src[i];
-        uint32_t h;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-        const float hf = __uint_as_float(h);
-        hi[i] = hf;
-        lo[i] = __fsub_rn(x, hf);  // exact; the tensor core truncates it to tf32 (error ~2^-22 |x|)
     }
 }
 
@@ -384,16 +446,18 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2-D row-major matrix (rows x D) -> tensor map with a (128 B x box_rows) swizzled box
-int make_map(einx_ctx* ctx, CUtensorMap* map, void* base, CUtensorMapDataType dt, int elt, size_t rows, int D, int box_rows) {
+// 2-D row-major matrix (rows x D) -> tensor map with a (kb bytes x box_rows) swizzled box
+int make_map(einx_ctx* ctx, CUtensorMap* map, const void* base, CUtensorMapDataType dt, int elt, size_t rows, int D,
+             int box_rows, int kb) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return einx_fail(ctx, EINX_ERR_CUDA, "einx_mnn: cuTensorMapEncodeTiled entry point unavailable");
     cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)D * elt};
-    cuuint32_t box[2] = {(cuuint32_t)(KBLOCK_BYTES / elt), (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)(kb / elt), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, dt, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    kb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return einx_fail(ctx, EINX_ERR_CUDA, "einx_mnn: cuTensorMapEncodeTiled failed (%d)", (int)r);
     return EINX_OK;
 }
@@ -405,78 +469,68 @@ uint32_t make_idesc(int kind) {
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 }
 
+template <int KIND, int KB>
+int launch_tc(einx_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, int grid, cudaStream_t stream) {
+    auto kern = mnn_tc_kernel<KIND, KB>;
+    const size_t smem = Cfg<KIND, KB>::kSmem;
+    EINX_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    einx_prof_begin(ctx, 3, stream);
+    kern<<<grid, kThreads, smem, stream>>>(ma, mb, P);
+    einx_prof_end(ctx, 3, stream);
+    EINX_CHECK_LAUNCH(ctx);
+    return EINX_OK;
+}
+
 }  // namespace
 
 size_t einx_mnn_tc_scratch_bytes(int B, int ncap, int mcap, int D, int precision) {
     const size_t elems = (size_t)B * ((size_t)ncap + mcap) * D;
-    return precision == EINX_MNN_BF16 ? align_up(elems * 2, 1024) + 2048 : 2 * align_up(elems * 4, 1024) + 4096;
+    return precision == EINX_MNN_BF16 ? align_up(elems * 2, 1024) + 2048 : 0;  // TF32X3 reads the descriptors in place
 }
 
-bool einx_mnn_tc_supported(int D, int precision) {
-    // TMA needs 16-byte aligned row pitches
-    return precision == EINX_MNN_BF16 ? (D % 8 == 0) : (D % 4 == 0);
+bool einx_mnn_tc_supported(const float* d0, const float* d1, int D, int precision) {
+    // TMA needs 16-byte aligned bases and row pitches
+    if (precision == EINX_MNN_BF16) return D % 8 == 0 && ((uintptr_t)d0 % 16 == 0) && ((uintptr_t)d1 % 16 == 0);
+    return D % 4 == 0 && ((uintptr_t)d0 % 16 == 0) && ((uintptr_t)d1 % 16 == 0);
 }
 
 int einx_mnn_tc(einx_ctx* ctx, const float* d0, const float* d1, const int32_t* n0, const int32_t* n1, int B, int ncap,
                 int mcap, int D, int precision, unsigned long long* rowkey, unsigned long long* colkey,
                 unsigned char* scratch, size_t scratch_bytes, cudaStream_t stream) {
     const size_t e0 = (size_t)B * ncap * D, e1 = (size_t)B * mcap * D;
-    unsigned char* base = (unsigned char*)(((uintptr_t)scratch + 1023) & ~(uintptr_t)1023);
-    CUtensorMap maps[4];
+    CUtensorMap maps[2];
     memset(maps, 0, sizeof(maps));
     TcParams P = {};
     P.n0 = n0; P.n1 = n1; P.B = B; P.ncap = ncap; P.mcap = mcap;
     P.tiles_m = (ncap + TILE_M - 1) / TILE_M;
     P.tiles_n = (mcap + TILE_N - 1) / TILE_N;
     P.rowkey = rowkey; P.colkey = colkey;
-    int rc;
-    if (precision == EINX_MNN_BF16) {
-        __nv_bfloat16* a = (__nv_bfloat16*)base;
-        __nv_bfloat16* b = a + e0;  // e0 * 2 bytes: keeps 16-byte alignment when D % 8 == 0
-        to_bf16_kernel<<<(unsigned)((e0 / 4 + 255) / 256 + 1), 256, 0, stream>>>(d0, a, e0);
-        EINX_CHECK_LAUNCH(ctx);
-        to_bf16_kernel<<<(unsigned)((e1 / 4 + 255) / 256 + 1), 256, 0, stream>>>(d1, b, e1);
-        EINX_CHECK_LAUNCH(ctx);
-        if ((rc = make_map(ctx, &maps[0], a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (size_t)B * ncap, D, TILE_M))) return rc;
-        if ((rc = make_map(ctx, &maps[2], b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (size_t)B * mcap, D, TILE_N))) return rc;
-        maps[1] = maps[0];
-        maps[3] = maps[2];
-        P.nkb = (D * 2 + KBLOCK_BYTES - 1) / KBLOCK_BYTES;
-        P.passes = 1;
-        P.idesc = make_idesc(0);
-    } else {
-        float* ahi = (float*)base;
-        float* alo = ahi + e0;
-        float* bhi = alo + e0;
-        float* blo = bhi + e1;
-        split_tf32_kernel<<<(unsigned)((e0 + 255) / 256), 256, 0, stream>>>(d0, ahi, alo, e0);
-        EINX_CHECK_LAUNCH(ctx);
-        split_tf32_kernel<<<(unsigned)((e1 + 255) / 256), 256, 0, stream>>>(d1, bhi, blo, e1);
-        EINX_CHECK_LAUNCH(ctx);
-        if ((rc = make_map(ctx, &maps[0], ahi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (size_t)B * ncap, D, TILE_M))) return rc;
-        if ((rc = make_map(ctx, &maps[1], alo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (size_t)B * ncap, D, TILE_M))) return rc;
-        if ((rc = make_map(ctx, &maps[2], bhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (size_t)B * mcap, D, TILE_N))) return rc;
-        if ((rc = make_map(ctx, &maps[3], blo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (size_t)B * mcap, D, TILE_N))) return rc;
-        P.nkb = (D * 4 + KBLOCK_BYTES - 1) / KBLOCK_BYTES;
-        P.passes = 3;
-        P.idesc = make_idesc(1);
-    }
-    const size_t smem = 1024 + (size_t)STAGES * (A_BYTES + B_BYTES) + 128 + 4 * TILE_N * sizeof(unsigned long long) +
-                        (size_t)kEpilogueWarps * 32 * kScratchPitch * sizeof(float);
     const int total_tiles = B * P.tiles_m * P.tiles_n;
     int grid = ctx->num_sms < total_tiles ? ctx->num_sms : total_tiles;
     if (grid < 1) grid = 1;
-    if (precision == EINX_MNN_BF16) {
-        EINX_CUDA(ctx, cudaFuncSetAttribute(mnn_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        einx_prof_begin(ctx, 3, stream);
-        mnn_tc_kernel<0><<<grid, kThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], P);
-    } else {
-        EINX_CUDA(ctx, cudaFuncSetAttribute(mnn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        einx_prof_begin(ctx, 3, stream);
-        mnn_tc_kernel<1><<<grid, kThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], P);
-    }
-    einx_prof_end(ctx, 3, stream);
-    EINX_CHECK_LAUNCH(ctx);
+    int rc;
     (void)scratch_bytes;
-    return EINX_OK;
+    if (precision == EINX_MNN_BF16) {
+        __nv_bfloat16* a = (__nv_bfloat16*)(((uintptr_t)scratch + 1023) & ~(uintptr_t)1023);
+        __nv_bfloat16* b = a + e0;  // e0 * 2 bytes: keeps 16-byte alignment when D % 8 == 0
+        const size_t quads = (e0 + e1) / 4;
+        unsigned blocks = (unsigned)((quads + 255) / 256);
+        if (blocks > (unsigned)ctx->num_sms * 16) blocks = (unsigned)ctx->num_sms * 16;
+        to_bf16_kernel<<<blocks ? blocks : 1, 256, 0, stream>>>(d0, e0, d1, e1, a);
+        EINX_CHECK_LAUNCH(ctx);
+        if ((rc = make_map(ctx, &maps[0], a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (size_t)B * ncap, D, TILE_M, 128))) return rc;
+        if ((rc = make_map(ctx, &maps[1], b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (size_t)B * mcap, D, TILE_N, 128))) return rc;
+        P.nkb = (D * 2 + 127) / 128;
+        P.idesc = make_idesc(0);
+        return launch_tc<0, 128>(ctx, maps[0], maps[1], P, grid, stream);
+    }
+    // TF32X3: stage depth by k-block width -- 64-byte blocks give 4 stages of 48 KB, 128-byte blocks 2 of 96 KB
+    static const int kb_env = getenv("EINX_MNN_TF32_KB") ? atoi(getenv("EINX_MNN_TF32_KB")) : 0;
+    const int KB = kb_env == 128 ? 128 : 64;
+    if ((rc = make_map(ctx, &maps[0], d0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (size_t)B * ncap, D, TILE_M, KB))) return rc;
+    if ((rc = make_map(ctx, &maps[1], d1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (size_t)B * mcap, D, TILE_N, KB))) return rc;
+    P.nkb = (D * 4 + KB - 1) / KB;
+    P.idesc = make_idesc(1);
+    return KB == 128 ? launch_tc<1, 128>(ctx, maps[0], maps[1], P, grid, stream)
+                     : launch_tc<1, 64>(ctx, maps[0], maps[1], P, grid, stream);
 }

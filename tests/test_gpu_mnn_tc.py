@@ -120,3 +120,30 @@ def test_tc_ragged_counts(einx, synth, precision):
         assert nm == keep.sum()
         assert np.array_equal(out["matched_kpts0"][b, :nm].cpu().numpy(), k0[b][keep])
         assert np.array_equal(out["matched_kpts1"][b, :nm].cpu().numpy(), k1[b][m0[keep]])
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "fp32"])
+def test_similarity_values_are_fp32_accurate(einx, precision):
+    """The 3xTF32 split must reproduce fp32 similarity VALUES (not only the argmax): probe them through
+    the distance threshold.  Rows are a_i*e_i against b_i*e_i, so sim(i, i) = a_i*b_i exactly; a
+    single-pass tf32 product (or a wrong hi/lo split) is off by ~2e-4 and misclassifies dozens of rows."""
+    rng = np.random.default_rng(77)
+    B, N, D = 32, 64, 64
+    a = (1.0 - 0.01 * rng.random((B, N))).astype(np.float32)
+    b = (1.0 - 0.01 * rng.random((B, N))).astype(np.float32)
+    sign = np.where(rng.random((B, N)) < 0.5, -1.0, 1.0).astype(np.float32)  # negative operands too
+    d0 = np.zeros((B, N, D), np.float32)
+    d1 = np.zeros((B, N, D), np.float32)
+    idx = np.arange(N)
+    d0[:, idx, idx] = a * sign
+    d1[:, idx, idx] = b * sign
+    p = a.astype(np.float64) * b.astype(np.float64)
+    T = float(np.median(p))
+    thr = float(np.sqrt(2.0 * (1.0 - T)))  # dist = 2 (1 - sim) <= thr^2  <=>  sim >= T
+    out = einx.mnn(cuda(d0), cuda(d1), distance_thresh=thr, precision=precision)
+    got = (out["matches0"] > -1).cpu().numpy()
+    assert np.array_equal(out["matches0"].cpu().numpy()[got], np.broadcast_to(idx, (B, N))[got])
+    must, must_not = p >= T + 1e-6, p <= T - 1e-6
+    assert must.sum() > 500 and must_not.sum() > 500
+    assert got[must].all(), f"{(~got[must]).sum()} rows above the threshold were dropped"
+    assert not got[must_not].any(), f"{got[must_not].sum()} rows below the threshold were kept"
