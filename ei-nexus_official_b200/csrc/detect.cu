@@ -9,10 +9,16 @@
 // A round (detector_util.py:286-335 restated):
 //   lm(p)  = v(p) > 0  and  v(p) >= every window value  and  no equal value earlier in raster order
 //   v(p)   = 0 for every p that has a local maximum in its window and is not one itself
-// Local maxima are monotone (values only decrease), so segments with no undecided pixel are
-// skipped in later rounds, and the loop ends when no pixel is undecided -- the same fixpoint the
-// reference reaches when its batch-wide count of maxima stops changing.
+// Local maxima are monotone (values only decrease), and an undecided pixel (positive, not a maximum,
+// not suppressed) has no maximum in its window, so only the undecided pixels matter after a round.
+// Dense rounds are separable: pass A takes the horizontal window maximum of 4 pixels per thread from
+// float4 loads, pass B the vertical one of 8 rows per thread and decides the pixel; suppression is a
+// dilation of the maxima bitmap on 32-bit words.  As soon as the undecided pixels of a band fit the
+// worklist (after round 0 on i.i.d. maps: 3.7 %), rounds visit those pixels only.  The loop ends when
+// no pixel of the image is undecided -- the same fixpoint the reference reaches when its batch-wide
+// count of maxima stops changing.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -22,7 +28,6 @@ namespace {
 
 constexpr int kThreads = 1024;
 constexpr int kWarps = kThreads / 32;
-constexpr int kSegRows = 24;  // rows per (strip, segment) work item of the fused row/column pass
 constexpr int kMaxCluster = 8;
 constexpr int kWorklistCap = 4096;  // late NMS rounds visit only the still-undecided pixels (per CTA)
 
@@ -35,8 +40,10 @@ struct DetectParams {
     int B, Hp, Wp, border, kcap;
     int CS;      // CTAs per image (cluster size)
     int S;       // 32-column strips per row
-    int WS;      // padded row stride of V in floats: 32*S + 2R
+    int WS;      // padded row stride of V in floats: 32*S + 2*PAD
     int RBmax;   // max own rows of a band
+    int vec4;    // rows of `score` (and `mask`) can be moved as float4 (uchar4)
+    unsigned magic_s, magic_ch;  // ceil(2^32 / S), ceil(2^32 / (8*S)): t / S == umulhi(t, magic_s) for t < 2^20
     float prob_thresh;
     int use_topk;  // 1: threshold from order statistics rank_lo / rank_hi; 2: top_k >= n (thr_k = 0)
     int rank_lo, rank_hi;
@@ -46,9 +53,17 @@ struct DetectParams {
     unsigned int* worklists;  // [B * CS][2][kWorklistCap] entries (local row << 16 | x), L2-resident
     // global-memory variant (maps too large for a cluster's shared memory)
     float* gV;
+    float* gH;
     uint32_t* gLM;
     uint32_t* gRD;
+    uint32_t* gPS;
+    long long* trace;  // developer aid (EINX_DETECT_TRACE=1): clock64() at phase boundaries of CTA 0
 };
+
+#define EINX_TRACE(slot)                                                          \
+    do {                                                                          \
+        if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && (slot) < 128) P.trace[(slot)] = clock64(); \
+    } while (0)
 
 struct Shared {
     int flags[2];
@@ -157,14 +172,79 @@ __device__ void select_two(const float* __restrict__ list, int n, int j, bool ne
     b_out = b;
 }
 
+// PAD columns of zeros on both sides of a band row; a multiple of 4 so that pixel 0 of every row is
+// 16-byte aligned and the passes below can move float4.
+template <int R>
+struct Geo {
+    static constexpr int PAD = (R + 3) / 4 * 4;
+};
+
+// Horizontal window maxima of 4 neighbouring pixels.  a[] holds the 4 + 2*PAD values starting PAD
+// to the left of the first pixel; o[i] = max a[PAD+i-R .. PAD+i+R].  The values shared by all four
+// windows are reduced once, then extended left / right: 2R+7 max operations for 4 outputs.
+template <int R>
+__device__ __forceinline__ void hmax4(const float* a, float (&o)[4]) {
+    constexpr int PAD = Geo<R>::PAD;
+    if constexpr (R >= 2) {
+        float common = a[PAD + 3 - R];
+#pragma unroll
+        for (int k = PAD + 4 - R; k <= PAD + R; ++k) common = fmaxf(common, a[k]);
+        const float l1 = a[PAD + 2 - R], l2 = fmaxf(a[PAD + 1 - R], l1), l3 = fmaxf(a[PAD - R], l2);
+        const float r1 = a[PAD + R + 1], r2 = fmaxf(r1, a[PAD + R + 2]), r3 = fmaxf(r2, a[PAD + R + 3]);
+        o[0] = fmaxf(common, l3);
+        o[1] = fmaxf(fmaxf(common, l2), r1);
+        o[2] = fmaxf(fmaxf(common, l1), r2);
+        o[3] = fmaxf(common, r3);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float m = a[PAD + i];
+#pragma unroll
+            for (int d = 1; d <= R; ++d) m = fmaxf(m, fmaxf(a[PAD + i - d], a[PAD + i + d]));
+            o[i] = m;
+        }
+    }
+}
+
+// Vertical window maxima of 8 consecutive rows from the 8 + 2R row maxima a[] above/below them:
+// o[i] = max a[i .. i+2R].  For 2R >= 8 every window straddles the 7|8 boundary, so a suffix scan of
+// a[0..7] and a prefix scan of a[8..] give all eight with 2R+14 operations.
+template <int R>
+__device__ __forceinline__ void vmax8(const float* a, float (&o)[8]) {
+    if constexpr (R >= 4) {
+        float suf[8];
+        suf[7] = a[7];
+#pragma unroll
+        for (int i = 6; i >= 0; --i) suf[i] = fmaxf(a[i], suf[i + 1]);
+        float pre = a[8];
+#pragma unroll
+        for (int k = 9; k <= 2 * R; ++k) pre = fmaxf(pre, a[k]);
+        o[0] = fmaxf(suf[0], pre);
+#pragma unroll
+        for (int i = 1; i < 8; ++i) {
+            pre = fmaxf(pre, a[i + 2 * R]);
+            o[i] = fmaxf(suf[i], pre);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float m = a[i];
+#pragma unroll
+            for (int k = 1; k <= 2 * R; ++k) m = fmaxf(m, a[i + k]);
+            o[i] = m;
+        }
+    }
+}
+
 template <int R, bool SMEM>
 __global__ void __launch_bounds__(kThreads, 1) detect_kernel(const DetectParams P) {
+    constexpr int PAD = Geo<R>::PAD;
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int CS = P.CS;
     const int b = blockIdx.x / CS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int S = P.S, WS = P.WS, Hp = P.Hp, Wp = P.Wp;
+    const int S = P.S, WS = P.WS, HS = 32 * P.S, Hp = P.Hp, Wp = P.Wp;
 
     // balanced row bands
     const int base_rows = Hp / CS, rem = Hp % CS;
@@ -174,67 +254,99 @@ __global__ void __launch_bounds__(kThreads, 1) detect_kernel(const DetectParams 
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
-    float* V;
-    uint32_t *LM, *RD;
-    unsigned char* item_active;
-    const int lrows = P.RBmax + 2 * R;  // local rows incl. halo
-    const int nseg = (P.RBmax + kSegRows - 1) / kSegRows;
+    // Local row lr of every array is image row ys - R + lr: own rows are lr in [R, R + nrows), the R
+    // rows on either side are the halo (copies of the neighbouring bands in the shared-memory
+    // variant; simply the neighbours' rows of the same padded image in the global variant).
+    float *V, *Hm;
+    uint32_t *LM, *RD, *PS;
+    const int lrows = P.RBmax + 2 * R;
     if (SMEM) {
         size_t o = align_up(sizeof(Shared), 16);
         V = reinterpret_cast<float*>(smem_raw + o);
         o += sizeof(float) * (size_t)lrows * WS;
+        Hm = reinterpret_cast<float*>(smem_raw + o);
+        o += sizeof(float) * (size_t)lrows * HS;
         LM = reinterpret_cast<uint32_t*>(smem_raw + o);
         o += sizeof(uint32_t) * (size_t)lrows * S;
         RD = reinterpret_cast<uint32_t*>(smem_raw + o);
         o += sizeof(uint32_t) * (size_t)lrows * S;
-        item_active = smem_raw + o;
+        PS = reinterpret_cast<uint32_t*>(smem_raw + o);
     } else {
-        // global variant: one padded image per batch entry; a CTA indexes its band so that local row
-        // lr maps to padded row ys + lr, neighbours' rows are simply adjacent (no halo copies)
         const size_t img_rows = (size_t)Hp + 2 * R;
         V = P.gV + ((size_t)b * img_rows + ys) * WS;
+        Hm = P.gH + ((size_t)b * img_rows + ys) * HS;
         LM = P.gLM + ((size_t)b * img_rows + ys) * S;
         RD = P.gRD + ((size_t)b * img_rows + ys) * S;
-        item_active = smem_raw + align_up(sizeof(Shared), 16);
+        PS = P.gPS + ((size_t)b * img_rows + ys) * S;
     }
-    const int nitems = S * nseg;
-
     // ---- load the band: border + mask zeroing (in place on `score`), zero padding ---------- //
     if (SMEM) {
-        for (int i = tid; i < lrows * WS; i += kThreads) V[i] = 0.0f;
-        for (int i = tid; i < lrows * S; i += kThreads) { LM[i] = 0u; RD[i] = 0u; }
+        float4* v4 = reinterpret_cast<float4*>(V);
+        for (int i = tid; i < lrows * WS / 4; i += kThreads) v4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < lrows * S; i += kThreads) { LM[i] = 0u; RD[i] = 0u; PS[i] = 0u; }
     }
-    for (int i = tid; i < nitems; i += kThreads) item_active[i] = 1;
-    if (tid == 0) { sh.flags[0] = sh.flags[1] = 0; sh.xcnt[0] = sh.xcnt[1] = 0; }
+    if (tid == 0) { sh.flags[0] = sh.flags[1] = 0; sh.xcnt[0] = sh.xcnt[1] = 0; sh.wl_n[0] = sh.wl_n[1] = 0; }
     __syncthreads();
     {
         float* simg = P.score + (size_t)b * Hp * Wp;
         const uint8_t* mimg = P.mask ? P.mask + (size_t)b * Hp * Wp : nullptr;
         const int bd = P.border;
-        for (int e = tid; e < nrows * Wp; e += kThreads) {
-            const int lr = e / Wp, x = e - lr * Wp, y = ys + lr;
-            const size_t gi = (size_t)y * Wp + x;
-            float v = simg[gi];
-            bool kill = (y < bd) | (y >= Hp - bd) | (x < bd) | (x >= Wp - bd);
-            if (mimg) kill |= (mimg[gi] == 0);
-            if (kill) {
-                if (v != 0.0f) simg[gi] = 0.0f;
-                v = 0.0f;
+        for (int lr = warp; lr < nrows; lr += kWarps) {
+            const int y = ys + lr;
+            const bool rowkill = (y < bd) | (y >= Hp - bd);
+            float* srow = simg + (size_t)y * Wp;
+            const uint8_t* mrow = mimg ? mimg + (size_t)y * Wp : nullptr;
+            float* vrow = V + (size_t)(lr + R) * WS + PAD;
+            if (P.vec4) {
+                for (int c = lane; c < (Wp >> 2); c += 32) {
+                    float4 v = *reinterpret_cast<const float4*>(srow + 4 * c);
+                    float e[4] = {v.x, v.y, v.z, v.w};
+                    uchar4 m4 = make_uchar4(1, 1, 1, 1);
+                    if (mrow) m4 = *reinterpret_cast<const uchar4*>(mrow + 4 * c);
+                    const unsigned char mm[4] = {m4.x, m4.y, m4.z, m4.w};
+                    bool changed = false;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int x = 4 * c + j;
+                        const bool kill = rowkill | (x < bd) | (x >= Wp - bd) | (mm[j] == 0);
+                        if (kill) {
+                            changed |= (e[j] != 0.0f);
+                            e[j] = 0.0f;
+                        }
+                    }
+                    v = make_float4(e[0], e[1], e[2], e[3]);
+                    if (changed) *reinterpret_cast<float4*>(srow + 4 * c) = v;
+                    *reinterpret_cast<float4*>(vrow + 4 * c) = v;
+                }
+            } else {
+                for (int x = lane; x < Wp; x += 32) {
+                    float v = srow[x];
+                    bool kill = rowkill | (x < bd) | (x >= Wp - bd);
+                    if (mrow) kill |= (mrow[x] == 0);
+                    if (kill) {
+                        if (v != 0.0f) srow[x] = 0.0f;
+                        v = 0.0f;
+                    }
+                    vrow[x] = v;
+                }
             }
-            V[(size_t)(lr + R) * WS + x + R] = v;
         }
     }
     if (!SMEM) __threadfence();
+    EINX_TRACE(0);
+    int trace_slot = 1;
 
     // ---- NMS rounds ------------------------------------------------------------------------ //
     if constexpr (R > 0) {
         constexpr int P2 = 2 * R + 1;
         unsigned int* const wl0 = P.worklists + (size_t)blockIdx.x * 2 * kWorklistCap;
         int wl_cur = 0;         // list buffer holding the current undecided set
-        bool wl_mode = false;   // CTA-uniform: this round runs on the worklist instead of full passes
-        if (tid == 0) sh.wl_n[0] = sh.wl_n[1] = 0;
+        bool wl_mode = false;   // CTA-uniform: this round runs on the worklist instead of dense passes
+        const int CH = 8 * S;   // float4 chunks per row
         for (int round = 0;; ++round) {
             cluster.sync();  // S1: every band's V (and the previous round's flag) is final
+            trace_slot = 1 + 8 * round;
+            EINX_TRACE(trace_slot); ++trace_slot;
             if (round > 0) {
                 int any = 0;
                 for (int r = 0; r < CS; ++r) any |= *cluster.map_shared_rank(&sh.flags[(round - 1) & 1], r);
@@ -242,64 +354,79 @@ __global__ void __launch_bounds__(kThreads, 1) detect_kernel(const DetectParams 
             }
             if (SMEM) {
                 if (rank > 0) {
-                    const float* src = cluster.map_shared_rank(V, rank - 1) + (size_t)nprev * WS;
-                    for (int i = tid; i < R * WS; i += kThreads) V[i] = src[i];
+                    const float4* src = reinterpret_cast<const float4*>(cluster.map_shared_rank(V, rank - 1) + (size_t)nprev * WS);
+                    float4* dst = reinterpret_cast<float4*>(V);
+                    for (int i = tid; i < R * WS / 4; i += kThreads) dst[i] = src[i];
                 }
                 if (rank < CS - 1) {
-                    const float* src = cluster.map_shared_rank(V, rank + 1) + (size_t)R * WS;
-                    float* dst = V + (size_t)(R + nrows) * WS;
-                    for (int i = tid; i < R * WS; i += kThreads) dst[i] = src[i];
+                    const float4* src = reinterpret_cast<const float4*>(cluster.map_shared_rank(V, rank + 1) + (size_t)R * WS);
+                    float4* dst = reinterpret_cast<float4*>(V + (size_t)(R + nrows) * WS);
+                    for (int i = tid; i < R * WS / 4; i += kThreads) dst[i] = src[i];
                 }
                 __syncthreads();
             }
             if (!wl_mode) {
-                // fused row/column window pass: one warp walks a 32-column strip down a row segment.
-                // The last 2R+1 full-width row maxima (F) and centre values (C) live in registers as
-                // a ring addressed with compile-time slots (the row loop is unrolled by 2R+1).
-                for (int item = warp; item < nitems; item += kWarps) {
-                    if (!item_active[item]) continue;
-                    const int s = item % S, g = item / S;
-                    const int r0 = g * kSegRows;
-                    const int r1 = min(r0 + kSegRows, nrows);
-                    if (r0 >= r1) continue;
-                    const int lc = 32 * s + lane + R;
-                    float F[P2], C[P2];
+                // pass A: Hm = horizontal window maximum of every local row, halo included (in the
+                // global variant the halo rows are the neighbours' own rows: both CTAs then store
+                // identical values, so no cross-CTA ordering is needed inside a round)
+                {
+                    for (int t = tid; t < (nrows + 2 * R) * CH; t += kThreads) {
+                        const int row = (int)__umulhi((unsigned)t, P.magic_ch);
+                        const int ch = t - row * CH;
+                        const float4* src = reinterpret_cast<const float4*>(V + (size_t)row * WS) + ch;
+                        float a[4 + 2 * PAD];
 #pragma unroll
-                    for (int k = 0; k < P2; ++k) { F[k] = 0.0f; C[k] = 0.0f; }
-                    const int nsteps = (r1 - r0) + 2 * R;
-                    for (int base = 0; base < nsteps; base += P2) {
+                        for (int k = 0; k < 1 + PAD / 2; ++k) {
+                            const float4 q = src[k];
+                            a[4 * k] = q.x; a[4 * k + 1] = q.y; a[4 * k + 2] = q.z; a[4 * k + 3] = q.w;
+                        }
+                        float o[4];
+                        hmax4<R>(a, o);
+                        *(reinterpret_cast<float4*>(Hm + (size_t)row * HS) + ch) = make_float4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+                __syncthreads();
+                EINX_TRACE(trace_slot); ++trace_slot;
+                // pass B: a warp decides 8 rows x 32 columns.  lm = v > 0, v == window max, and no
+                // equal value earlier in raster order (rows above: their row maxima; same row: the R
+                // values to the left) -- the first-occurrence argmax of detector_util.py:298-308.
+                {
+                    const int nblk = (nrows + 7) >> 3;
+                    const int avail_all = nrows + 2 * R;
+                    for (int t = warp; t < nblk * S; t += kWarps) {
+                        const int rb = (int)__umulhi((unsigned)t, P.magic_s);
+                        const int s = t - rb * S;
+                        const int r0 = rb * 8;
+                        const int x = 32 * s + lane;
+                        const int avail = avail_all - r0;
+                        float a[8 + 2 * R];
 #pragma unroll
-                        for (int u = 0; u < P2; ++u) {
-                            const int i = base + u;
-                            if (i < nsteps) {
-                                const float* row = V + (size_t)(r0 + i) * WS + lc;
-                                float f = row[0];
-                                C[u] = f;
+                        for (int k = 0; k < 8 + 2 * R; ++k) a[k] = (k < avail) ? Hm[(size_t)(r0 + k) * HS + x] : 0.0f;
+                        float m[8];
+                        vmax8<R>(a, m);
+                        uint32_t lm_mine = 0, pos_mine = 0;
 #pragma unroll
-                                for (int d = 1; d <= R; ++d) f = fmaxf(f, fmaxf(row[-d], row[d]));
-                                F[u] = f;
-                                if (i >= 2 * R) {
-                                    const int c = r0 + i - 2 * R;        // own row being decided
-                                    const float vc = C[(u + R + 1) % P2];  // row i-R
-                                    float above = F[(u + 1) % P2], below = F[(u + R + 2) % P2];
+                        for (int i = 0; i < 8; ++i) {
+                            const int lr = r0 + i;
+                            const float* crow = V + (size_t)(lr + R) * WS + PAD + x;
+                            const float vc = (lr < nrows) ? crow[0] : 0.0f;
+                            const bool pos = vc > 0.0f;
+                            bool lm = pos && (vc == m[i]);
+                            if (lm) {
+                                float early = crow[-1];
 #pragma unroll
-                                    for (int k = 1; k < R; ++k) {
-                                        above = fmaxf(above, F[(u + 1 + k) % P2]);
-                                        below = fmaxf(below, F[(u + R + 2 + k) % P2]);
-                                    }
-                                    const float m = fmaxf(fmaxf(above, below), F[(u + R + 1) % P2]);
-                                    bool lm = (vc > 0.0f) && (vc == m) && (above < vc);
-                                    if (lm) {  // an equal value to the left in the same row wins the argmax
-                                        const float* crow = V + (size_t)(c + R) * WS + lc;
-                                        float left = crow[-1];
+                                for (int d = 2; d <= R; ++d) early = fmaxf(early, crow[-d]);
 #pragma unroll
-                                        for (int d = 2; d <= R; ++d) left = fmaxf(left, crow[-d]);
-                                        lm = left < vc;
-                                    }
-                                    const unsigned bits = __ballot_sync(0xffffffffu, lm);
-                                    if (lane == 0) LM[(size_t)(c + R) * S + s] = bits;
-                                }
+                                for (int k = 0; k < R; ++k) early = fmaxf(early, a[i + k]);
+                                lm = early < vc;
                             }
+                            const uint32_t lb = __ballot_sync(0xffffffffu, lm);
+                            const uint32_t pb = __ballot_sync(0xffffffffu, pos);
+                            if (lane == i) { lm_mine = lb; pos_mine = pb; }
+                        }
+                        if (lane < 8 && r0 + lane < nrows) {
+                            LM[(size_t)(r0 + lane + R) * S + s] = lm_mine;
+                            PS[(size_t)(r0 + lane + R) * S + s] = pos_mine;
                         }
                     }
                 }
@@ -309,7 +436,7 @@ __global__ void __launch_bounds__(kThreads, 1) detect_kernel(const DetectParams 
                 for (int e = tid; e < n; e += kThreads) {
                     const unsigned ent = wl0[wl_cur * kWorklistCap + e];
                     const int lr = (int)(ent >> 16), x = (int)(ent & 0xffffu);
-                    const float* crow = V + (size_t)(lr + R) * WS + x + R;
+                    const float* crow = V + (size_t)(lr + R) * WS + x + PAD;
                     const float vc = crow[0];
                     float emax = 0.0f, lmax = 0.0f;  // raster-earlier / raster-later halves of the window
 #pragma unroll
@@ -329,6 +456,7 @@ __global__ void __launch_bounds__(kThreads, 1) detect_kernel(const DetectParams 
                 }
             }
             if (!SMEM) __threadfence();
+            EINX_TRACE(trace_slot); ++trace_slot;
             cluster.sync();  // S2: own-row maxima bits are ready in every band
             if (SMEM) {
                 if (rank > 0) {
@@ -344,70 +472,65 @@ __global__ void __launch_bounds__(kThreads, 1) detect_kernel(const DetectParams 
             const int wl_next = wl_cur ^ 1;
             if (tid == 0) sh.wl_n[wl_next] = 0;
             __syncthreads();
+            EINX_TRACE(trace_slot); ++trace_slot;
             int und = 0;
             if (!wl_mode) {
-                // horizontal dilation of the maxima bits, on words.  In the global variant only own
-                // rows are stored; halo rows are recomputed by the consumer below.
-                for (int i = tid; i < (nrows + 2 * R) * S; i += kThreads) {
-                    const int row = i / S, s = i - row * S;
-                    const int yy = ys - R + row;
-                    uint32_t acc = 0;
-                    if (yy >= 0 && yy < Hp) {
-                        const uint32_t w = LM[i];
-                        const uint32_t wl = s > 0 ? LM[i - 1] : 0u;
-                        const uint32_t wr = s < S - 1 ? LM[i + 1] : 0u;
-                        acc = w;
+                // horizontal dilation of the maxima bits, on words, for every local row
+                for (int t = tid; t < (nrows + 2 * R) * S; t += kThreads) {
+                    const int rr = (int)__umulhi((unsigned)t, P.magic_s);
+                    const int s = t - rr * S;
+                    const size_t i = (size_t)rr * S + s;
+                    const uint32_t w = LM[i];
+                    const uint32_t wl = s > 0 ? LM[i - 1] : 0u;
+                    const uint32_t wr = s < S - 1 ? LM[i + 1] : 0u;
+                    uint32_t acc = w;
 #pragma unroll
-                        for (int d = 1; d <= R; ++d) acc |= (w >> d) | (wr << (32 - d)) | (w << d) | (wl >> (32 - d));
+                    for (int d = 1; d <= R; ++d) acc |= (w >> d) | (wr << (32 - d)) | (w << d) | (wl >> (32 - d));
+                    RD[i] = acc;
+                }
+            }
+            if (!wl_mode) {
+                __syncthreads();
+                EINX_TRACE(trace_slot); ++trace_slot;
+                // suppression set + undecided census per own word; the undecided pixels become the
+                // next round's worklist
+                for (int t = tid; t < nrows * S; t += kThreads) {
+                    const int lr = (int)__umulhi((unsigned)t, P.magic_s);
+                    const int s = t - lr * S;
+                    uint32_t dil = 0;
+#pragma unroll
+                    for (int dy = 0; dy < P2; ++dy) dil |= RD[(size_t)(lr + dy) * S + s];
+                    const size_t i = (size_t)(lr + R) * S + s;
+                    const uint32_t posw = PS[i];
+                    const uint32_t sup = dil & ~LM[i] & posw;  // positive pixels a neighbouring maximum suppresses
+                    uint32_t u = posw & ~dil;                   // positive, not a maximum, not suppressed
+                    PS[i] = sup;
+                    if (u) {
+                        und = 1;
+                        int pos = atomicAdd(&sh.wl_n[wl_next], __popc(u));
+                        while (u) {
+                            const int bit = __ffs(u) - 1;
+                            u &= u - 1;
+                            if (pos < kWorklistCap) wl0[wl_next * kWorklistCap + pos] = ((unsigned)lr << 16) | (unsigned)(32 * s + bit);
+                            ++pos;
+                        }
                     }
-                    if (SMEM || (row >= R && row < R + nrows)) RD[i] = acc;
                 }
                 __syncthreads();
-                // suppression + undecided census (the undecided pixels also go to the next worklist)
-                for (int wi = warp, lr = warp / S, s = warp - (warp / S) * S; wi < nrows * S; wi += kWarps) {
-                    if (wi != warp) {  // advance (lr, s) by kWarps words without dividing
-                        s += kWarps;
-                        while (s >= S) { s -= S; ++lr; }
-                    }
-                    uint32_t part = 0;
-                    if (lane <= 2 * R) {
-                        const int row = lr + lane;  // local rows lr .. lr+2R  (centre lr+R)
-                        if (SMEM || (row >= R && row < R + nrows)) {
-                            part = RD[(size_t)row * S + s];
-                        } else {
-                            const int yy = ys - R + row;
-                            if (yy >= 0 && yy < Hp) {
-                                const size_t i = (size_t)row * S + s;
-                                const uint32_t w = LM[i];
-                                const uint32_t wl = s > 0 ? LM[i - 1] : 0u;
-                                const uint32_t wr = s < S - 1 ? LM[i + 1] : 0u;
-                                part = w;
-#pragma unroll
-                                for (int d = 1; d <= R; ++d)
-                                    part |= (w >> d) | (wr << (32 - d)) | (w << d) | (wl >> (32 - d));
-                            }
-                        }
-                    }
-                    const uint32_t dil = __reduce_or_sync(0xffffffffu, part);
-                    const uint32_t lmw = LM[(size_t)(lr + R) * S + s];
-                    const uint32_t sup = dil & ~lmw;
-                    float* cell = V + (size_t)(lr + R) * WS + 32 * s + lane + R;
-                    const float v = *cell;
-                    const bool is_sup = (sup >> lane) & 1u;
-                    if (is_sup && v != 0.0f) *cell = 0.0f;
-                    const bool u = (v > 0.0f) && !is_sup && !((lmw >> lane) & 1u);
-                    const unsigned ub = __ballot_sync(0xffffffffu, u);
-                    if (ub) {
-                        und = 1;
-                        int basei = 0;
-                        if (lane == 0) {
-                            // a still-undecided pixel keeps its (strip, segment) item alive
-                            item_active[(lr / kSegRows) * S + s] = 2;
-                            basei = atomicAdd(&sh.wl_n[wl_next], __popc(ub));
-                        }
-                        basei = __shfl_sync(0xffffffffu, basei, 0);
-                        const int pos = basei + __popc(ub & ((1u << lane) - 1u));
-                        if (u && pos < kWorklistCap) wl0[wl_next * kWorklistCap + pos] = ((unsigned)lr << 16) | (unsigned)(32 * s + lane);
+                EINX_TRACE(trace_slot); ++trace_slot;
+                // apply: zero the suppressed pixels, 4 at a time
+                for (int t = tid; t < nrows * CH; t += kThreads) {
+                    const int lr = (int)__umulhi((unsigned)t, P.magic_ch);
+                    const int ch = t - lr * CH;
+                    const uint32_t bits = (PS[(size_t)(lr + R) * S + (ch >> 3)] >> ((ch & 7) * 4)) & 0xfu;
+                    if (bits) {
+                        float4* cell = reinterpret_cast<float4*>(V + (size_t)(lr + R) * WS + PAD) + ch;
+                        float4 v = *cell;
+                        if (bits & 1u) v.x = 0.0f;
+                        if (bits & 2u) v.y = 0.0f;
+                        if (bits & 4u) v.z = 0.0f;
+                        if (bits & 8u) v.w = 0.0f;
+                        *cell = v;
                     }
                 }
             } else {
@@ -430,7 +553,7 @@ __global__ void __launch_bounds__(kThreads, 1) detect_kernel(const DetectParams 
                         any |= (uint32_t)(both >> sh_) & ((1u << P2) - 1u);
                     }
                     if (any) {
-                        V[(size_t)(lr + R) * WS + x + R] = 0.0f;
+                        V[(size_t)(lr + R) * WS + x + PAD] = 0.0f;
                     } else {
                         const int pos = atomicAdd(&sh.wl_n[wl_next], 1);
                         wl0[wl_next * kWorklistCap + pos] = ent;  // pos < n <= kWorklistCap
@@ -439,9 +562,8 @@ __global__ void __launch_bounds__(kThreads, 1) detect_kernel(const DetectParams 
                 }
             }
             und = __syncthreads_or(und);
-            // 2 = touched this round, 1 = stale from the previous round
-            for (int i = tid; i < nitems; i += kThreads) item_active[i] = item_active[i] == 2 ? 1 : 0;
-            wl_mode = (round >= 1) && (sh.wl_n[wl_next] <= kWorklistCap);
+            EINX_TRACE(trace_slot); ++trace_slot;
+            wl_mode = sh.wl_n[wl_next] <= kWorklistCap;
             wl_cur = wl_next;
             if (tid == 0) sh.flags[round & 1] = und;
             if (!SMEM) __threadfence();
@@ -451,13 +573,14 @@ __global__ void __launch_bounds__(kThreads, 1) detect_kernel(const DetectParams 
         __syncthreads();
         for (int wi = warp; wi < nrows * S; wi += kWarps) {
             const int lr = wi / S, s = wi - lr * S;
-            const float v = V[(size_t)(lr + R) * WS + 32 * s + lane + R];
+            const float v = V[(size_t)(lr + R) * WS + 32 * s + lane + PAD];
             const unsigned bits = __ballot_sync(0xffffffffu, v > 0.0f);
             if (lane == 0) LM[(size_t)(lr + R) * S + s] = bits;
         }
         __syncthreads();
     }
 
+    EINX_TRACE(120);
     // ---- survivors -> ordered per-image list (global workspace) ------------------------------ //
     // At the fixpoint every positive pixel is a local maximum, so the maxima bits of the last
     // round are exactly the survivors.
@@ -494,7 +617,7 @@ __global__ void __launch_bounds__(kThreads, 1) detect_kernel(const DetectParams 
                     bits &= bits - 1;
                     const int x = 32 * s + bit;
                     if (pos < P.scap) {
-                        slist[pos] = V[(size_t)(lr + R) * WS + x + R];
+                        slist[pos] = V[(size_t)(lr + R) * WS + x + PAD];
                         sidx[pos] = (ys + lr) * Wp + x;
                     }
                     ++pos;
@@ -504,7 +627,9 @@ __global__ void __launch_bounds__(kThreads, 1) detect_kernel(const DetectParams 
         }
     }
     __threadfence();
+    EINX_TRACE(121);
     cluster.sync();  // the whole image's list is visible
+    EINX_TRACE(122);
 
     // ---- threshold (detector_util.py:108-133), computed redundantly by every CTA ------------ //
     float thr = P.prob_thresh;
@@ -527,6 +652,7 @@ __global__ void __launch_bounds__(kThreads, 1) detect_kernel(const DetectParams 
         thr = fminf(thr_k, P.prob_thresh);
     }
 
+    EINX_TRACE(123);
     // ---- keypoint rows in raster order + optional dense map ---------------------------------- //
     {
         int c = 0;
@@ -570,11 +696,13 @@ __global__ void __launch_bounds__(kThreads, 1) detect_kernel(const DetectParams 
         float* out = P.nms_map + (size_t)b * Hp * Wp;
         for (int e = tid; e < nrows * Wp; e += kThreads) {
             const int lr = e / Wp, x = e - lr * Wp;
-            const float v = V[(size_t)(lr + R) * WS + x + R];
+            const float v = V[(size_t)(lr + R) * WS + x + PAD];
             out[(size_t)(ys + lr) * Wp + x] = v > thr ? v : 0.0f;
         }
     }
+    EINX_TRACE(124);
     cluster.sync();  // nobody leaves while a neighbour may still read its shared memory
+    EINX_TRACE(125);
 }
 
 template <int R, bool SMEM>
@@ -598,6 +726,17 @@ int launch_detect(einx_ctx* ctx, const DetectParams& P, size_t smem, cudaStream_
     einx_prof_end(ctx, 1, stream);
     EINX_CUDA(ctx, le);
     ctx->launches++;
+    if (P.trace) {  // developer aid: print the phase timeline of CTA 0 (synchronises)
+        long long h[128];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h, P.trace, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[einx_detect trace] CS=%d smem=%zu:", P.CS, smem);
+        long long prev = h[0];
+        for (int i = 0; i < 128; ++i)
+            if (h[i]) { fprintf(stderr, " %d:+%lld", i, h[i] - prev); prev = h[i]; }
+        fprintf(stderr, "\n");
+        cudaMemset(P.trace, 0, sizeof(h));
+    }
     return EINX_OK;
 }
 
@@ -646,7 +785,11 @@ extern "C" int einx_detect(einx_ctx* ctx, float* score, const uint8_t* mask, int
     P.score = score; P.mask = mask; P.nms_map = nms_map; P.kpts = kpts; P.counts = counts;
     P.B = B; P.Hp = Hp; P.Wp = Wp; P.border = border; P.kcap = kcap;
     P.S = (Wp + 31) / 32;
-    P.WS = 32 * P.S + 2 * R;
+    const int PAD = (R + 3) / 4 * 4;
+    P.WS = 32 * P.S + 2 * PAD;
+    P.magic_s = (unsigned)((0x100000000ull + P.S - 1) / P.S);
+    P.magic_ch = (unsigned)((0x100000000ull + 8 * P.S - 1) / (8 * P.S));
+    P.vec4 = (Wp % 4 == 0) && ((uintptr_t)score % 16 == 0) && (!mask || (uintptr_t)mask % 4 == 0);
     P.prob_thresh = prob_thresh;
     const int n = Hp * Wp;
     if (top_k > 0) {
@@ -655,19 +798,17 @@ extern "C" int einx_detect(einx_ctx* ctx, float* score, const uint8_t* mask, int
     }
     P.scap = R == 0 ? n : ((Hp + R) / (R + 1)) * ((Wp + R) / (R + 1));
 
-    // pick the cluster size: smallest that fits the band in shared memory, then widen while the
-    // machine would otherwise sit idle
+    // pick the cluster size: smallest that fits the band (values, row maxima, three bitmaps) in
+    // shared memory, then widen while the machine would otherwise sit idle
     const size_t fixed = align_up(sizeof(Shared), 16);
-    const size_t row_bytes = (size_t)P.WS * 4 + (size_t)P.S * 8;
-    auto smem_for = [&](int rb) {
-        const int nseg = (rb + kSegRows - 1) / kSegRows;
-        return fixed + row_bytes * (size_t)(rb + 2 * R) + align_up((size_t)P.S * nseg, 16);
-    };
+    const size_t row_bytes = (size_t)P.WS * 4 + (size_t)P.S * 32 * 4 + (size_t)P.S * 12;
+    auto smem_for = [&](int rb) { return fixed + row_bytes * (size_t)(rb + 2 * R); };
     const size_t budget = (size_t)ctx->max_smem_optin;
     int CS = 0;
     for (int c = 1; c <= kMaxCluster; ++c) {
         const int rb = (Hp + c - 1) / c;
         if (c > 1 && Hp / c < (R > 0 ? R : 1)) break;
+        if ((long long)(rb + 2 * R) * 8 * P.S >= (1 << 20)) continue;  // magic-number division range
         if (smem_for(rb) <= budget) { CS = c; break; }
     }
     bool use_smem = CS > 0;
@@ -679,31 +820,37 @@ extern "C" int einx_detect(einx_ctx* ctx, float* score, const uint8_t* mask, int
     }
     P.CS = CS;
     P.RBmax = (Hp + CS - 1) / CS;
+    if ((long long)(P.RBmax + 2 * R) * 8 * P.S >= (1 << 20))
+        return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_detect: %dx%d map too large for one cluster", Hp, Wp);
 
-    // workspace: survivor lists (+ padded global image for the large-map variant)
+    // workspace: survivor lists (+ padded global image, row maxima and bitmaps for the large-map variant)
     const size_t list_bytes = align_up((size_t)B * P.scap * 4, 256);
     const size_t wl_bytes = align_up((size_t)B * CS * 2 * kWorklistCap * 4, 256);
     size_t ws_bytes = 2 * list_bytes + wl_bytes;
     const size_t img_rows = (size_t)Hp + 2 * R;
     const size_t gv_bytes = align_up((size_t)B * img_rows * P.WS * 4, 256);
+    const size_t gh_bytes = align_up((size_t)B * img_rows * P.S * 32 * 4, 256);
     const size_t gw_bytes = align_up((size_t)B * img_rows * P.S * 4, 256);
-    if (!use_smem) ws_bytes += gv_bytes + 2 * gw_bytes;
+    if (!use_smem) ws_bytes += gv_bytes + gh_bytes + 3 * gw_bytes;
     int rc = einx_ws_reserve(ctx, ws_bytes);
     if (rc) return rc;
     unsigned char* ws = (unsigned char*)ctx->ws;
     P.surv_val = (float*)ws;
     P.surv_idx = (int32_t*)(ws + list_bytes);
     P.worklists = (unsigned int*)(ws + 2 * list_bytes);
-    size_t smem;
-    if (use_smem) {
-        smem = smem_for(P.RBmax);
-        return dispatch_radius<true>(ctx, R, P, smem, stream);
+    static const bool want_trace = getenv("EINX_DETECT_TRACE") != nullptr;
+    if (want_trace) {
+        static long long* trace_buf = nullptr;
+        if (!trace_buf && cudaMalloc(&trace_buf, 128 * sizeof(long long)) == cudaSuccess) cudaMemset(trace_buf, 0, 128 * sizeof(long long));
+        P.trace = trace_buf;
     }
-    P.gV = (float*)(ws + 2 * list_bytes + wl_bytes);
-    P.gLM = (uint32_t*)(ws + 2 * list_bytes + wl_bytes + gv_bytes);
-    P.gRD = (uint32_t*)(ws + 2 * list_bytes + wl_bytes + gv_bytes + gw_bytes);
-    EINX_CUDA(ctx, cudaMemsetAsync(P.gV, 0, gv_bytes + 2 * gw_bytes, stream));
-    const int nseg = (P.RBmax + kSegRows - 1) / kSegRows;
-    smem = fixed + align_up((size_t)P.S * nseg, 16);
-    return dispatch_radius<false>(ctx, R, P, smem, stream);
+    if (use_smem) return dispatch_radius<true>(ctx, R, P, smem_for(P.RBmax), stream);
+    unsigned char* g = ws + 2 * list_bytes + wl_bytes;
+    P.gV = (float*)g;
+    P.gLM = (uint32_t*)(g + gv_bytes);
+    P.gRD = (uint32_t*)(g + gv_bytes + gw_bytes);
+    P.gPS = (uint32_t*)(g + gv_bytes + 2 * gw_bytes);
+    P.gH = (float*)(g + gv_bytes + 3 * gw_bytes);
+    EINX_CUDA(ctx, cudaMemsetAsync(P.gV, 0, gv_bytes + 3 * gw_bytes, stream));  // zero padding, empty bitmaps
+    return dispatch_radius<false>(ctx, R, P, fixed, stream);
 }
