@@ -108,7 +108,7 @@ __device__ __forceinline__ float bilinear_unnormalize(float p, float size_padded
 }
 
 template <int NJ>  // channel groups of 32 held per lane: C == 32 * NJ exactly, or NJ == kMaxPerLane with guards
-__global__ void __launch_bounds__(kSlabThreads, 2)
+__global__ void __launch_bounds__(kSlabThreads, 3)
 sample_bilinear_slab_kernel(const float* __restrict__ raw, int C, int Hd, int Wd, float Hp, float Wp,
                             const float* __restrict__ kpts, const int32_t* __restrict__ counts, int kcap, float scale,
                             int normalize, float* __restrict__ desc, int SP) {
@@ -120,66 +120,74 @@ sample_bilinear_slab_kernel(const float* __restrict__ raw, int C, int Hd, int Wd
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int cnt = counts[b];
     if (cnt > kcap) cnt = kcap;
-    if (blockIdx.x == 0) {  // padding rows are defined (zero)
-        float* z = desc + ((size_t)b * kcap + cnt) * C;
-        for (size_t i = tid; i < (size_t)(kcap - cnt) * C; i += kSlabThreads) z[i] = 0.0f;
+
+    // ---- stage rows y0, y0+1 of every channel first: one warp per channel, lanes along the 2*Wd
+    // floats, everything in flight at once (cp.async, no register staging); the keypoint scan below
+    // runs while the copies land.  Rows outside the map (y0 = -1, y0+1 = Hd) are zero.
+    const float* img = raw + (size_t)b * C * Hd * Wd;
+    const int row_elems = 2 * Wd;  // <= 128: a lane owns at most 4 elements of a channel
+    const bool oy0 = (y0 >= 0) & (y0 < Hd), oy1 = (y0 + 1 >= 0) & (y0 + 1 < Hd);
+    if (!(oy0 && oy1)) {
+        const int lo = oy0 ? Wd : 0, hi = oy1 ? Wd : row_elems;  // the out-of-map row's span
+        for (int c = warp; c < C; c += kSlabWarps)
+            for (int e = lo + lane; e < hi; e += 32) slab[c * SP + e] = 0.0f;
     }
+    {
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = lane + 32 * u;
+            ok[u] = e < row_elems && (e < Wd ? oy0 : oy1);
+        }
+        const float* src = img + ((ptrdiff_t)warp * Hd + y0) * Wd + lane;  // rows y0 and y0+1 are adjacent in memory
+        const size_t cstep = (size_t)kSlabWarps * Hd * Wd;
+        uint32_t dst = (uint32_t)__cvta_generic_to_shared(slab + warp * SP + lane);
+        const uint32_t dstep = (uint32_t)(kSlabWarps * SP * sizeof(float));
+#pragma unroll 4
+        for (int c = warp; c < C; c += kSlabWarps, src += cstep, dst += dstep) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (ok[u]) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 128u * u), "l"(src + 32 * u) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    if (blockIdx.x == 0) {  // padding rows are defined (zero)
+        float4* z = reinterpret_cast<float4*>(desc + ((size_t)b * kcap + cnt) * C);  // C % 4 == 0 on this path
+        const size_t nz = (size_t)(kcap - cnt) * C / 4;
+        for (size_t i = tid; i < nz; i += kSlabThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    // ---- keypoints are in raster order, so this CTA's keypoints form one contiguous run [first, last]
     const float* kp = kpts + (size_t)b * kcap * 3;
-    // keypoints are in raster order, so this CTA's keypoints form one contiguous run [first, last]
     int first = cnt, last = -1;
-    for (int k = tid; k < cnt; k += kSlabThreads) {
-        const float iy = bilinear_unnormalize(kp[3 * k], Hp, Hd);
-        if ((int)floorf(iy) == y0) { first = min(first, k); last = max(last, k); }
+    for (int base = 0; base < cnt; base += 4 * kSlabThreads) {
+        float py[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {  // all loads in flight before the first use
+            const int k = base + u * kSlabThreads + tid;
+            py[u] = k < cnt ? __ldg(kp + 3 * k) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = base + u * kSlabThreads + tid;
+            if (k < cnt && (int)floorf(bilinear_unnormalize(py[u], Hp, Hd)) == y0) { first = min(first, k); last = max(last, k); }
+        }
     }
     first = __reduce_min_sync(0xffffffffu, first);
     last = __reduce_max_sync(0xffffffffu, last);
     if (lane == 0) { s_first[warp] = first; s_last[warp] = last; }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 #pragma unroll
     for (int w = 0; w < kSlabWarps; ++w) { first = min(first, s_first[w]); last = max(last, s_last[w]); }
     if (last < first) return;
 
-    // stage rows y0, y0+1 of every channel: one warp per channel, lanes along the 2*Wd floats
-    const float* img = raw + (size_t)b * C * Hd * Wd;
-    const int row_elems = 2 * Wd;
-    const bool oy0 = (y0 >= 0) & (y0 < Hd), oy1 = (y0 + 1 >= 0) & (y0 + 1 < Hd);
-    // (cp.async: every element is in flight at once, no register staging -- the loop would
-    // otherwise expose one L2/HBM round trip per channel).  Per-lane element offsets and their
-    // validity are hoisted: row_elems <= 128, so a lane owns at most 4 elements of a channel.
-    {
-        int roff[4];
-        bool rok[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            roff[u] = lane + 32 * u;
-            rok[u] = roff[u] < row_elems && (roff[u] < Wd ? oy0 : oy1);
-            if (roff[u] < row_elems && !rok[u])  // out-of-map row: zero once per channel below
-                rok[u] = false;
-        }
-        const bool zero_any = !(oy0 && oy1);
-        const float* src = img + ((ptrdiff_t)warp * Hd + y0) * Wd;  // rows y0 and y0+1 are adjacent in memory
-        const size_t cstep = (size_t)kSlabWarps * Hd * Wd;
-        uint32_t dst = (uint32_t)__cvta_generic_to_shared(slab + warp * SP);
-        const uint32_t dstep = (uint32_t)(kSlabWarps * SP * sizeof(float));
-        for (int c = warp; c < C; c += kSlabWarps, src += cstep, dst += dstep) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (rok[u])
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * roff[u]), "l"(src + roff[u]) : "memory");
-                else if (zero_any && roff[u] < row_elems)
-                    slab[c * SP + roff[u]] = 0.0f;
-            }
-        }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-
     for (int base = first; base <= last; base += kSlabThreads) {
-        __syncthreads();  // slab staged (first pass) / taps consumed (later passes)
+        if (base != first) __syncthreads();  // taps consumed by the previous pass
         const int k = base + tid;
         if (k <= last) {
-            const float iy = bilinear_unnormalize(kp[3 * k], Hp, Hd);
-            const float ix = bilinear_unnormalize(kp[3 * k + 1], Wp, Wd);
+            const float iy = bilinear_unnormalize(__ldg(kp + 3 * k), Hp, Hd);
+            const float ix = bilinear_unnormalize(__ldg(kp + 3 * k + 1), Wp, Wd);
             const float fy = floorf(iy), fx = floorf(ix);
             const int x0 = (int)fx;
             const float wy1 = __fsub_rn(iy, fy), wx1 = __fsub_rn(ix, fx);
@@ -262,7 +270,7 @@ extern "C" int einx_sample(einx_ctx* ctx, const float* raw, int B, int C, int Hd
         // channels, so an odd channel pitch makes every tap conflict-free)
         const int SP = (2 * Wd) | 1;
         const size_t slab_bytes = (size_t)C * SP * sizeof(float);
-        if (slab_bytes <= 100 * 1024 && Hd + 1 <= 65535 && 2 * Wd <= 128) {
+        if (slab_bytes <= 100 * 1024 && Hd + 1 <= 65535 && 2 * Wd <= 128 && C % 4 == 0) {
             auto launch = [&](auto kern) -> cudaError_t {
                 cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slab_bytes);
                 if (e != cudaSuccess) return e;

@@ -90,6 +90,32 @@ def test_voxel_edge_cases(einx):
     assert voxel_ok(got, ref, l1).all()
 
 
+@pytest.mark.parametrize("bins,H,W", [(5, 180, 240), (5, 260, 346), (8, 96, 128), (3, 700, 400)])
+def test_voxel_unsorted_and_tiny_windows(einx, synth, bins, H, W):
+    """The fused cluster path finds each bin's events by searching the time-sorted window; unsorted
+    windows (checked on the device) and windows of a handful of events must still match."""
+    rng = np.random.default_rng(11)
+    batch = [synth.events(rng, 30_000, H, W, "mvsec"), synth.events(rng, 20_000, H, W, "ec")]
+    perm = rng.permutation(20_000)
+    batch[1] = {k: v[perm] for k, v in batch[1].items()}  # unsorted: t[0] / t[-1] are no longer min / max
+    for n in (2, 3, 7, 1500):
+        batch.append(synth.events(rng, n, H, W, "mvsec"))
+    same_t = synth.events(rng, 50, H, W, "mvsec")
+    same_t["t"][10:40] = same_t["t"][10]  # a run of equal timestamps
+    batch.append(same_t)
+    for normalize in (False, True):
+        got = einx.voxelize_batch(batch, (bins, H, W), normalize=normalize, device=DEV).cpu().numpy()
+        for i, ev in enumerate(batch):
+            ref, l1 = O.events_to_voxel_grid(ev["x"], ev["y"], ev["t"], ev["p"], bins, H, W, False, return_l1=True)
+            if not normalize:
+                assert voxel_ok(got[i], ref, l1).all(), (i, normalize)
+            else:
+                refn = O.normalize_nonzero(ref)
+                mask = (ref != 0) & (np.abs(ref) > 1e-6 * l1)  # cells that cancel to ~0 may flip the != 0 mask
+                ok = np.abs(got[i] - refn) <= 2e-5 * np.maximum(np.abs(refn), 1.0)
+                assert ok[mask].mean() > 0.9999, (i, normalize)
+
+
 # ------------------------------------------------------------------ detection ------- #
 def _detect_cases(g):
     for tag in g["tags"]:
