@@ -14,9 +14,13 @@
 // Dense rounds are separable: pass A takes the horizontal window maximum of 4 pixels per thread from
 // float4 loads, pass B the vertical one of 8 rows per thread and decides the pixel; suppression is a
 // dilation of the maxima bitmap on 32-bit words.  As soon as the undecided pixels of a band fit the
-// worklist (after round 0 on i.i.d. maps: 3.7 %), rounds visit those pixels only.  The loop ends when
-// no pixel of the image is undecided -- the same fixpoint the reference reaches when its batch-wide
-// count of maxima stops changing.
+// worklist (i.i.d. maps: 21 % undecided after round 0, 4 % after round 1, 0.4 %, ...), rounds visit those
+// pixels only.  The worklists live in the shared-memory rows of the horizontal maxima, which are dead
+// outside the dense passes, so a round writes nothing to global memory and the cluster barriers have
+// no stores to drain.  (Measured and rejected: following only the still-positive neighbours through a
+// bitmap in worklist rounds -- the dependent bit-scan/load chains cost 4x the 81 independent loads.)
+// The loop ends when no pixel of the image is undecided -- the same fixpoint the reference reaches
+// when its batch-wide count of maxima stops changing.
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
@@ -43,6 +47,7 @@ struct DetectParams {
     int WS;      // padded row stride of V in floats: 32*S + 2*PAD
     int RBmax;   // max own rows of a band
     int vec4;    // rows of `score` (and `mask`) can be moved as float4 (uchar4)
+    int wl_smem; // worklists alias the shared-memory row maxima (bands large enough to host them)
     unsigned magic_s, magic_ch;  // ceil(2^32 / S), ceil(2^32 / (8*S)): t / S == umulhi(t, magic_s) for t < 2^20
     float prob_thresh;
     int use_topk;  // 1: threshold from order statistics rank_lo / rank_hi; 2: top_k >= n (thr_k = 0)
@@ -107,14 +112,29 @@ __device__ __forceinline__ int block_excl_scan(int v, int* scratch, int& total) 
 __device__ void select_two(const float* __restrict__ list, int n, int j, bool need_next, Shared& sh, float& a_out,
                            float& b_out) {
     if (threadIdx.x == 0) { sh.sel_prefix = 0; sh.sel_rank = (unsigned)j; }
+    // the usual list (a few thousand survivors) is read from L2 once and kept in registers
+    constexpr int kHeld = 4;
+    const bool held = n <= kHeld * kThreads;
+    unsigned ev[kHeld];
+#pragma unroll
+    for (int u = 0; u < kHeld; ++u) {
+        const int i = threadIdx.x + u * kThreads;
+        ev[u] = (held && i < n) ? __float_as_uint(__ldcg(list + i)) : 0u;
+    }
     unsigned mask = 0;
     for (int shift = 24; shift >= 0; shift -= 8) {
         for (int i = threadIdx.x; i < 256; i += kThreads) sh.hist[i] = 0;
         __syncthreads();
         const unsigned prefix = sh.sel_prefix;
-        for (int i = threadIdx.x; i < n; i += kThreads) {
-            const unsigned e = __float_as_uint(__ldcg(list + i));
-            if ((e & mask) == prefix) atomicAdd(&sh.hist[(e >> shift) & 255u], 1u);
+        if (held) {
+#pragma unroll
+            for (int u = 0; u < kHeld; ++u)
+                if (threadIdx.x + u * kThreads < n && (ev[u] & mask) == prefix) atomicAdd(&sh.hist[(ev[u] >> shift) & 255u], 1u);
+        } else {
+            for (int i = threadIdx.x; i < n; i += kThreads) {
+                const unsigned e = __float_as_uint(__ldcg(list + i));
+                if ((e & mask) == prefix) atomicAdd(&sh.hist[(e >> shift) & 255u], 1u);
+            }
         }
         __syncthreads();
         if (threadIdx.x < 32) {
@@ -152,10 +172,19 @@ __device__ void select_two(const float* __restrict__ list, int n, int j, bool ne
         if (threadIdx.x == 0) { sh.sel_min = 0xffffffffu; sh.sel_cnt = 0; }
         __syncthreads();
         unsigned cnt = 0, mn = 0xffffffffu;
-        for (int i = threadIdx.x; i < n; i += kThreads) {
-            const unsigned e = __float_as_uint(__ldcg(list + i));
-            if (e <= abits) cnt++;
-            else mn = min(mn, e);
+        if (held) {
+#pragma unroll
+            for (int u = 0; u < kHeld; ++u)
+                if (threadIdx.x + u * kThreads < n) {
+                    if (ev[u] <= abits) cnt++;
+                    else mn = min(mn, ev[u]);
+                }
+        } else {
+            for (int i = threadIdx.x; i < n; i += kThreads) {
+                const unsigned e = __float_as_uint(__ldcg(list + i));
+                if (e <= abits) cnt++;
+                else mn = min(mn, e);
+            }
         }
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         mn = __reduce_min_sync(0xffffffffu, mn);
@@ -339,7 +368,7 @@ __global__ void __launch_bounds__(kThreads, 1) detect_kernel(const DetectParams 
     // ---- NMS rounds ------------------------------------------------------------------------ //
     if constexpr (R > 0) {
         constexpr int P2 = 2 * R + 1;
-        unsigned int* const wl0 = P.worklists + (size_t)blockIdx.x * 2 * kWorklistCap;
+        unsigned int* const wl0 = (SMEM && P.wl_smem) ? reinterpret_cast<unsigned int*>(Hm) : P.worklists + (size_t)blockIdx.x * 2 * kWorklistCap;
         int wl_cur = 0;         // list buffer holding the current undecided set
         bool wl_mode = false;   // CTA-uniform: this round runs on the worklist instead of dense passes
         const int CH = 8 * S;   // float4 chunks per row
@@ -825,7 +854,8 @@ extern "C" int einx_detect(einx_ctx* ctx, float* score, const uint8_t* mask, int
 
     // workspace: survivor lists (+ padded global image, row maxima and bitmaps for the large-map variant)
     const size_t list_bytes = align_up((size_t)B * P.scap * 4, 256);
-    const size_t wl_bytes = align_up((size_t)B * CS * 2 * kWorklistCap * 4, 256);
+    P.wl_smem = use_smem && (size_t)(P.RBmax + 2 * R) * P.S * 32 * 4 >= (size_t)2 * kWorklistCap * 4;
+    const size_t wl_bytes = P.wl_smem ? 0 : align_up((size_t)B * CS * 2 * kWorklistCap * 4, 256);
     size_t ws_bytes = 2 * list_bytes + wl_bytes;
     const size_t img_rows = (size_t)Hp + 2 * R;
     const size_t gv_bytes = align_up((size_t)B * img_rows * P.WS * 4, 256);

@@ -4,7 +4,11 @@
 // Layout in HBM: SoA events (x, y, p fp32; t fp64) for the whole ragged batch, grid
 // (B, bins, H, W) fp32.  The grid of a batch is L2-resident on B200 (C2: 64 x 0.86 MB), so the
 // zero / scatter / stats / apply passes hit L2, and DRAM sees the events once and the grid once.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -16,6 +20,10 @@ __device__ __forceinline__ void red_add(float* addr, float v) {
 }
 __device__ __forceinline__ void red_add2(float* addr, float a, float b) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+__device__ __forceinline__ void red_add4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 struct TimeBase {
@@ -36,11 +44,13 @@ __device__ __forceinline__ TimeBase make_time_base(const double* __restrict__ t,
     return tb;
 }
 
-// One event -> up to 8 corner contributions.  x-adjacent corners go out as one 8-byte vector
-// reduction when the pair is 8-byte aligned; exact-zero weights (integer-pixel EC events) are
-// skipped, which cannot change any cell (0 + 0) nor the `!= 0` normalisation mask.
+// One event -> up to 8 corner contributions.  An L2 reduction costs the same whatever its width
+// (tools/microbench_red.cu), so x-adjacent corners go out as ONE 16-byte vector reduction on the
+// aligned group of four cells that holds both (zeros in the other two lanes: x + 0 = x), unless the
+// pair straddles two groups or the group leaves the buffer [lo, hi).  Exact-zero weights
+// (integer-pixel EC events) are skipped, which cannot change any cell nor the `!= 0` mask.
 __device__ __forceinline__ void splat_event(float* __restrict__ g, float xf, float yf, float tn, float pf,
-                                            int bins, int H, int W) {
+                                            int bins, int H, int W, const float* lo, const float* hi) {
     if (tn != tn) return;  // 0/0 time span: the reference's NaN bin index is out of range
     const float pol = pf < 1.0f ? -1.0f : pf;  // value[value < 1] = -1   (:88-89)
     const int x0 = (int)xf, y0 = (int)yf, t0 = (int)tn;  // .int() truncates (:83-85)
@@ -63,7 +73,12 @@ __device__ __forceinline__ void splat_event(float* __restrict__ g, float xf, flo
             const float w1 = vx1 ? __fmul_rn(a1, wt) : 0.0f;
             if (w0 == 0.0f && w1 == 0.0f) continue;
             float* cell = g + ((size_t)tl * H + yl) * W + x0;
-            if (vx0 && vx1 && ((reinterpret_cast<uintptr_t>(cell) & 7u) == 0)) {
+            const unsigned off = (unsigned)(reinterpret_cast<uintptr_t>(cell) & 15u) >> 2;  // x0's slot in its group
+            float* group = cell - off;
+            if (vx0 && vx1 && off < 3u && group >= lo && group + 4 <= hi && w0 != 0.0f && w1 != 0.0f) {
+                red_add4(group, off == 0 ? w0 : 0.0f, off == 0 ? w1 : (off == 1 ? w0 : 0.0f),
+                         off == 1 ? w1 : (off == 2 ? w0 : 0.0f), off == 2 ? w1 : 0.0f);
+            } else if (vx0 && vx1 && ((reinterpret_cast<uintptr_t>(cell) & 7u) == 0)) {
                 red_add2(cell, w0, w1);
             } else {
                 if (w0 != 0.0f) red_add(cell, w0);
@@ -83,6 +98,7 @@ voxel_scatter_kernel(const float* __restrict__ x, const float* __restrict__ y, c
     const TimeBase tb = make_time_base(t, beg, end);
     const float bm1 = (float)(bins - 1);
     float* g = out + (size_t)b * bins * H * W;
+    const float* out_end = out + (size_t)gridDim.y * bins * H * W;
     const int64_t stride = (int64_t)gridDim.x * kScatterThreads * kEventsPerThread;
     for (int64_t base = beg + (int64_t)blockIdx.x * kScatterThreads * kEventsPerThread; base < end; base += stride) {
         float xf[kEventsPerThread], yf[kEventsPerThread], pf[kEventsPerThread];
@@ -103,7 +119,7 @@ voxel_scatter_kernel(const float* __restrict__ x, const float* __restrict__ y, c
             if (i >= end) continue;
             const float tf = (float)((td[k] - tb.t0) / tb.denom);                          // :19-20, :76
             const float tn = __fdiv_rn(__fmul_rn(bm1, __fsub_rn(tf, tb.tf0)), tb.span);  // :81
-            splat_event(g, xf[k], yf[k], tn, pf[k], bins, H, W);
+            splat_event(g, xf[k], yf[k], tn, pf[k], bins, H, W, out, out_end);
         }
     }
 }
@@ -195,6 +211,85 @@ voxel_apply_kernel(float* __restrict__ grid, size_t ncell, const double* __restr
     }
 }
 
+// ---- normalisation, fused: one thread-block cluster per window ------------------------------- //
+// Each CTA of the cluster pulls its slice of the window's grid (L2-resident after the scatter) into
+// shared memory once, the (count, sum, sum of squares) of the non-zero cells is reduced across the
+// cluster through DSMEM, and the slice is normalised out of shared memory: the grid is read once and
+// written once, with no statistics buffer, memset or second launch.
+constexpr int kNormThreads = 512;
+
+struct NormShared {
+    double red[3][kNormThreads / 32];
+    double part[3];
+};
+
+__global__ void __launch_bounds__(kNormThreads)
+voxel_norm_cluster_kernel(float* __restrict__ grid, size_t ncell, int slice) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CS = (int)cluster.num_blocks(), r = (int)cluster.block_rank();
+    const int b = blockIdx.x / CS;
+    extern __shared__ __align__(16) unsigned char norm_raw[];
+    NormShared& sh = *reinterpret_cast<NormShared*>(norm_raw);
+    float* buf = reinterpret_cast<float*>(norm_raw + align_up(sizeof(NormShared), 16));
+    const size_t start = (size_t)r * slice;
+    const int n = start < ncell ? (int)min((size_t)slice, ncell - start) : 0;  // slice % 4 == 0, ncell % 4 == 0
+    float4* g4 = reinterpret_cast<float4*>(grid + (size_t)b * ncell + start);
+    float4* b4 = reinterpret_cast<float4*>(buf);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double cn = 0.0, cs = 0.0, css = 0.0;
+    for (int i = tid; i < n / 4; i += kNormThreads) {
+        const float4 v = g4[i];
+        b4[i] = v;
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (e[k] != 0.0f) { cn += 1.0; cs += (double)e[k]; css += (double)e[k] * (double)e[k]; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cn += __shfl_xor_sync(0xffffffffu, cn, o);
+        cs += __shfl_xor_sync(0xffffffffu, cs, o);
+        css += __shfl_xor_sync(0xffffffffu, css, o);
+    }
+    if (lane == 0) { sh.red[0][warp] = cn; sh.red[1][warp] = cs; sh.red[2][warp] = css; }
+    __syncthreads();
+    if (tid < 3) {
+        double a = 0.0;
+        for (int w = 0; w < kNormThreads / 32; ++w) a += sh.red[tid][w];
+        sh.part[tid] = a;
+    }
+    cluster.sync();
+    double wn = 0.0, ws = 0.0, wss = 0.0;
+    for (int q = 0; q < CS; ++q) {  // same order in every CTA: identical statistics
+        const double* pq = cluster.map_shared_rank(sh.part, q);
+        wn += pq[0]; ws += pq[1]; wss += pq[2];
+    }
+    cluster.sync();  // peers have read this CTA's partials: it may exit
+    if (wn <= 0.0) return;
+    const double mean_d = ws / wn;
+    const float mean = (float)mean_d;
+    // unbiased std (torch.Tensor.std); a single cell gives nan, which fails `std > 0` (:118-121)
+    float sd = nanf("");
+    if (wn > 1.0) {
+        const double var = (wss - wn * mean_d * mean_d) / (wn - 1.0);
+        sd = (float)sqrt(var > 0.0 ? var : 0.0);
+    }
+    const bool divide = sd > 0.0f;
+    for (int i = tid; i < n / 4; i += kNormThreads) {
+        const float4 v = b4[i];
+        float e[4] = {v.x, v.y, v.z, v.w};
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (e[k] != 0.0f) {
+                const float c = __fsub_rn(e[k], mean);
+                e[k] = divide ? __fdiv_rn(c, sd) : c;
+                any = true;
+            }
+        if (any) g4[i] = make_float4(e[0], e[1], e[2], e[3]);
+    }
+}
+
 }  // namespace
 
 extern "C" int einx_voxelize(einx_ctx* ctx, const float* x, const float* y, const double* t, const float* p,
@@ -220,6 +315,36 @@ extern "C" int einx_voxelize(einx_ctx* ctx, const float* x, const float* y, cons
     voxel_scatter_kernel<<<dim3(per_window, B), kScatterThreads, 0, stream>>>(x, y, t, p, ev_offsets, bins, H, W, out);
     einx_prof_end(ctx, 0, stream);
     EINX_CHECK_LAUNCH(ctx);
+    if (normalize && (ncell & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+        // fused path: smallest cluster whose slices fit shared memory
+        const size_t fixed = align_up(sizeof(NormShared), 16);
+        int CS = 0;
+        // (two CTAs per SM: with one 225 KB CTA per SM -- MVSEC grids -- the two-kernel path below is faster)
+        for (int c = 1; c <= 8; c *= 2) {
+            const size_t slice = align_up((ncell + c - 1) / c, 4);
+            if (slice * 4 <= (size_t)110 * 1024) { CS = c; break; }
+        }
+        if (CS) {
+            const int slice = (int)align_up((ncell + CS - 1) / CS, 4);
+            const size_t smem = fixed + (size_t)slice * 4;
+            EINX_CUDA(ctx, cudaFuncSetAttribute(voxel_norm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(B * CS);
+            cfg.blockDim = dim3(kNormThreads);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = CS;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            EINX_CUDA(ctx, cudaLaunchKernelEx(&cfg, voxel_norm_cluster_kernel, out, ncell, slice));
+            ctx->launches++;
+            return EINX_OK;
+        }
+    }
     if (normalize) {
         int rc = einx_ws_reserve(ctx, sizeof(double) * 3 * B);
         if (rc) return rc;
