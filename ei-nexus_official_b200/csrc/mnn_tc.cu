@@ -28,7 +28,9 @@ namespace {
 constexpr int TILE_M = 128;          // rows of d0 per tile  (UMMA M, TMEM lanes)
 constexpr int TILE_N = 256;          // rows of d1 per tile  (UMMA N, TMEM columns)
 constexpr int kEpilogueWarp0 = 4;
-constexpr int kThreads = 384;        // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4.. epilogue (+ converters)
+#ifndef EINX_TF32_CONV_WARPS
+#define EINX_TF32_CONV_WARPS 8
+#endif
 constexpr int kScratchPitch = 33;    // floats; 32x32 transpose tile per epilogue warp, conflict-free both ways
 constexpr uint32_t kTmemCols = 512;
 
@@ -48,12 +50,13 @@ struct Cfg {
     static constexpr int kStageBytes = (kABytes + kBBytes) * (kConvert ? 2 : 1);
     static constexpr int kStages = KIND == 0 ? 3 : (192 * 1024) / kStageBytes;
     static constexpr int kEpiWarps = KIND == 0 ? 8 : 4;
-    static constexpr int kConvWarps = kConvert ? 4 : 0;
+    static constexpr int kConvWarps = kConvert ? EINX_TF32_CONV_WARPS : 0;
     static constexpr int kConvWarp0 = kEpilogueWarp0 + kEpiWarps;
     static constexpr int kColsPerWarp = TILE_N / (kEpiWarps / 4);
+    // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4.. epilogue, then converters
+    static constexpr int kThreads = 32 * (kEpilogueWarp0 + kEpiWarps + kConvWarps);
     static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + 256 + 4 * TILE_N * sizeof(unsigned long long) +
                                     (size_t)kEpiWarps * 32 * kScratchPitch * sizeof(float);
-    static_assert(kEpilogueWarp0 + kEpiWarps + kConvWarps <= kThreads / 32, "warp roles exceed the CTA");
     static_assert(kStages <= 4, "Barriers holds 4 stages");
 };
 
@@ -140,7 +143,7 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
             : "memory");
     }
 }
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -151,7 +154,41 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// The registers of an issued load are written asynchronously until wait::ld; passing them through
+// the wait as in/out operands makes every later use depend on it (the compiler cannot hoist one).
+__device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+
+// First-occurrence argmax of 32 register values as a tournament tree: 31 (compare, select value,
+// select index) triples at depth 5 instead of a 32-long dependent chain; the left operand wins ties.
+__device__ __forceinline__ void argmax32(const float (&x)[32], float& val, int& idx) {
+    float a[16];
+    int ia[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const bool p = x[2 * k + 1] > x[2 * k];
+        a[k] = p ? x[2 * k + 1] : x[2 * k];
+        ia[k] = p ? 2 * k + 1 : 2 * k;
+    }
+#pragma unroll
+    for (int n = 8; n >= 1; n >>= 1) {
+#pragma unroll
+        for (int k = 0; k < n; ++k) {
+            const bool p = a[2 * k + 1] > a[2 * k];
+            a[k] = p ? a[2 * k + 1] : a[2 * k];
+            ia[k] = p ? ia[2 * k + 1] : ia[2 * k];
+        }
+    }
+    val = a[0];
+    idx = ia[0];
 }
 
 // K-major operand tile whose rows are one swizzle span (KB = 128 or 64 bytes) wide: 8-row groups are
@@ -176,13 +213,15 @@ __device__ __forceinline__ float tf32_lo(float x) {
 }
 
 template <int KIND, int KB>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(Cfg<KIND, KB>::kThreads, 1)
 mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams P) {
     using C = Cfg<KIND, KB>;
     constexpr int A_BYTES = C::kABytes, B_BYTES = C::kBBytes, STAGES = C::kStages, STAGE_BYTES = C::kStageBytes;
     extern __shared__ __align__(1024) unsigned char smem[];
     // carve: [stages x (A | B [| A lo | B lo])] 1024-aligned, then barriers, then the column-merge buffer
-    unsigned char* tiles = (unsigned char*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
+    // (offset arithmetic on the shared array, not an integer round trip: the compiler must keep the
+    // shared address space, or every access below becomes a generic LD.E/ST.E)
+    unsigned char* tiles = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
     Barriers* bars = reinterpret_cast<Barriers*>(tiles + (size_t)STAGES * STAGE_BYTES);
     unsigned long long* colpart = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(bars) + 256);
     float* scratch_all = reinterpret_cast<float*>(colpart + 4 * TILE_N);
@@ -349,35 +388,44 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * TILE_N + C::kColsPerWarp * part);
             float best = -INFINITY;
             int best_j = 0;
-#pragma unroll 1
-            for (int c = 0; c < C::kColsPerWarp / 32; ++c) {
-                uint32_t v[32];
-                tc_ld32(taddr + 32 * c, v);
+            constexpr int kChunksPerWarp = C::kColsPerWarp / 32;
+            // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is reduced
+            uint32_t v[2][32];
+            tc_ld32_issue(taddr, v[0]);
+#pragma unroll
+            for (int c = 0; c < kChunksPerWarp; ++c) {
+                tc_ld_wait(v[c & 1]);
+                if (c + 1 < kChunksPerWarp) tc_ld32_issue(taddr + 32 * (c + 1), v[(c + 1) & 1]);
                 const int jc = j0 + C::kColsPerWarp * part + 32 * c;
                 if (jc < M) {  // warp-uniform; beyond M the tile is padding
+                    float f[32];
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) {
-                        const float f = __uint_as_float(v[k]);
-                        const bool ok = full_tile || (jc + k < M);
-                        if (ok && f > best) { best = f; best_j = jc + k; }
-                        scratch[lane * kScratchPitch + k] = f;
+                    for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[c & 1][k]);
+                    if (!full_tile) {
+                        // ragged edge: padding columns and rows can never win a strict '>'
+#pragma unroll
+                        for (int k = 0; k < 32; ++k)
+                            if (jc + k >= M || !row_ok) f[k] = -INFINITY;
                     }
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) scratch[lane * kScratchPitch + k] = f[k];
+                    // row: tournament over this thread's 32 columns (left wins ties = lowest column)
+                    float rv;
+                    int rk;
+                    argmax32(f, rv, rk);
+                    if (rv > best) { best = rv; best_j = jc + rk; }
                     __syncwarp();
-                    // two independent scan chains (rows 0-15, 16-31) keep the compare latency hidden
-                    float c0 = -INFINITY, c1 = -INFINITY;
-                    int r0 = 0, r1 = 16;
+                    // column: lane c owns column c of the transposed tile (upper wins ties = lowest row)
+                    float g[32];
 #pragma unroll
-                    for (int r = 0; r < 16; ++r) {
-                        const float x0 = scratch[r * kScratchPitch + lane];
-                        const float x1 = scratch[(r + 16) * kScratchPitch + lane];
-                        if ((full_tile || r < rows_here) && x0 > c0) { c0 = x0; r0 = r; }
-                        if ((full_tile || r + 16 < rows_here) && x1 > c1) { c1 = x1; r1 = r + 16; }
-                    }
-                    if (c1 > c0) { c0 = c1; r0 = r1; }
-                    const bool col_ok = (jc + lane < M) && (c0 > -INFINITY);
+                    for (int r = 0; r < 32; ++r) g[r] = scratch[r * kScratchPitch + lane];
+                    float cv;
+                    int cr;
+                    argmax32(g, cv, cr);
+                    const bool col_ok = (jc + lane < M) && (cv > -INFINITY);
                     colpart[q * TILE_N + C::kColsPerWarp * part + 32 * c + lane] =
-                        col_ok ? (((unsigned long long)f32_orderable(c0 + 0.0f) << 32) |
-                                  (0xffffffffu - (uint32_t)(i0 + 32 * q + r0)))
+                        col_ok ? (((unsigned long long)f32_orderable(cv + 0.0f) << 32) |
+                                  (0xffffffffu - (uint32_t)(i0 + 32 * q + cr)))
                                : 0ull;
                     __syncwarp();  // the tile is rewritten by the next chunk
                 }
@@ -475,7 +523,7 @@ int launch_tc(einx_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const
     const size_t smem = Cfg<KIND, KB>::kSmem;
     EINX_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     einx_prof_begin(ctx, 3, stream);
-    kern<<<grid, kThreads, smem, stream>>>(ma, mb, P);
+    kern<<<grid, Cfg<KIND, KB>::kThreads, smem, stream>>>(ma, mb, P);
     einx_prof_end(ctx, 3, stream);
     EINX_CHECK_LAUNCH(ctx);
     return EINX_OK;

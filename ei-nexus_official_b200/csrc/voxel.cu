@@ -5,6 +5,7 @@
 // (B, bins, H, W) fp32.  The grid of a batch is L2-resident on B200 (C2: 64 x 0.86 MB), so the
 // zero / scatter / stats / apply passes hit L2, and DRAM sees the events once and the grid once.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -290,6 +291,219 @@ voxel_norm_cluster_kernel(float* __restrict__ grid, size_t ncell, int slice) {
     }
 }
 
+
+// ---- shared-memory tile path: one thread-block cluster per window ----------------------------- //
+// CTA (bin, row band) of the cluster keeps its slice of the grid in shared memory.  Events are
+// time-sorted, so the events that touch bin k -- those with t_norm in (k-1, k+1) -- are one contiguous
+// range, found by a warp-wide 32-ary search over the same fp32 expression the splat uses.  The CTA
+// accumulates that range with shared-memory atomics, the cluster exchanges the (count, sum, sum of
+// squares) of its non-zero cells through DSMEM, and every slice is normalised and written to HBM
+// exactly once: no memset, no global reductions, no second pass over the grid.  Each event is read by
+// the (at most two) bins it touches; the second read comes from L2.  Unsorted windows are detected
+// (cluster-wide check of t) and handled by scanning the whole window in every CTA.
+constexpr int kTileThreads = 1024;
+
+struct TileShared {
+    double red[3][kTileThreads / 32];
+    double part[3];
+    int unsorted;
+    long long bound[2];
+};
+
+__device__ __forceinline__ float event_tnorm(double td, const TimeBase& tb, float bm1) {
+    const float tf = (float)((td - tb.t0) / tb.denom);                          // :19-20, :76
+    return __fdiv_rn(__fmul_rn(bm1, __fsub_rn(tf, tb.tf0)), tb.span);           // :81
+}
+
+// first i in [L, R) for which t_norm(i) > bound (STRICT) or >= bound; R if none.  One warp.
+template <bool STRICT>
+__device__ long long tnorm_search(const double* __restrict__ t, long long L, long long R, const TimeBase& tb, float bm1,
+                                  float bound, int lane) {
+    while (R > L) {
+        const long long n = R - L;
+        const long long s = (n + 31) / 32;
+        const long long i = L + (long long)lane * s;
+        bool pr = false;
+        if (i < R) {
+            const float tn = event_tnorm(__ldg(t + i), tb, bm1);
+            pr = STRICT ? (tn > bound) : (tn >= bound);
+        }
+        const unsigned valid = __ballot_sync(0xffffffffu, i < R);
+        const unsigned hit = __ballot_sync(0xffffffffu, pr);
+        if (hit) {
+            const int j = __ffs(hit) - 1;
+            R = L + (long long)j * s;                 // first probe that satisfies the predicate
+            if (j == 0) break;
+            L = L + (long long)(j - 1) * s + 1;       // the probe before it does not
+        } else {
+            const int last = 31 - __clz(valid);
+            L = L + (long long)last * s + 1;
+        }
+        if (s == 1) break;  // probes were consecutive: R is exact
+    }
+    return R;
+}
+
+__device__ __forceinline__ void splat_tile(float* __restrict__ tile, float xf, float yf, float tn, float pf, int bin, int ys,
+                                           int nrows, int W) {
+    if (tn != tn) return;  // 0/0 time span: the reference's NaN bin index is out of range
+    const int t0 = (int)tn;
+    if (t0 != bin && t0 + 1 != bin) return;
+    const float wt = __fsub_rn(1.0f, fabsf(__fsub_rn((float)bin, tn)));
+    const float pol = pf < 1.0f ? -1.0f : pf;
+    const int x0 = (int)xf, y0 = (int)yf;
+    const float wx0 = __fmul_rn(pol, __fsub_rn(1.0f, fabsf(__fsub_rn((float)x0, xf))));
+    const float wx1 = __fmul_rn(pol, __fsub_rn(1.0f, fabsf(__fsub_rn((float)(x0 + 1), xf))));
+    const bool vx0 = (x0 >= 0) & (x0 < W);
+    const bool vx1 = (x0 + 1 >= 0) & (x0 + 1 < W);
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+        const int yl = y0 + dy;
+        const int row = yl - ys;
+        if ((unsigned)row >= (unsigned)nrows) continue;  // band rows lie inside [0, H)
+        const float wy = __fsub_rn(1.0f, fabsf(__fsub_rn((float)yl, yf)));
+        const float w0 = __fmul_rn(__fmul_rn(wx0, wy), wt);
+        const float w1 = __fmul_rn(__fmul_rn(wx1, wy), wt);
+        float* cell = tile + row * W + x0;
+        if (vx0 && w0 != 0.0f) atomicAdd(cell, w0);
+        if (vx1 && w1 != 0.0f) atomicAdd(cell + 1, w1);
+    }
+}
+
+__global__ void __launch_bounds__(kTileThreads, 1)
+voxel_tile_kernel(const float* __restrict__ x, const float* __restrict__ y, const double* __restrict__ t,
+                  const float* __restrict__ p, const int64_t* __restrict__ off, int bins, int H, int W, int bands,
+                  int band_rows, int normalize, float* __restrict__ out) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int b = blockIdx.x / CS;
+    const int bin = rank / bands, band = rank - bin * bands;
+    const int ys = band * band_rows;
+    const int nrows = max(0, min(band_rows, H - ys));
+    const int ncell = nrows * W;
+    extern __shared__ __align__(16) unsigned char tile_raw[];
+    TileShared& sh = *reinterpret_cast<TileShared*>(tile_raw);
+    float* tile = reinterpret_cast<float*>(tile_raw + align_up(sizeof(TileShared), 16));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int i = tid; i < (ncell + 3) / 4; i += kTileThreads) reinterpret_cast<float4*>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    const long long beg = off[b], end = off[b + 1];
+    const long long nev = end - beg;
+    TimeBase tb = {};
+    if (nev > 0) tb = make_time_base(t, beg, end);
+    const float bm1 = (float)(bins - 1);
+
+    // sortedness: this CTA checks its share of adjacent timestamp pairs
+    int bad = 0;
+    if (nev > 1) {
+        const long long pairs = nev - 1, share = (pairs + CS - 1) / CS;
+        const long long s0 = beg + (long long)rank * share, s1 = min(s0 + share, beg + pairs);
+        for (long long i = s0 + tid; i < s1; i += kTileThreads) bad |= (__ldg(t + i) > __ldg(t + i + 1));
+    }
+    bad = __syncthreads_or(bad);  // also orders the tile zeroing before the atomics below
+    if (tid == 0) sh.unsorted = bad;
+    cluster.sync();
+    int unsorted = 0;
+    for (int r = 0; r < CS; ++r) unsorted |= *cluster.map_shared_rank(&sh.unsorted, r);
+
+    long long lo = beg, hi = end;
+    if (!unsorted && nev > 0) {
+        if (warp == 0) {
+            const long long v = bin == 0 ? beg : tnorm_search<true>(t, beg, end, tb, bm1, (float)(bin - 1), lane);
+            if (lane == 0) sh.bound[0] = v;
+        } else if (warp == 1) {
+            const long long v = bin == bins - 1 ? end : tnorm_search<false>(t, beg, end, tb, bm1, (float)(bin + 1), lane);
+            if (lane == 0) sh.bound[1] = v;
+        }
+        __syncthreads();
+        lo = sh.bound[0];
+        hi = sh.bound[1];
+    }
+    if (ncell > 0) {
+        constexpr int U = 4;
+        for (long long base = lo + tid; base < hi; base += (long long)U * kTileThreads) {
+            float xf[U], yf[U], pf[U];
+            double td[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const long long i = base + (long long)k * kTileThreads;
+                const bool ok = i < hi;
+                xf[k] = ok ? __ldg(x + i) : 0.f;
+                yf[k] = ok ? __ldg(y + i) : 0.f;
+                pf[k] = ok ? __ldg(p + i) : 0.f;
+                td[k] = ok ? __ldg(t + i) : tb.t0;
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                if (base + (long long)k * kTileThreads >= hi) continue;
+                splat_tile(tile, xf[k], yf[k], event_tnorm(td[k], tb, bm1), pf[k], bin, ys, nrows, W);
+            }
+        }
+    }
+    __syncthreads();
+
+    // statistics of the non-zero cells of the whole window, through DSMEM
+    double cn = 0.0, cs = 0.0, css = 0.0;
+    if (normalize) {
+        for (int i = tid; i < ncell; i += kTileThreads) {
+            const float e = tile[i];
+            if (e != 0.0f) { cn += 1.0; cs += (double)e; css += (double)e * (double)e; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            cn += __shfl_xor_sync(0xffffffffu, cn, o);
+            cs += __shfl_xor_sync(0xffffffffu, cs, o);
+            css += __shfl_xor_sync(0xffffffffu, css, o);
+        }
+        if (lane == 0) { sh.red[0][warp] = cn; sh.red[1][warp] = cs; sh.red[2][warp] = css; }
+        __syncthreads();
+        if (tid < 3) {
+            double a = 0.0;
+            for (int w = 0; w < kTileThreads / 32; ++w) a += sh.red[tid][w];
+            sh.part[tid] = a;
+        }
+    }
+    cluster.sync();
+    double wn = 0.0, ws = 0.0, wss = 0.0;
+    if (normalize)
+        for (int q = 0; q < CS; ++q) {  // same order in every CTA: identical statistics
+            const double* pq = cluster.map_shared_rank(sh.part, q);
+            wn += pq[0]; ws += pq[1]; wss += pq[2];
+        }
+    cluster.sync();  // peers have read this CTA's flag and partials: it may exit
+    float mean = 0.0f, sd = 1.0f;
+    bool shift = false, divide = false;
+    if (normalize && wn > 0.0) {
+        const double mean_d = ws / wn;
+        mean = (float)mean_d;
+        shift = true;
+        // unbiased std (torch.Tensor.std); a single cell gives nan, which fails `std > 0` (:118-121)
+        sd = nanf("");
+        if (wn > 1.0) {
+            const double var = (wss - wn * mean_d * mean_d) / (wn - 1.0);
+            sd = (float)sqrt(var > 0.0 ? var : 0.0);
+        }
+        divide = sd > 0.0f;
+    }
+    float* dst = out + (((size_t)b * bins + bin) * H + ys) * W;
+    auto fin = [&](float e) {
+        if (shift && e != 0.0f) {
+            const float c = __fsub_rn(e, mean);
+            e = divide ? __fdiv_rn(c, sd) : c;
+        }
+        return e;
+    };
+    if ((ncell & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        for (int i = tid; i < ncell / 4; i += kTileThreads) {
+            const float4 v = reinterpret_cast<const float4*>(tile)[i];
+            __stcs(reinterpret_cast<float4*>(dst) + i, make_float4(fin(v.x), fin(v.y), fin(v.z), fin(v.w)));
+        }
+    } else {
+        for (int i = tid; i < ncell; i += kTileThreads) dst[i] = fin(tile[i]);
+    }
+}
+
 }  // namespace
 
 extern "C" int einx_voxelize(einx_ctx* ctx, const float* x, const float* y, const double* t, const float* p,
@@ -305,6 +519,46 @@ extern "C" int einx_voxelize(einx_ctx* ctx, const float* x, const float* y, cons
     DeviceGuard guard(ctx->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const size_t ncell = (size_t)bins * H * W;
+    // Shared-memory tile path: small sensors whose bin slice fits one CTA (EC 180x240: 169 KB).  With
+    // more than one row band per bin every band re-reads the bin's events, and sub-pixel events cost
+    // four shared-memory CAS loops each, so larger sensors stay on the L2-reduction path below.
+    {
+        static const int tile_env = getenv("EINX_VOXEL_TILE") ? atoi(getenv("EINX_VOXEL_TILE")) : -1;
+        const size_t fixed = align_up(sizeof(TileShared), 16);
+        const size_t budget = (size_t)ctx->max_smem_optin - fixed;
+        int bands = (int)(((size_t)H * W * 4 + budget - 1) / budget);
+        const int band_rows = (H + bands - 1) / bands;
+        bands = (H + band_rows - 1) / band_rows;
+        const int CS = bins * bands;
+        const size_t smem = fixed + align_up((size_t)band_rows * W * 4, 16);
+        bool want = tile_env < 0 ? (bands == 1) : (tile_env != 0);
+        if (want && CS <= 16 && smem <= (size_t)ctx->max_smem_optin && (size_t)B * CS <= 0x7fffffffu) {
+            EINX_CUDA(ctx, cudaFuncSetAttribute(voxel_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (CS > 8) EINX_CUDA(ctx, cudaFuncSetAttribute(voxel_tile_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(B * CS);
+            cfg.blockDim = dim3(kTileThreads);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = CS;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            int max_clusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, voxel_tile_kernel, &cfg) == cudaSuccess && max_clusters > 0) {
+                einx_prof_begin(ctx, 0, stream);
+                EINX_CUDA(ctx, cudaLaunchKernelEx(&cfg, voxel_tile_kernel, x, y, t, p, ev_offsets, bins, H, W, bands, band_rows,
+                                                  normalize, out));
+                einx_prof_end(ctx, 0, stream);
+                ctx->launches++;
+                return EINX_OK;
+            }
+            cudaGetLastError();
+        }
+    }
     EINX_CUDA(ctx, cudaMemsetAsync(out, 0, sizeof(float) * ncell * B, stream));
     // enough CTAs per window to cover the machine a few times over; windows are ragged, so a
     // CTA grid-strides over its own window only
