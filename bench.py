@@ -149,6 +149,8 @@ def workload_config(args, synth):
                     f"{Wp}x{Hp}, top-{c['top_k']} keypoints, {c['D']}-d descriptors, MNN",
         "batch_per_gpu": args.batch, "global_batch": args.batch * args.gpus, "parallelism": f"dp{args.gpus}",
         "mnn_precision": args.precision,
+        "streams": "1 (serial)" if args.serial else "3 (voxelise | side 0 | side 1, joined before MNN)",
+        "e2e_chunks": args.e2e_chunks,
         "l2_policy": f"{NUM_INPUT_SETS} distinct resident input batches rotated between steps (inputs larger than L2)",
     }
 
@@ -267,7 +269,7 @@ def run_einx(args, synth):
     B = args.batch
     Hp, Wp, _ = synth.padded_size(c["H"], c["W"], c["cell"])
     cfg = einx.PathConfig(bins=c["bins"], height=c["H"], width=c["W"], top_k=c["top_k"], descriptor_mode=c["kind"],
-                          descriptor_scale=c["scale"], precision=args.precision)
+                          descriptor_scale=c["scale"], precision=args.precision, concurrent=not args.serial)
     pipe = einx.ExtractMatchPipeline(cfg)
 
     # ---- inputs: pinned host copies (e2e arm) and NUM_INPUT_SETS resident copies (device arm) ----
@@ -276,21 +278,21 @@ def run_einx(args, synth):
     for s in range(NUM_INPUT_SETS):
         first = (rank * NUM_INPUT_SETS + s) * B
         evs, s0, r0, s1, r1 = make_batch(synth, args.config, B, first)
-        ev = einx.pack_events(evs, pin=True)
-        maps = [torch.from_numpy(a).pin_memory() for a in (s0, r0, s1, r1)]
-        host_sets.append((ev, maps))
+        ev = einx.pack_events(evs)
+        maps = [torch.from_numpy(a) for a in (s0, r0, s1, r1)]
+        # e2e arm: the same batch in pinned host memory, as contiguous sub-batches for copy/compute overlap
+        host_sets.append(einx.HostBatch(evs, s0, r0, s1, r1, chunks=args.e2e_chunks))
         dev_sets.append((tuple(t.to(dev) for t in ev), [m.to(dev) for m in maps]))
     log(f"[rank {rank}] generated {NUM_INPUT_SETS} x {B} pairs in {time.time() - t_gen:.1f}s")
-    h2d_bytes = sum(t.numel() * t.element_size() for t in host_sets[0][0]) + \
-        sum(m.numel() * m.element_size() for m in host_sets[0][1])
+    h2d_bytes = host_sets[0].nbytes
 
     def step_device(i):
         ev, (s0, r0, s1, r1) = dev_sets[i % NUM_INPUT_SETS]
         return pipe(ev, s0, r0, s1, r1)
 
-    # staging buffers of the e2e arm
-    stage_ev = tuple(torch.empty_like(t, device=dev) for t in host_sets[0][0])
-    stage_maps = [torch.empty_like(m, device=dev) for m in host_sets[0][1]]
+    # e2e arm: public host-facing API -- every step uploads its events and maps from pinned host memory
+    # (sub-batch i+1 while sub-batch i computes) and reads the matches back into pinned host tensors
+    streamer = einx.HostStreamer(pipe, dev)
     K = c["top_k"]
     out_host = {"matches0": torch.empty((B, K), dtype=torch.int64).pin_memory(),
                 "matching_scores0": torch.empty((B, K), dtype=torch.float32).pin_memory(),
@@ -300,15 +302,7 @@ def run_einx(args, synth):
     d2h_bytes = sum(t.numel() * t.element_size() for t in out_host.values())
 
     def step_e2e(i):
-        ev, maps = host_sets[i % NUM_INPUT_SETS]
-        for d, h in zip(stage_ev, ev):
-            d.copy_(h, non_blocking=True)
-        for d, h in zip(stage_maps, maps):
-            d.copy_(h, non_blocking=True)
-        out = pipe(stage_ev, stage_maps[0], stage_maps[1], stage_maps[2], stage_maps[3])
-        for k, h in out_host.items():
-            h.copy_(out[k], non_blocking=True)
-        return out
+        streamer.run(host_sets[i % NUM_INPUT_SETS], out_host)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -337,9 +331,9 @@ def run_einx(args, synth):
 
     sampler = ClockSampler(local)
     sampler.start()
-    launches0 = ctx.launches
+    launches0 = einx.launch_count(dev)
     ms, window = timed(step_device, args.steps, args.warmup)
-    launches = (ctx.launches - launches0) * args.steps // (args.steps + args.warmup)
+    launches = (einx.launch_count(dev) - launches0) * args.steps // (args.steps + args.warmup)
     sampler.window = list(window)
     ms_e2e, _ = timed(step_e2e, args.steps, max(3, args.warmup))
     sampler.stop_flag = True
@@ -462,6 +456,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="einx", choices=["einx", "reference"])
     ap.add_argument("--config", default="c2_ec_superpoint")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="sub-batches per step of the e2e arm (copy/compute overlap)")
+    ap.add_argument("--serial", action="store_true", help="run the stages of a step on one stream (no fork/join)")
     ap.add_argument("--batch", type=int, default=None, help="pairs per GPU per step")
     ap.add_argument("--precision", default=os.environ.get("EINX_MNN_PRECISION", "tf32x3"), choices=["fp32", "tf32x3", "bf16"],
                     help="MNN arithmetic: tf32x3 (default; fp32-accurate on the tensor pipe), fp32 (FFMA), bf16")

@@ -103,17 +103,35 @@ _contexts = {}
 
 
 def context_for(device) -> Context:
-    """Context of a torch device / ordinal (created on first use)."""
+    """Context of a torch device / ordinal and of the CURRENT stream on it (created on first use).
+
+    One einx_ctx owns one stream-ordered workspace, so kernels issued on different streams must not
+    share it: every (device, stream) pair gets its own context and concurrent streams never alias."""
     import torch
 
     dev = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
     if dev.type != "cuda":
         raise EinxError(f"einx kernels run on CUDA sm_100a only; got device '{dev}'. There is no CPU fallback.")
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
-    ctx = _contexts.get(idx)
+    key = (idx, int(torch.cuda.current_stream(idx).cuda_stream))
+    ctx = _contexts.get(key)
     if ctx is None:
-        ctx = _contexts[idx] = Context(idx)
+        ctx = _contexts[key] = Context(idx)
     return ctx
+
+
+def contexts_of(device):
+    """Every context created so far on a device (one per stream that has run einx kernels)."""
+    import torch
+
+    dev = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    return [c for (d, _), c in _contexts.items() if d == idx]
+
+
+def launch_count(device) -> int:
+    """Kernel launches issued through libeinx on a device, over all of its streams."""
+    return sum(c.launches for c in contexts_of(device))
 
 
 def ptr(t):

@@ -531,7 +531,11 @@ extern "C" int einx_voxelize(einx_ctx* ctx, const float* x, const float* y, cons
         bands = (H + band_rows - 1) / band_rows;
         const int CS = bins * bands;
         const size_t smem = fixed + align_up((size_t)band_rows * W * 4, 16);
-        bool want = tile_env < 0 ? (bands == 1) : (tile_env != 0);
+        // Measured on B200 (C2, B=64; profiles/r1_voxel_tile.txt): 123 us for the whole window set against
+        // 105 us for memset + L2-reduction scatter + cluster normalisation -- with one 170 KB CTA per SM
+        // the zero / search / scan / statistics / flush phases each expose their latency and the
+        // clusters run in 2.5 waves.  The path is therefore opt-in (EINX_VOXEL_TILE=1).
+        const bool want = tile_env > 0;
         if (want && CS <= 16 && smem <= (size_t)ctx->max_smem_optin && (size_t)B * CS <= 0x7fffffffu) {
             EINX_CUDA(ctx, cudaFuncSetAttribute(voxel_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             if (CS > 8) EINX_CUDA(ctx, cudaFuncSetAttribute(voxel_tile_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -578,6 +582,8 @@ extern "C" int einx_voxelize(einx_ctx* ctx, const float* x, const float* y, cons
             const size_t slice = align_up((ncell + c - 1) / c, 4);
             if (slice * 4 <= (size_t)110 * 1024) { CS = c; break; }
         }
+        // small batches: more, smaller CTAs (several per SM) hide the load -> reduce -> store latency chain
+        while (CS && CS < 8 && (size_t)B * CS < (size_t)ctx->num_sms * 3) CS *= 2;
         if (CS) {
             const int slice = (int)align_up((ncell + CS - 1) / CS, 4);
             const size_t smem = fixed + (size_t)slice * 4;

@@ -9,7 +9,7 @@ with per-image counts, exactly the layout the next kernel consumes.  This is the
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Dict, Optional
+from typing import Dict, List, Optional, Sequence
 
 import torch
 
@@ -30,6 +30,7 @@ class PathConfig:
     descriptor_scale: float = 1.0      # 1.0 (SP, D=256) / 1.41 (SiLK, D=128)
     precision: str = "fp32"    # MNN arithmetic: fp32 | tf32x3 | bf16
     normalize_voxels: bool = True
+    concurrent: bool = True    # run voxelisation and the two sides' detect -> sample chains on three streams
 
 
 class ExtractMatchPipeline:
@@ -37,6 +38,7 @@ class ExtractMatchPipeline:
 
     def __init__(self, cfg: PathConfig):
         self.cfg = cfg
+        self._side_streams = {}
 
     @torch.no_grad()
     def voxelize(self, x, y, t, p, offsets) -> torch.Tensor:
@@ -53,13 +55,130 @@ class ExtractMatchPipeline:
         desc = describe.sample(raw, kpts, counts, mode, score.shape[-2:], c.descriptor_scale, True)
         return kpts, counts, desc
 
+    def _streams(self, device):
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        st = self._side_streams.get(key)
+        if st is None:
+            st = self._side_streams[key] = (torch.cuda.Stream(device), torch.cuda.Stream(device))
+        return st
+
     @torch.no_grad()
     def __call__(self, events, score0, raw0, score1, raw1, mask0=None, mask1=None) -> Dict[str, torch.Tensor]:
-        """events = (x, y, t, p, offsets) on the device; score/raw maps of both sides on the device."""
-        grid = self.voxelize(*events)
-        k0, c0, d0 = self.extract(score0, raw0, mask0)
-        k1, c1, d1 = self.extract(score1, raw1, mask1)
+        """events = (x, y, t, p, offsets) on the device; score/raw maps of both sides on the device.
+
+        The three branches of the step share no data until the matcher: voxelisation (L2-reduction bound)
+        and the second side's detect -> sample chain are forked onto two side streams, each with its own
+        einx context (workspace), and joined before the MNN kernel -- so the latency-bound NMS rounds of
+        one side overlap the other side's sampling and the event scatter instead of queueing behind them."""
+        if not self.cfg.concurrent:
+            grid = self.voxelize(*events)
+            k0, c0, d0 = self.extract(score0, raw0, mask0)
+            k1, c1, d1 = self.extract(score1, raw1, mask1)
+        else:
+            dev = score0.device
+            main = torch.cuda.current_stream(dev)
+            s_vox, s_side = self._streams(dev)
+            s_vox.wait_stream(main)
+            s_side.wait_stream(main)
+            with torch.cuda.stream(s_side):
+                k1, c1, d1 = self.extract(score1, raw1, mask1)
+            with torch.cuda.stream(s_vox):
+                grid = self.voxelize(*events)
+            k0, c0, d0 = self.extract(score0, raw0, mask0)
+            main.wait_stream(s_side)
+            main.wait_stream(s_vox)
+            # caching-allocator bookkeeping: tensors cross streams in both directions
+            for t in (k1, c1, d1, grid):
+                t.record_stream(main)
+            for t in (score1, raw1, mask1):
+                if t is not None:
+                    t.record_stream(s_side)
+            for t in events:
+                t.record_stream(s_vox)
         out = match.mnn(d0, d1, c0, c1, k0, k1, None, None, True, self.cfg.precision)
         out.update(voxel_grid=grid, keypoints0=k0, keypoints1=k1, counts0=c0, counts1=c1,
                    descriptors0=d0, descriptors1=d1)
         return out
+
+
+class HostBatch:
+    """Pinned host inputs of one batch of pairs, split into ``len(chunks)`` contiguous sub-batches so
+    that the host->device copy of one sub-batch overlaps the kernels of the previous one."""
+
+    def __init__(self, events: Sequence[dict], score0, raw0, score1, raw1, chunks: int = 4):
+        B = len(events)
+        chunks = max(1, min(int(chunks), B))
+        bounds = [B * i // chunks for i in range(chunks + 1)]
+        self.batch = B
+        self.chunks: List[tuple] = []
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            ev = voxel.pack_events(events[a:b], pin=True)
+            maps = tuple(torch.from_numpy(m[a:b]).pin_memory() if not torch.is_tensor(m) else m[a:b].pin_memory()
+                         for m in (score0, raw0, score1, raw1))
+            self.chunks.append((a, b, ev, maps))
+
+    @property
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for _, _, ev, maps in self.chunks for t in (*ev, *maps))
+
+
+RESULT_KEYS = ("matches0", "matching_scores0", "num_matches", "matched_kpts0", "matched_kpts1")
+
+
+class HostStreamer:
+    """End-to-end driver of the path for inputs that live in pinned HOST memory.
+
+    A copy stream uploads sub-batch i+1 into the second of two device staging sets while the compute
+    streams run sub-batch i; results are written back to the caller's pinned host tensors on the
+    compute stream.  Everything is asynchronous: the caller synchronises (or records an event) when it
+    needs the results."""
+
+    def __init__(self, pipe: ExtractMatchPipeline, device):
+        self.pipe = pipe
+        self.dev = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(self.dev)
+        self._stage = {}
+        self._free = [None, None]  # event: the kernels that read staging set k have finished
+
+    def _staging(self, k, ev, maps):
+        key = (k, tuple(t.shape[1:] for t in maps))
+        st = self._stage.get(key)
+        need_ev = ev[0].numel()
+        need_b = maps[0].shape[0]
+        if st is None or st["ev_cap"] < need_ev or st["b_cap"] < need_b:
+            st = self._stage[key] = {
+                "ev_cap": need_ev, "b_cap": need_b,
+                "ev": tuple(torch.empty(need_ev, dtype=t.dtype, device=self.dev) for t in ev[:4]),
+                "off": torch.empty(need_b + 1, dtype=torch.int64, device=self.dev),
+                "maps": tuple(torch.empty((need_b, *m.shape[1:]), dtype=m.dtype, device=self.dev) for m in maps),
+            }
+        return st
+
+    @torch.no_grad()
+    def run(self, hb: HostBatch, out_host: Dict[str, torch.Tensor]) -> None:
+        main = torch.cuda.current_stream(self.dev)
+        self.copy_stream.wait_stream(main)
+        for i, (a, b, ev, maps) in enumerate(hb.chunks):
+            k = i & 1
+            st = self._staging(k, ev, maps)
+            n_ev, nb = ev[0].numel(), b - a
+            with torch.cuda.stream(self.copy_stream):
+                if self._free[k] is not None:
+                    self.copy_stream.wait_event(self._free[k])
+                d_ev = tuple(d[:n_ev] for d in st["ev"])
+                for d, h in zip(d_ev, ev[:4]):
+                    d.copy_(h, non_blocking=True)
+                d_off = st["off"][:nb + 1]
+                d_off.copy_(ev[4], non_blocking=True)
+                d_maps = tuple(d[:nb] for d in st["maps"])
+                for d, h in zip(d_maps, maps):
+                    d.copy_(h, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(self.copy_stream)
+            main.wait_event(ready)
+            out = self.pipe((*d_ev, d_off), d_maps[0], d_maps[1], d_maps[2], d_maps[3])
+            for key in RESULT_KEYS:
+                if key in out_host:
+                    out_host[key][a:b].copy_(out[key], non_blocking=True)
+            self._free[k] = torch.cuda.Event()
+            self._free[k].record(main)

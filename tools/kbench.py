@@ -94,8 +94,11 @@ def bench_stages(args):
             ks.append(ctx.profile_read()[slot])
         ctx.profile(False)
         print(f"{name}: entry point {total:.4f} ms, dominant kernel {float(np.median(ks)):.4f} ms", flush=True)
-    total = time_ms(lambda: pipe(ev, s0, r0, s1, r1))
-    print(f"pipeline: {total:.4f} ms/step = {B / total * 1e3:.0f} pairs/s", flush=True)
+    import dataclasses
+    for conc in (False, True):
+        pp = einx.ExtractMatchPipeline(dataclasses.replace(cfg, concurrent=conc))
+        total = time_ms(lambda: pp(ev, s0, r0, s1, r1), iters=50)
+        print(f"pipeline ({'3 streams' if conc else 'serial'}): {total:.4f} ms/step = {B / total * 1e3:.0f} pairs/s", flush=True)
 
 
 if __name__ == "__main__":
