@@ -72,3 +72,27 @@ __device__ __forceinline__ float f32_from_orderable(uint32_t u) {
 __device__ __forceinline__ unsigned long long pack_best(float v, uint32_t idx) {
     return ((unsigned long long)f32_orderable(v + 0.0f) << 32) | (unsigned long long)(0xffffffffu - idx);
 }
+
+// First-occurrence argmax of 32 register values as a tournament tree: 31 (compare, select value,
+// select index) triples at depth 5 instead of a 32-long dependent chain; the left operand wins ties.
+__device__ __forceinline__ void argmax32(const float (&x)[32], float& val, int& idx) {
+    float a[16];
+    int ia[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const bool p = x[2 * k + 1] > x[2 * k];
+        a[k] = p ? x[2 * k + 1] : x[2 * k];
+        ia[k] = p ? 2 * k + 1 : 2 * k;
+    }
+#pragma unroll
+    for (int n = 8; n >= 1; n >>= 1) {
+#pragma unroll
+        for (int k = 0; k < n; ++k) {
+            const bool p = a[2 * k + 1] > a[2 * k];
+            a[k] = p ? a[2 * k + 1] : a[2 * k];
+            ia[k] = p ? ia[2 * k + 1] : ia[2 * k];
+        }
+    }
+    val = a[0];
+    idx = ia[0];
+}

@@ -114,3 +114,86 @@ def prob_map_to_positions_with_prob(prob_map: torch.Tensor, threshold: float = 0
     if ordering == "xy":
         out = tuple(torch.cat((p[:, [1, 0]], p[:, 2:]), dim=1) for p in out)
     return out
+
+
+# --------------------------------------------------------------------------------------------- #
+# adjacent rows (SURVEY.md section 8 f): detector head post-processing and the event mask
+# --------------------------------------------------------------------------------------------- #
+HEAD_SCORE, HEAD_PROB, HEAD_SHUFFLE = 0, 1, 2
+
+
+def _head(x: torch.Tensor, cell: int, mode: int) -> torch.Tensor:
+    if x.dtype != torch.float32 or not x.is_cuda:
+        raise _lib.EinxError("detector head: expected a float32 CUDA tensor (there is no CPU fallback)")
+    if x.dim() != 4:
+        raise ValueError("detector head: expected (B, C, Hc, Wc)")
+    x = x.contiguous()
+    B, C, Hc, Wc = x.shape
+    dev = x.device
+    ctx = _lib.context_for(dev)
+    shape = (B, C, Hc, Wc) if mode == HEAD_PROB else (B, 1, Hc * cell, Wc * cell)
+    out = torch.empty(shape, dtype=torch.float32, device=dev)
+    rc = ctx.lib.einx_logits_to_score(ctx.handle, _lib.ptr(x), B, C, Hc, Wc, int(cell), mode, _lib.ptr(out),
+                                      _lib.stream_of(dev))
+    ctx.check(rc, "einx_logits_to_score")
+    return out
+
+
+@torch.no_grad()
+def logits_to_score(logits: torch.Tensor, cell_size: int = 8) -> torch.Tensor:
+    """``depth_to_space(logits_to_prob(logits), cell_size)`` in one kernel (detector_util.py:18-77):
+    (B, cell^2+1, Hc, Wc) logits -> (B, 1, Hc*cell, Wc*cell) scores; the probability tensor is never
+    written."""
+    return _head(logits, cell_size, HEAD_SCORE)
+
+
+@torch.no_grad()
+def logits_to_prob(logits: torch.Tensor, channel_dim: int = 1) -> torch.Tensor:
+    """Drop-in for ``detector_util.py:18-39`` (softmax over channels, or 1/(1+exp(-x)) for one channel)."""
+    if channel_dim not in (1, -3):
+        raise ValueError("logits_to_prob: channel_dim must be 1 (the only layout the reference uses)")
+    return _head(logits, 1, HEAD_PROB)
+
+
+@torch.no_grad()
+def depth_to_space(prob: torch.Tensor, cell_size: int = 8, channel_dim: int = 1) -> torch.Tensor:
+    """Drop-in for ``detector_util.py:42-77`` (drop the dustbin, pixel-shuffle by ``cell_size``)."""
+    if channel_dim not in (1, -3):
+        raise ValueError("depth_to_space: channel_dim must be 1 (the only layout the reference uses)")
+    if cell_size > 1:
+        assert prob.shape[1] == cell_size * cell_size + 1
+    else:
+        assert prob.shape[1] == 1
+        return prob
+    return _head(prob, cell_size, HEAD_SHUFFLE)
+
+
+@torch.no_grad()
+def events_mask(events_image: torch.Tensor, cell_size: int = 1) -> torch.Tensor:
+    """(B, H, W) / (B, 1, H, W) event accumulation image -> (B, 1, Hp, Wp) bool score mask.
+
+    ``events_image > 0`` (train_extractor.py:225), ``Padder.pad`` with constant zeros
+    (core/modules/utils/util.py:17-32) and the 3x3 box filter + ``> 0`` of
+    core/modules/event_extractors/EventExtractors.py:357-363, in one kernel.  Pass the result as
+    ``mask`` to :func:`detect`, which applies ``score[~mask] = 0`` (:374-375) while loading."""
+    if not events_image.is_cuda:
+        raise _lib.EinxError("events_mask: expected a CUDA tensor (there is no CPU fallback)")
+    img = events_image
+    if img.dim() == 4:
+        if img.shape[1] != 1:
+            raise ValueError("events_mask: expected (B, 1, H, W)")
+        img = img[:, 0]
+    if img.dtype != torch.uint8:
+        img = (img > 0).to(torch.uint8)
+    img = img.contiguous()
+    B, H, W = img.shape
+    hp = (((H // cell_size) + 1) * cell_size - H) % cell_size
+    wp = (((W // cell_size) + 1) * cell_size - W) % cell_size
+    Hp, Wp = H + hp, W + wp
+    dev = img.device
+    ctx = _lib.context_for(dev)
+    mask = torch.empty((B, 1, Hp, Wp), dtype=torch.uint8, device=dev)
+    rc = ctx.lib.einx_mask_dilate(ctx.handle, _lib.ptr(img), B, H, W, hp // 2, wp // 2, Hp, Wp, _lib.ptr(mask),
+                                  _lib.stream_of(dev))
+    ctx.check(rc, "einx_mask_dilate")
+    return mask.view(torch.bool)

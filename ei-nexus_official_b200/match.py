@@ -117,3 +117,25 @@ class NearestNeighborMatcher(nn.Module):
             out["matched_kpts0"], out["matched_kpts1"] = mk0[0, : nm[0]], mk1[0, : nm[0]]
         out["similarity"], out["log_assignment"] = mnn_dense(desc0, desc1) if dense else (None, None)
         return out
+
+
+@torch.no_grad()
+def filter_matches(scores: torch.Tensor, th: float):
+    """Drop-in for ``core/modules/matchers/lightglue.py:402-418``: matches from a log-assignment matrix
+    (B, M+1, N+1) -> ``(m0, m1, mscores0, mscores1)``; one pass over the matrix (einx_filter_matches)."""
+    if scores.dtype != torch.float32 or not scores.is_cuda:
+        raise _lib.EinxError("filter_matches: expected a float32 CUDA tensor (there is no CPU fallback)")
+    if scores.dim() != 3:
+        raise ValueError("filter_matches: expected (B, M+1, N+1)")
+    scores = scores.contiguous()
+    B, M, N = scores.shape[0], scores.shape[1] - 1, scores.shape[2] - 1
+    dev = scores.device
+    ctx = _lib.context_for(dev)
+    m0 = torch.empty((B, M), dtype=torch.int64, device=dev)
+    m1 = torch.empty((B, N), dtype=torch.int64, device=dev)
+    s0 = torch.empty((B, M), dtype=torch.float32, device=dev)
+    s1 = torch.empty((B, N), dtype=torch.float32, device=dev)
+    rc = ctx.lib.einx_filter_matches(ctx.handle, _lib.ptr(scores), B, M, N, float(th), _lib.ptr(m0), _lib.ptr(m1),
+                                     _lib.ptr(s0), _lib.ptr(s1), _lib.stream_of(dev))
+    ctx.check(rc, "einx_filter_matches")
+    return m0, m1, s0, s1

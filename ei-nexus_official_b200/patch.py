@@ -20,10 +20,15 @@ _FUNCS = {
     "sparsify_full_resolution_descriptors": describe.sparsify_full_resolution_descriptors,
     "sparsify_low_resolution_descriptors": describe.sparsify_low_resolution_descriptors,
     "NearestNeighborMatcher": match.NearestNeighborMatcher,
+    # adjacent rows (SURVEY.md section 8 f)
+    "draw_events_accumulation_image": voxel.draw_events_accumulation_image,
+    "logits_to_prob": detect.logits_to_prob,
+    "depth_to_space": detect.depth_to_space,
+    "filter_matches": match.filter_matches,
 }
 
 _MODULE_HINTS = ("representations", "detector_util", "descriptor_util", "MNN", "EventExtractors",
-                 "superpoint_extractor", "silk_extractor", "Matchers", "MVSEC", "EC")
+                 "superpoint_extractor", "silk_extractor", "Matchers", "MVSEC", "EC", "visualize", "lightglue")
 
 
 def patch_reference(modules=None):

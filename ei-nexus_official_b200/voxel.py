@@ -95,3 +95,40 @@ def events_to_voxel_grid(events: Dict, input_size: Tuple, normalize: bool = True
     events["t"] = torch.from_numpy(events["t"].astype("float32"))
     events["p"][events["p"] < 1] = -1
     return grid
+
+
+# --------------------------------------------------------------------------------------------- #
+# adjacent row (SURVEY.md section 8 f): event accumulation image
+# --------------------------------------------------------------------------------------------- #
+@torch.no_grad()
+def events_image_device(x: torch.Tensor, y: torch.Tensor, offsets: torch.Tensor, height: int, width: int) -> torch.Tensor:
+    """einx_events_image on device-resident coordinates (fp32 or fp64) -> (B, H, W) uint8."""
+    dev = x.device
+    if not x.is_cuda:
+        raise _lib.EinxError("events_image: expected CUDA tensors (there is no CPU fallback)")
+    if x.dtype != y.dtype or x.dtype not in (torch.float32, torch.float64):
+        raise ValueError("events_image: x and y must both be float32 or both float64")
+    if offsets.dtype != torch.int64:
+        raise ValueError("events_image: offsets must be int64")
+    ctx = _lib.context_for(dev)
+    B = offsets.numel() - 1
+    out = torch.empty((B, int(height), int(width)), dtype=torch.uint8, device=dev)
+    rc = ctx.lib.einx_events_image(ctx.handle, _lib.ptr(x.contiguous()), _lib.ptr(y.contiguous()),
+                                   int(x.dtype == torch.float64), _lib.ptr(offsets.contiguous()), B, int(height),
+                                   int(width), _lib.ptr(out), _lib.stream_of(dev))
+    ctx.check(rc, "einx_events_image")
+    return out
+
+
+def draw_events_accumulation_image(events, image_shape, device="cuda") -> np.ndarray:
+    """Drop-in for ``datasets/visualize.py:23-49`` (dict branch): (H, W) uint8 numpy image.
+
+    ``image_shape`` is (W, H) like the reference's ``RESOLUTION`` tuples.  The coordinates cross to the
+    device as fp64, so ``int()`` truncation matches the reference's per-event Python loop exactly."""
+    if not isinstance(events, dict):
+        raise ValueError("events must be a dictionary (the (N, 4) array branch of the reference is not on the path)")
+    dev = torch.device(device)
+    x = torch.from_numpy(np.ascontiguousarray(events["x"], dtype=np.float64)).to(dev)
+    y = torch.from_numpy(np.ascontiguousarray(events["y"], dtype=np.float64)).to(dev)
+    off = torch.tensor([0, x.numel()], dtype=torch.int64, device=dev)
+    return events_image_device(x, y, off, image_shape[1], image_shape[0])[0].cpu().numpy()

@@ -125,6 +125,60 @@ int einx_mnn(einx_ctx* ctx, const float* d0, const float* d1, const int32_t* n0,
 int einx_mnn_dense(einx_ctx* ctx, const float* d0, const float* d1, int B, int N, int M, int D,
                    float* similarity, float* log_assignment, einx_stream stream);
 
+/* ---- rows adjacent to the path (SURVEY.md section 8 f) ---------------------------------------- */
+
+/*
+ * Event accumulation image.  Replaces datasets/visualize.py:23-49 (draw_events_accumulation_image,
+ * dict branch: one count per event at (int(y), int(x)), then (c - min) / (max - min) * 255 in fp64,
+ * clipped to 255 and truncated to uint8) for a ragged batch -- the reference runs a per-event Python
+ * loop here (datasets/MVSEC.py:850, datasets/EC.py:300).
+ *   x, y      : (N_total) event coordinates, fp64 if coord_f64 != 0 (what the datasets hold:
+ *               truncation then matches the reference bit for bit) else fp32 (the voxeliser's SoA;
+ *               identical unless a coordinate lies within one fp32 ulp below an integer)
+ *   image     : (B, H, W) uint8.  A window whose counts are all equal (max == min) yields zeros
+ *               (the reference divides 0/0 and casts NaN).  Events outside [0,W)x[0,H) are skipped
+ *               (the reference raises IndexError or wraps negative indices).
+ */
+int einx_events_image(einx_ctx* ctx, const void* x, const void* y, int coord_f64,
+                      const int64_t* ev_offsets, int B, int H, int W, uint8_t* image,
+                      einx_stream stream);
+
+/*
+ * Event mask for the detector.  Replaces `events_image > 0` (train_extractor.py:225), the constant
+ * padding of Padder.pad for bool tensors (core/modules/utils/util.py:17-32) and the 3x3 box
+ * convolution + `> 0` of core/modules/event_extractors/EventExtractors.py:357-363, i.e. a 3x3 binary
+ * dilation of the zero-extended mask.  The result is the `mask` argument of einx_detect, which applies
+ * `score[~mask] = 0` (:374-375) on load.
+ *   image (B, H, W) uint8 -> mask (B, Hp, Wp) uint8 in {0,1}; the image sits at (pad_top, pad_left).
+ */
+int einx_mask_dilate(einx_ctx* ctx, const uint8_t* image, int B, int H, int W, int pad_top,
+                     int pad_left, int Hp, int Wp, uint8_t* mask, einx_stream stream);
+
+/*
+ * Detector head post-processing.  Replaces core/modules/utils/detector_util.py:18-39
+ * (logits_to_prob: softmax over the channel dimension, or 1 / (1 + exp(-x)) for one channel) and
+ * :42-77 (depth_to_space: drop the dustbin channel, pixel-shuffle by `cell`).
+ *   logits : (B, C, Hc, Wc) fp32 with C == cell*cell + 1 (cell > 1) or C == 1 (cell == 1)
+ *   mode   : EINX_HEAD_SCORE  -> out (B, 1, Hc*cell, Wc*cell)   depth_to_space(logits_to_prob(x))
+ *            EINX_HEAD_PROB   -> out (B, C, Hc, Wc)             logits_to_prob(x)
+ *            EINX_HEAD_SHUFFLE-> out (B, 1, Hc*cell, Wc*cell)   depth_to_space(x), x already probabilities
+ * fp32 exp / sum: agrees with torch to a few ulp (1e-6 relative), not bit-exact.
+ */
+#define EINX_HEAD_SCORE 0
+#define EINX_HEAD_PROB 1
+#define EINX_HEAD_SHUFFLE 2
+int einx_logits_to_score(einx_ctx* ctx, const float* logits, int B, int C, int Hc, int Wc, int cell,
+                         int mode, float* out, einx_stream stream);
+
+/*
+ * LightGlue match filtering.  Replaces core/modules/matchers/lightglue.py:402-418 (filter_matches)
+ * on a log-assignment matrix: row / column argmax of scores[:, :-1, :-1] (first index on ties),
+ * mutual check, exp of the row maxima, threshold.  One pass over the matrix.
+ *   scores (B, M+1, N+1) fp32; m0 (B, M), m1 (B, N) int64 (-1 = none); ms0 (B, M), ms1 (B, N) fp32
+ */
+int einx_filter_matches(einx_ctx* ctx, const float* scores, int B, int M, int N, float th,
+                        int64_t* m0, int64_t* m1, float* ms0, float* ms1, einx_stream stream);
+
 /* Number of kernel launches issued through `ctx` so far (bench.py's gpu_launches). */
 int64_t einx_launch_count(const einx_ctx* ctx);
 

@@ -427,3 +427,81 @@ def pair_pipeline(ev, bins, H, W, score0, raw0, score1, raw1, kind, top_k, scale
     p1, d1 = extract_side(score1, raw1, kind, nms_dist, border, top_k, prob_thresh, scale)
     m = mnn_match(d0[0], d1[0], p0[0], p1[0])
     return grid, p0[0], p1[0], m
+
+
+# --------------------------------------------------------------------------- #
+# adjacent rows (SURVEY.md section 8 f)
+# --------------------------------------------------------------------------- #
+def draw_events_accumulation_image(x, y, H, W):
+    """Event count image, min-max scaled to uint8 (datasets/visualize.py:23-49, dict branch).
+
+    One count per event at (int(y), int(x)) -- Python ``int()`` truncates toward zero (:35) -- then
+    ``(c - min) / (max - min) * 255`` in fp64 (:45), clipped (:46), ``astype(uint8)`` (:48).
+    In-range events only (the reference indexes a numpy array, so negative indices would wrap)."""
+    img = np.zeros((H, W), dtype=np.float64)
+    iy = np.trunc(np.asarray(y, dtype=np.float64)).astype(np.int64)
+    ix = np.trunc(np.asarray(x, dtype=np.float64)).astype(np.int64)
+    np.add.at(img, (iy, ix), 1.0)
+    mn, mx = img.min(), img.max()
+    if mx == mn:  # 0/0 -> NaN -> uint8 cast (0 on x86); the CUDA path defines this case as zeros
+        return np.zeros((H, W), dtype=np.uint8)
+    img = (img - mn) / (mx - mn) * 255
+    img[img > 255] = 255
+    return img.astype(np.uint8)
+
+
+def events_mask(events_image, cell):
+    """``events_image > 0`` (train_extractor.py:225) -> constant-zero padding to a multiple of ``cell``
+    (core/modules/utils/util.py:9-32, bool tensors) -> 3x3 box filter, ``> 0``
+    (core/modules/event_extractors/EventExtractors.py:357-363) = 3x3 dilation of the padded mask."""
+    m = np.asarray(events_image) > 0
+    H, W = m.shape[-2:]
+    w0, w1, h0, h1 = padder_sizes(H, W, cell)
+    Hp, Wp = H + h0 + h1, W + w0 + w1
+    pad = [(0, 0)] * (m.ndim - 2) + [(h0, h1), (w0, w1)]
+    m = np.pad(m, pad, mode="constant")
+    z = np.pad(m, [(0, 0)] * (m.ndim - 2) + [(1, 1), (1, 1)], mode="constant")
+    out = np.zeros_like(m)
+    for dy in range(3):
+        for dx in range(3):
+            out |= z[..., dy:dy + Hp, dx:dx + Wp]
+    return out
+
+
+def logits_to_prob(logits):
+    """Channel softmax, or 1 / (1 + exp(-x)) for a single channel (detector_util.py:18-39); fp32."""
+    x = np.asarray(logits, dtype=F32)
+    if x.shape[1] == 1:
+        return (F32(1) / (F32(1) + np.exp(-x))).astype(F32)
+    e = np.exp(x - x.max(axis=1, keepdims=True)).astype(F32)
+    return (e / e.sum(axis=1, keepdims=True, dtype=F32)).astype(F32)
+
+
+def depth_to_space(prob, cell):
+    """Drop the dustbin channel and pixel-shuffle by ``cell`` (detector_util.py:42-77):
+    out[b, 0, h*cell + i, w*cell + j] = prob[b, i*cell + j, h, w]."""
+    p = np.asarray(prob)
+    if cell == 1:
+        assert p.shape[1] == 1
+        return p
+    B, C, Hc, Wc = p.shape
+    assert C == cell * cell + 1
+    p = p[:, :cell * cell].reshape(B, cell, cell, Hc, Wc)
+    return np.ascontiguousarray(p.transpose(0, 3, 1, 4, 2).reshape(B, 1, Hc * cell, Wc * cell))
+
+
+def filter_matches(scores, th):
+    """Matches from a LightGlue log-assignment matrix (core/modules/matchers/lightglue.py:402-418):
+    row / column argmax of scores[:, :-1, :-1] (first index on ties), mutual check, exp, threshold."""
+    s = np.asarray(scores, dtype=F32)[:, :-1, :-1]
+    m0, m1 = s.argmax(2), s.argmax(1)
+    max0 = s.max(2)
+    B = s.shape[0]
+    bi = np.arange(B)[:, None]
+    mutual0 = np.arange(s.shape[1])[None] == m1[bi, m0]
+    mutual1 = np.arange(s.shape[2])[None] == m0[bi, m1]
+    ms0 = np.where(mutual0, np.exp(max0), F32(0)).astype(F32)
+    ms1 = np.where(mutual1, ms0[bi, m1], F32(0)).astype(F32)
+    valid0 = mutual0 & (ms0 > F32(th))
+    valid1 = mutual1 & valid0[bi, m1]
+    return np.where(valid0, m0, -1), np.where(valid1, m1, -1), ms0, ms1

@@ -1,0 +1,138 @@
+"""CUDA path of the rows adjacent to the hot path (SURVEY.md section 8 f) vs reference goldens and the
+oracle, through the C ABI (run with -m gpu on the B200 box)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import einx_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def einx():
+    import einx as m
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    m.context_for(DEV)
+    return m
+
+
+def cuda(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return (t.to(dtype) if dtype else t).to(DEV)
+
+
+# ------------------------------------------------------------- events image / mask ---- #
+def test_events_image_golden(einx, golden):
+    g = golden["next"]
+    for ci in range(int(g["img_ncases"])):
+        H, W, cell = (int(v) for v in g[f"img{ci}_shape"])
+        ev = {"x": g[f"img{ci}_x"], "y": g[f"img{ci}_y"]}
+        img = einx.draw_events_accumulation_image(ev, (W, H), DEV)
+        assert img.dtype == np.uint8 and np.array_equal(img, g[f"img{ci}_out"])  # bit-exact (integer work)
+        mask = einx.events_mask(cuda(img)[None], cell)
+        assert mask.dtype == torch.bool and np.array_equal(mask[0, 0].cpu().numpy(), g[f"img{ci}_mask"])
+
+
+def test_events_image_batch_vs_oracle(einx):
+    import importlib
+
+    synth = importlib.import_module("ei-nexus_official_b200.synth")
+    rng = np.random.default_rng(5)
+    H, W = 180, 240
+    evs = [synth.events(rng, n, H, W, style) for n, style in ((60_000, "ec"), (1, "ec"), (20_000, "mvsec"), (333, "mvsec"))]
+    x, y, t, p, off = (a.to(DEV) for a in einx.pack_events(evs))
+    img = einx.events_image_device(x, y, off, H, W).cpu().numpy()
+    for i, ev in enumerate(evs):
+        # fp32 coordinates: same truncation as fp64 here (EC integral; MVSEC rounding never crosses an integer
+        # for this seed -- checked by comparing with the fp32-rounded oracle)
+        ref = O.draw_events_accumulation_image(ev["x"].astype(np.float32), ev["y"].astype(np.float32), H, W)
+        assert np.array_equal(img[i], ref), i
+    mask = einx.events_mask(torch.from_numpy(img).to(DEV), 8).cpu().numpy()
+    assert mask.shape == (4, 1, 184, 240)
+    for i in range(4):
+        assert np.array_equal(mask[i, 0], O.events_mask(img[i], 8))
+
+
+def test_event_mask_fused_into_detect(einx):
+    """score[~mask] = 0 on load (EventExtractors.py:374-375): detect(score, mask) == detect(score * mask)."""
+    rng = np.random.default_rng(9)
+    score = rng.random((3, 1, 64, 80)).astype(np.float32)
+    img = (rng.random((3, 64, 80)) < 0.02).astype(np.uint8) * 200
+    mask = einx.events_mask(cuda(img), 8)
+    a = cuda(score)
+    _, k_a, c_a = einx.detect(a, 1.0, 4, 4, 50, mask=mask)
+    ref_in = score * O.events_mask(img, 8)[:, None]
+    for i in range(3):
+        nms = O.prob_map_to_points_map(ref_in[i:i + 1].copy(), 1.0, 4, 4, 50)
+        pos = O.prob_map_to_positions_with_prob(nms)[0]
+        n = int(c_a[i])
+        assert np.array_equal(k_a[i, :n].cpu().numpy(), pos)
+    assert np.array_equal(a.cpu().numpy()[:, :, 4:-4, 4:-4], ref_in[:, :, 4:-4, 4:-4])  # zeroed in place
+
+
+# ------------------------------------------------------------------ detector head ---- #
+HEAD_RTOL = 2e-6  # fp32 exp / sum order; the reference's own CPU and CUDA softmax differ by as much
+
+
+def test_detector_head_golden(einx, golden):
+    g = golden["next"]
+    lo = cuda(g["head_logits65"])
+    np.testing.assert_allclose(einx.logits_to_prob(lo).cpu().numpy(), g["head_prob65"], rtol=HEAD_RTOL, atol=1e-9)
+    np.testing.assert_allclose(einx.logits_to_score(lo, 8).cpu().numpy(), g["head_score65"], rtol=HEAD_RTOL, atol=1e-9)
+    # pure data movement is exact
+    assert np.array_equal(einx.depth_to_space(cuda(g["head_prob65"]), 8).cpu().numpy(), g["head_score65"])
+    l1 = cuda(g["head_logits1"])
+    np.testing.assert_allclose(einx.logits_to_prob(l1).cpu().numpy(), g["head_prob1"], rtol=HEAD_RTOL, atol=1e-9)
+    np.testing.assert_allclose(einx.logits_to_score(l1, 1).cpu().numpy(), g["head_score1"], rtol=HEAD_RTOL, atol=1e-9)
+    np.testing.assert_allclose(einx.logits_to_score(cuda(g["head_logits17"]), 4).cpu().numpy(), g["head_score17"],
+                               rtol=HEAD_RTOL, atol=1e-9)
+
+
+def test_detector_head_config_size(einx):
+    rng = np.random.default_rng(11)
+    lo = (3 * rng.standard_normal((8, 65, 23, 30))).astype(np.float32)  # EC SuperPoint head: 184x240 / 8
+    score = einx.logits_to_score(cuda(lo), 8)
+    assert score.shape == (8, 1, 184, 240)
+    ref = O.depth_to_space(O.logits_to_prob(lo), 8)
+    np.testing.assert_allclose(score.cpu().numpy(), ref, rtol=HEAD_RTOL, atol=1e-9)
+    # partition of unity: every cell's 64 scores + dustbin sum to 1
+    prob = einx.logits_to_prob(cuda(lo)).cpu().numpy()
+    np.testing.assert_allclose(prob.sum(1), 1.0, atol=3e-6)
+    with pytest.raises(einx.EinxError):
+        einx.logits_to_score(cuda(lo[:, :64]), 8)  # the reference asserts C == cell^2 + 1
+
+
+# ---------------------------------------------------------------- filter_matches ---- #
+def test_filter_matches_golden(einx, golden):
+    g = golden["next"]
+    for ci in range(int(g["fm_ncases"])):
+        m0, m1, s0, s1 = einx.filter_matches(cuda(g[f"fm{ci}_scores"]), float(g[f"fm{ci}_th"]))
+        assert m0.dtype == torch.int64
+        assert np.array_equal(m0.cpu().numpy(), g[f"fm{ci}_m0"]) and np.array_equal(m1.cpu().numpy(), g[f"fm{ci}_m1"])
+        np.testing.assert_allclose(s0.cpu().numpy(), g[f"fm{ci}_s0"], rtol=2e-6)
+        np.testing.assert_allclose(s1.cpu().numpy(), g[f"fm{ci}_s1"], rtol=2e-6)
+
+
+def test_filter_matches_config_size(einx):
+    rng = np.random.default_rng(13)
+    B, M, N = 4, 1024, 1000
+    s = rng.standard_normal((B, M + 1, N + 1)).astype(np.float32) - 6.0
+    perm = rng.permutation(N)[:400]
+    s[:, np.arange(400), perm] += 5.5  # planted mutual maxima
+    m0, m1, s0, s1 = einx.filter_matches(cuda(s), 0.1)
+    r0, r1, rs0, rs1 = O.filter_matches(s, 0.1)
+    # indices are exact; scores within exp's ulp; a threshold flip would need exp(max) within 1e-6 of th
+    assert np.array_equal(m0.cpu().numpy(), r0) and np.array_equal(m1.cpu().numpy(), r1)
+    np.testing.assert_allclose(s0.cpu().numpy(), rs0, rtol=2e-6)
+    np.testing.assert_allclose(s1.cpu().numpy(), rs1, rtol=2e-6)
+    # mutual consistency
+    a = m0.cpu().numpy()
+    b = m1.cpu().numpy()
+    for k in range(B):
+        i = np.nonzero(a[k] >= 0)[0]
+        assert np.array_equal(b[k][a[k][i]], i) and (a[k] >= 0).sum() == (b[k] >= 0).sum()
+        assert (a[k] >= 0).sum() >= 400

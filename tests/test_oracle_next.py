@@ -1,0 +1,34 @@
+"""Oracle restatements of the rows adjacent to the hot path (SURVEY.md section 8 f) against the fixtures
+made by the reference's own functions (tests/golden/make_golden_next.py).  CPU only."""
+import numpy as np
+
+from oracle import einx_oracle as O
+
+
+def test_events_image_and_mask_match_reference(golden):
+    g = golden["next"]
+    for ci in range(int(g["img_ncases"])):
+        H, W, cell = (int(v) for v in g[f"img{ci}_shape"])
+        img = O.draw_events_accumulation_image(g[f"img{ci}_x"], g[f"img{ci}_y"], H, W)
+        assert img.dtype == np.uint8 and np.array_equal(img, g[f"img{ci}_out"])
+        assert np.array_equal(O.events_mask(img, cell), g[f"img{ci}_mask"])
+
+
+def test_detector_head_matches_reference(golden):
+    g = golden["next"]
+    p = O.logits_to_prob(g["head_logits65"])
+    np.testing.assert_allclose(p, g["head_prob65"], rtol=2e-6, atol=1e-9)
+    # the shuffle is pure data movement: exact on the reference's own probabilities
+    assert np.array_equal(O.depth_to_space(g["head_prob65"], 8), g["head_score65"])
+    np.testing.assert_allclose(O.logits_to_prob(g["head_logits1"]), g["head_prob1"], rtol=2e-6, atol=1e-9)
+    assert np.array_equal(O.depth_to_space(g["head_prob1"], 1), g["head_score1"])
+    np.testing.assert_allclose(O.depth_to_space(O.logits_to_prob(g["head_logits17"]), 4), g["head_score17"], rtol=2e-6, atol=1e-9)
+
+
+def test_filter_matches_matches_reference(golden):
+    g = golden["next"]
+    for ci in range(int(g["fm_ncases"])):
+        m0, m1, s0, s1 = O.filter_matches(g[f"fm{ci}_scores"], float(g[f"fm{ci}_th"]))
+        assert np.array_equal(m0, g[f"fm{ci}_m0"]) and np.array_equal(m1, g[f"fm{ci}_m1"])
+        np.testing.assert_allclose(s0, g[f"fm{ci}_s0"], rtol=2e-6)
+        np.testing.assert_allclose(s1, g[f"fm{ci}_s1"], rtol=2e-6)
