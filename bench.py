@@ -382,6 +382,7 @@ def run_einx(args, synth):
     if world > 1:
         out = step_device(0)
         packed = einx.pack_matches(out["matches0"], out["num_matches"])
+        einx.gather_matches(packed, B)  # first call sets up the NCCL communicator
         torch.cuda.synchronize(dev)
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()

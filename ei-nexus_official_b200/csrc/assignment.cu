@@ -14,7 +14,7 @@ constexpr int kStripThreads = 256;
 constexpr int kStripWarps = kStripThreads / 32;
 constexpr int kPitch = 33;
 
-__global__ void __launch_bounds__(kStripThreads)
+__global__ void __launch_bounds__(kStripThreads, 2)
 assignment_best_kernel(const float* __restrict__ scores, int M, int N, unsigned long long* __restrict__ rowkey,
                        unsigned long long* __restrict__ colkey) {
     const int b = blockIdx.y;

@@ -35,29 +35,38 @@ constexpr int kScratchPitch = 33;    // floats; 32x32 transpose tile per epilogu
 constexpr uint32_t kTmemCols = 512;
 
 // Per-precision shape of the pipeline.
-//   BF16   : 3 stages of (A 16 KB | B 32 KB), 8 epilogue warps (the epilogue is the critical path).
-//   TF32X3 : every stage also holds the low-order tiles (A lo | B lo) that 4 converter warps derive
+//   BF16   : stages of (A 16 KB | B 32 KB / CG), 8 epilogue warps.
+//   TF32X3 : every stage also holds the low-order tiles (A lo | B lo) that the converter warps derive
 //            from the raw fp32 tiles in shared memory, so each descriptor byte crosses L2 -> SM once
-//            per tile and no split copy of the descriptors ever exists in HBM.  The MMA work is 6x
-//            the bf16 one, so 4 epilogue warps keep up.
-template <int KIND, int KB>
+//            per tile and no split copy of the descriptors ever exists in HBM.
+// CG = 2 is the CTA-pair form (tcgen05 cta_group::2): the two CTAs of a cluster own the two 128-row
+// halves of a 256 x 256 tile.  Each loads its own A half and HALF of the B tile, the leader issues one
+// M=256 MMA that reads both CTAs' shared memory, and each CTA's accumulator half lands in its own
+// TMEM.  Per CTA that is 1/3 less operand traffic from L2 and out of shared memory than two
+// independent 128 x 256 tiles -- the two limits the single-CTA kernel runs into at D = 128..256.
+template <int KIND, int KB, int CG>
 struct Cfg {
     static constexpr int kElt = KIND == 0 ? 2 : 4;
     static constexpr int kKB = KB;                       // bytes of K per stage row (= swizzle span)
     static constexpr int kABytes = TILE_M * KB;
-    static constexpr int kBBytes = TILE_N * KB;
+    static constexpr int kBRows = TILE_N / CG;           // rows of d1 this CTA stages per k-block
+    static constexpr int kBBytes = kBRows * KB;
     static constexpr bool kConvert = KIND == 1;
-    static constexpr int kStageBytes = (kABytes + kBBytes) * (kConvert ? 2 : 1);
-    static constexpr int kStages = KIND == 0 ? 3 : (192 * 1024) / kStageBytes;
+    static constexpr int kRawBytes = kABytes + kBBytes;
+    static constexpr int kStageBytes = kRawBytes * (kConvert ? 2 : 1);
     static constexpr int kEpiWarps = KIND == 0 ? 8 : 4;
     static constexpr int kConvWarps = kConvert ? EINX_TF32_CONV_WARPS : 0;
     static constexpr int kConvWarp0 = kEpilogueWarp0 + kEpiWarps;
     static constexpr int kColsPerWarp = TILE_N / (kEpiWarps / 4);
     // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4.. epilogue, then converters
     static constexpr int kThreads = 32 * (kEpilogueWarp0 + kEpiWarps + kConvWarps);
-    static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + 256 + 4 * TILE_N * sizeof(unsigned long long) +
-                                    (size_t)kEpiWarps * 32 * kScratchPitch * sizeof(float);
-    static_assert(kStages <= 4, "Barriers holds 4 stages");
+    // alignment slack + barriers + column-merge buffer + one 32x32 transpose tile per epilogue warp
+    static constexpr size_t kFixedSmem = 1024 + 256 + 4 * TILE_N * sizeof(unsigned long long) +
+                                         (size_t)kEpiWarps * 32 * kScratchPitch * sizeof(float);
+    static constexpr int kStagesFit = (int)((227 * 1024 - kFixedSmem) / kStageBytes);
+    static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
+    static constexpr size_t kSmem = kFixedSmem + (size_t)kStages * kStageBytes;
+    static_assert(kStages >= 2 && kStages <= 8, "Barriers holds 8 stages");
 };
 
 struct TcParams {
@@ -71,10 +80,10 @@ struct TcParams {
     unsigned long long* colkey;
 };
 
-struct __align__(8) Barriers {
-    unsigned long long full[4];    // TMA landed the raw tiles of a stage
-    unsigned long long conv[4];    // converter warps wrote the lo tiles of a stage (TF32X3)
-    unsigned long long empty[4];   // the MMAs reading a stage have completed
+struct __align__(8) Barriers {   // 240 bytes; in the pair form the LEADER's full / conv / tmem_empty are the live ones
+    unsigned long long full[8];    // TMA landed the raw tiles of a stage (both CTAs' tiles in the pair form)
+    unsigned long long conv[8];    // converter warps wrote the lo tiles of a stage (TF32X3)
+    unsigned long long empty[8];   // the MMAs reading a stage have completed
     unsigned long long tmem_full[2];
     unsigned long long tmem_empty[2];
     uint32_t tmem_base;
@@ -127,18 +136,89 @@ __device__ __forceinline__ void tc_commit(unsigned long long* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
-template <int KIND>  // 0: kind::f16 (bf16 inputs), 1: kind::tf32
+// ---- CTA-pair (cta_group::2) forms ---- //
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address: "the leader's copy"
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster.  Plain (CTA-scope
+// release) form, as CUTLASS's ClusterBarrier::arrive(cta_id): a `.release.cluster` arrive costs a
+// cluster-wide memory fence (~0.8 us per call measured under ncu, stall_membar) and none of the
+// hand-offs below publishes generic-proxy global data -- TMEM reads are ordered by the tcgen05
+// fences, shared-memory tiles by fence.proxy.async before the arrive.
+__device__ __forceinline__ void mbar_arrive_cta(unsigned long long* bar, uint32_t cta) {
+    asm volatile(
+        "{\n.reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n}\n" ::"r"(smem_u32(bar)),
+        "r"(cta)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(unsigned long long* bar, uint32_t parity) {
+    // like mbar_wait, acquiring at cluster scope (the arrivals come from the peer CTA as well)
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    long long t0 = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if ((spins & 0xfffu) == 0xfffu) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > (1ll << 31)) __trap();
+        }
+    }
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+// MMA completion -> the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(unsigned long long* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+template <int KIND, int CG>  // KIND 0: kind::f16 (bf16 inputs), 1: kind::tf32; CG: cta_group
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    if (KIND == 0) {
+    if (KIND == 0 && CG == 1) {
         asm volatile(
             "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
             "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
             "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
             : "memory");
-    } else {
+    } else if (KIND == 0) {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else if (CG == 1) {
         asm volatile(
             "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
             "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
             "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
             : "memory");
     }
@@ -188,11 +268,12 @@ __device__ __forceinline__ float tf32_lo(float x) {
     return __fsub_rn(x, __uint_as_float(__float_as_uint(x) & 0xffffe000u));
 }
 
-template <int KIND, int KB>
-__global__ void __launch_bounds__(Cfg<KIND, KB>::kThreads, 1)
+template <int KIND, int KB, int CG>
+__global__ void __launch_bounds__(Cfg<KIND, KB, CG>::kThreads, 1)
 mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams P) {
-    using C = Cfg<KIND, KB>;
-    constexpr int A_BYTES = C::kABytes, B_BYTES = C::kBBytes, STAGES = C::kStages, STAGE_BYTES = C::kStageBytes;
+    using C = Cfg<KIND, KB, CG>;
+    constexpr int A_BYTES = C::kABytes, B_BYTES = C::kBBytes, RAW_BYTES = C::kRawBytes, STAGES = C::kStages,
+                  STAGE_BYTES = C::kStageBytes;
     extern __shared__ __align__(1024) unsigned char smem[];
     // carve: [stages x (A | B [| A lo | B lo])] 1024-aligned, then barriers, then the column-merge buffer
     // (offset arithmetic on the shared array, not an integer round trip: the compiler must keep the
@@ -203,8 +284,11 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     float* scratch_all = reinterpret_cast<float*>(colpart + 4 * TILE_N);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;  // which 128-row half of the pair's tile
+    const bool leader = rank == 0;
     const int tiles_per_pair = P.tiles_m * P.tiles_n;
     const int total_tiles = P.B * tiles_per_pair;
+    const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -212,32 +296,40 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&bars->full[s], 1);
-            mbar_init(&bars->conv[s], C::kConvWarps * 32);
+            mbar_init(&bars->full[s], (CG == 2 && !C::kConvert) ? 2 : 1);  // pair form: one arrival per producer
+            mbar_init(&bars->conv[s], CG * C::kConvWarps);     // one arrival per converter warp of the pair
             mbar_init(&bars->empty[s], 1);
         }
-        for (int a = 0; a < 2; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], C::kEpiWarps); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], CG * C::kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
-                     "r"(kTmemCols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                         "r"(kTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                         "r"(kTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();  // barriers initialised in both CTAs before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
+    // tile t of the schedule: pair b, rows [i0, i0 + 128*CG) of d0 (this CTA: the 128 from my_i0), columns [j0, j0+256)
     auto tile_coords = [&](int t, int& b, int& i0, int& j0, bool& live) {
         b = t / tiles_per_pair;
         const int r = t - b * tiles_per_pair;
-        i0 = (r / P.tiles_n) * TILE_M;
+        i0 = (r / P.tiles_n) * (TILE_M * CG);
         j0 = (r % P.tiles_n) * TILE_N;
         const int N = P.n0 ? min(P.n0[b], P.ncap) : P.ncap;
         const int M = P.n1 ? min(P.n1[b], P.mcap) : P.mcap;
-        live = (i0 < N) && (j0 < M);
+        live = (i0 < N) && (j0 < M);  // identical in both CTAs of a pair
     };
 
     if (warp == 0) {
@@ -245,67 +337,88 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int t = tile0; t < total_tiles; t += tile_step) {
                 int b, i0, j0;
                 bool live;
                 tile_coords(t, b, i0, j0, live);
                 if (!live) continue;
-                const int rowA = b * P.ncap + i0, rowB = b * P.mcap + j0;
+                const int rowA = b * P.ncap + i0 + (int)rank * TILE_M;
+                const int rowB = b * P.mcap + j0 + (int)rank * C::kBRows;
                 for (int kb = 0; kb < P.nkb; ++kb) {
                     mbar_wait(&bars->empty[stage], phase ^ 1);
                     unsigned char* sa = tiles + (size_t)stage * STAGE_BYTES;
-                    mbar_expect_tx(&bars->full[stage], A_BYTES + B_BYTES);
                     const int kcoord = kb * (KB / C::kElt);
-                    tma_load_2d(sa, &mapA, &bars->full[stage], kcoord, rowA);
-                    tma_load_2d(sa + A_BYTES, &mapB, &bars->full[stage], kcoord, rowB);
+                    if (CG == 1 || C::kConvert) {
+                        // (3xTF32 pair form: each CTA's converters wait for their own tiles, so the bytes are
+                        // counted locally; the leader's MMA waits for the converters of both CTAs instead)
+                        mbar_expect_tx(&bars->full[stage], RAW_BYTES);
+                        tma_load_2d(sa, &mapA, &bars->full[stage], kcoord, rowA);
+                        tma_load_2d(sa + A_BYTES, &mapB, &bars->full[stage], kcoord, rowB);
+                    } else {
+                        // both CTAs' bytes complete on the leader's barrier; the peer adds its arrival remotely
+                        if (leader) mbar_expect_tx(&bars->full[stage], 2 * RAW_BYTES);
+                        else mbar_arrive_cta(&bars->full[stage], 0);
+                        tma_load_2d_pair(sa, &mapA, &bars->full[stage], kcoord, rowA);
+                        tma_load_2d_pair(sa + A_BYTES, &mapB, &bars->full[stage], kcoord, rowB);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer (the leader CTA's, in the pair form) =====
+        if (lane == 0 && leader) {
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int t = tile0; t < total_tiles; t += tile_step) {
                 int b, i0, j0;
                 bool live;
                 tile_coords(t, b, i0, j0, live);
                 if (!live) continue;
-                mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+                if (CG == 2) mbar_wait_cluster(&bars->tmem_empty[acc], acc_phase ^ 1);
+                else mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)acc * TILE_N;
                 for (int kb = 0; kb < P.nkb; ++kb) {
-                    mbar_wait(&bars->full[stage], phase);
-                    if (C::kConvert) mbar_wait(&bars->conv[stage], phase);
+                    if (!(C::kConvert && CG == 2)) {
+                        if (CG == 2) mbar_wait_cluster(&bars->full[stage], phase);
+                        else mbar_wait(&bars->full[stage], phase);
+                    }
+                    if (C::kConvert) {  // every converter warp (of both CTAs) saw its tiles land and wrote the lo tiles
+                        if (CG == 2) mbar_wait_cluster(&bars->conv[stage], phase);
+                        else mbar_wait(&bars->conv[stage], phase);
+                    }
                     tc_fence_after();
                     const uint32_t sa = smem_u32(tiles + (size_t)stage * STAGE_BYTES);
                     const uint64_t a_hi = make_smem_desc<KB>(sa), b_hi = make_smem_desc<KB>(sa + A_BYTES);
                     if (C::kConvert) {
                         // x.y ~= hi.hi + hi.lo + lo.hi  (the raw tile is its own hi part: the tensor
                         // core drops the 13 low mantissa bits of a tf32 operand)
-                        const uint64_t a_lo = make_smem_desc<KB>(sa + A_BYTES + B_BYTES);
-                        const uint64_t b_lo = make_smem_desc<KB>(sa + 2 * A_BYTES + B_BYTES);
+                        const uint64_t a_lo = make_smem_desc<KB>(sa + RAW_BYTES);
+                        const uint64_t b_lo = make_smem_desc<KB>(sa + RAW_BYTES + A_BYTES);
 #pragma unroll
                         for (int k = 0; k < KB / 32; ++k)
-                            tc_mma<KIND>(tmem_d, a_hi + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), P.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            tc_mma<KIND, CG>(tmem_d, a_hi + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), P.idesc, (kb > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
                         for (int k = 0; k < KB / 32; ++k)
-                            tc_mma<KIND>(tmem_d, a_hi + (uint64_t)(2 * k), b_lo + (uint64_t)(2 * k), P.idesc, 1u);
+                            tc_mma<KIND, CG>(tmem_d, a_hi + (uint64_t)(2 * k), b_lo + (uint64_t)(2 * k), P.idesc, 1u);
 #pragma unroll
                         for (int k = 0; k < KB / 32; ++k)
-                            tc_mma<KIND>(tmem_d, a_lo + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), P.idesc, 1u);
+                            tc_mma<KIND, CG>(tmem_d, a_lo + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), P.idesc, 1u);
                     } else {
 #pragma unroll
                         for (int k = 0; k < KB / 32; ++k) {
                             // +32 B along K inside the swizzle span = +2 in the 16-byte-unit address field
-                            tc_mma<KIND>(tmem_d, a_hi + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), P.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            tc_mma<KIND, CG>(tmem_d, a_hi + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), P.idesc, (kb > 0 || k > 0) ? 1u : 0u);
                         }
                     }
-                    tc_commit(&bars->empty[stage]);  // smem slot free once these MMAs have read it
-                    if (kb == P.nkb - 1) tc_commit(&bars->tmem_full[acc]);
+                    // smem slot free (in both CTAs) once these MMAs have read it
+                    if (CG == 2) tc_commit_pair(&bars->empty[stage]); else tc_commit(&bars->empty[stage]);
+                    if (kb == P.nkb - 1) {
+                        if (CG == 2) tc_commit_pair(&bars->tmem_full[acc]); else tc_commit(&bars->tmem_full[acc]);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 acc ^= 1;
@@ -315,10 +428,10 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     } else if (C::kConvert && warp >= C::kConvWarp0 && warp < C::kConvWarp0 + C::kConvWarps) {
         // ===== converter: lo tiles = x - tf32_trunc(x), element-wise (so the swizzle is irrelevant) =====
         const int ct = threadIdx.x - C::kConvWarp0 * 32;
-        constexpr int kChunks = (A_BYTES + B_BYTES) / 16;
+        constexpr int kChunks = RAW_BYTES / 16;
         int stage = 0;
         uint32_t phase = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int t = tile0; t < total_tiles; t += tile_step) {
             int b, i0, j0;
             bool live;
             tile_coords(t, b, i0, j0, live);
@@ -326,7 +439,7 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             for (int kb = 0; kb < P.nkb; ++kb) {
                 mbar_wait(&bars->full[stage], phase);
                 const float4* raw = reinterpret_cast<const float4*>(tiles + (size_t)stage * STAGE_BYTES);
-                float4* lo = reinterpret_cast<float4*>(tiles + (size_t)stage * STAGE_BYTES + A_BYTES + B_BYTES);
+                float4* lo = reinterpret_cast<float4*>(tiles + (size_t)stage * STAGE_BYTES + RAW_BYTES);
 #pragma unroll 8
                 for (int i = ct; i < kChunks; i += C::kConvWarps * 32) {
                     const float4 v = raw[i];
@@ -334,30 +447,34 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 }
                 // generic-proxy writes must be visible to the tensor core's async-proxy reads
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive(&bars->conv[stage]);
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2) mbar_arrive_cta(&bars->conv[stage], 0);
+                    else mbar_arrive(&bars->conv[stage]);
+                }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp >= kEpilogueWarp0 && warp < kEpilogueWarp0 + C::kEpiWarps) {
         // ===== epilogue: TMEM -> registers -> row / column best keys =====
-        // Rows: the thread that owns TMEM lane r scans its columns with a strict '>' (lowest
-        // column wins ties).  Columns: the 32x32 chunk goes through a padded shared-memory tile so
-        // that lane c then owns column c and scans the 32 rows the same way (lowest row wins).
+        // Rows: the thread that owns TMEM lane r finds its row's best column with a tournament over
+        // each 32-column chunk (lowest column wins ties).  Columns: the 32x32 chunk goes through a
+        // padded shared-memory transpose so that lane c then owns column c (lowest row wins).
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
         const int part = (warp - kEpilogueWarp0) >> 2;   // which kColsPerWarp columns of the tile
         float* scratch = scratch_all + (size_t)(warp - kEpilogueWarp0) * 32 * kScratchPitch;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int t = tile0; t < total_tiles; t += tile_step) {
             int b, i0, j0;
             bool live;
             tile_coords(t, b, i0, j0, live);
             if (!live) continue;
+            i0 += (int)rank * TILE_M;  // this CTA's half of the pair's rows
             const int N = P.n0 ? min(P.n0[b], P.ncap) : P.ncap;
             const int M = P.n1 ? min(P.n1[b], P.mcap) : P.mcap;
             const int row = i0 + 32 * q + lane;  // this thread's row of d0
             const bool row_ok = row < N;
-            const int rows_here = min(max(N - (i0 + 32 * q), 0), 32);  // valid rows of this warp's quarter
             const bool full_tile = (i0 + TILE_M <= N) && (j0 + TILE_N <= M);
             mbar_wait(&bars->tmem_full[acc], acc_phase);
             tc_fence_after();
@@ -404,12 +521,17 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                                   (0xffffffffu - (uint32_t)(i0 + 32 * q + cr)))
                                : 0ull;
                     __syncwarp();  // the tile is rewritten by the next chunk
+                } else {
+                    colpart[q * TILE_N + C::kColsPerWarp * part + 32 * c + lane] = 0ull;
                 }
             }
-            // TMEM accumulator fully read by this warp: hand it back to the MMA warp
+            // TMEM accumulator fully read by this warp: hand it back to the MMA warp (the leader's)
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_cta(&bars->tmem_empty[acc], 0);
+                else mbar_arrive(&bars->tmem_empty[acc]);
+            }
             if (row_ok && best > -INFINITY)
                 atomicMax(P.rowkey + (size_t)b * P.ncap + row,
                           ((unsigned long long)f32_orderable(best + 0.0f) << 32) | (0xffffffffu - (uint32_t)best_j));
@@ -430,10 +552,13 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();  // neither CTA leaves while the other may still touch it
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        if (CG == 1)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
 }
 
@@ -486,22 +611,35 @@ int make_map(einx_ctx* ctx, CUtensorMap* map, const void* base, CUtensorMapDataT
     return EINX_OK;
 }
 
-uint32_t make_idesc(int kind) {
+uint32_t make_idesc(int kind, int cg) {
     // cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format @7/@10 (BF16 = 1, TF32 = 2),
-    // a/b K-major (0) @15/@16, N>>3 @17, M>>4 @24
+    // a/b K-major (0) @15/@16, N>>3 @17, M>>4 @24 (M = 256 across the CTA pair)
     const uint32_t fmt = kind == 0 ? 1u : 2u;
-    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)((TILE_M * cg) >> 4) << 24);
 }
 
-template <int KIND, int KB>
+template <int KIND, int KB, int CG>
 int launch_tc(einx_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, int grid, cudaStream_t stream) {
-    auto kern = mnn_tc_kernel<KIND, KB>;
-    const size_t smem = Cfg<KIND, KB>::kSmem;
+    auto kern = mnn_tc_kernel<KIND, KB, CG>;
+    using C = Cfg<KIND, KB, CG>;
+    const size_t smem = C::kSmem;
     EINX_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(C::kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     einx_prof_begin(ctx, 3, stream);
-    kern<<<grid, Cfg<KIND, KB>::kThreads, smem, stream>>>(ma, mb, P);
+    EINX_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, ma, mb, P));
     einx_prof_end(ctx, 3, stream);
-    EINX_CHECK_LAUNCH(ctx);
+    ctx->launches++;
     return EINX_OK;
 }
 
@@ -526,12 +664,20 @@ int einx_mnn_tc(einx_ctx* ctx, const float* d0, const float* d1, const int32_t* 
     memset(maps, 0, sizeof(maps));
     TcParams P = {};
     P.n0 = n0; P.n1 = n1; P.B = B; P.ncap = ncap; P.mcap = mcap;
-    P.tiles_m = (ncap + TILE_M - 1) / TILE_M;
+    // CTA pairs (cta_group::2, 256-row tiles) where the operand path is the limit: measured on B200 at
+    // 64x1024x1024x256 / 32x2048x2048x128 / 1x8192x8192x128 the pair form takes 3xTF32 from 150 / 185 /
+    // 102 us to 136 / 163 / 92 us (tensor pipe 60 % -> 76 % active), while the single-pass bf16 kernel is
+    // bound by its argmax epilogue and is 5 % faster unpaired (49 vs 52 us).  EINX_MNN_CTA_PAIR=0/1 forces.
+    static const int pair_env = getenv("EINX_MNN_CTA_PAIR") ? atoi(getenv("EINX_MNN_CTA_PAIR")) : -1;
+    const bool want_pair = pair_env < 0 ? precision != EINX_MNN_BF16 : pair_env != 0;
+    const int CG = (want_pair && ncap > TILE_M) ? 2 : 1;
+    P.tiles_m = (ncap + TILE_M * CG - 1) / (TILE_M * CG);
     P.tiles_n = (mcap + TILE_N - 1) / TILE_N;
     P.rowkey = rowkey; P.colkey = colkey;
     const int total_tiles = B * P.tiles_m * P.tiles_n;
-    int grid = ctx->num_sms < total_tiles ? ctx->num_sms : total_tiles;
+    int grid = (ctx->num_sms / CG) < total_tiles ? (ctx->num_sms / CG) : total_tiles;
     if (grid < 1) grid = 1;
+    grid *= CG;
     int rc;
     (void)scratch_bytes;
     if (precision == EINX_MNN_BF16) {
@@ -543,18 +689,22 @@ int einx_mnn_tc(einx_ctx* ctx, const float* d0, const float* d1, const int32_t* 
         to_bf16_kernel<<<blocks ? blocks : 1, 256, 0, stream>>>(d0, e0, d1, e1, a);
         EINX_CHECK_LAUNCH(ctx);
         if ((rc = make_map(ctx, &maps[0], a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (size_t)B * ncap, D, TILE_M, 128))) return rc;
-        if ((rc = make_map(ctx, &maps[1], b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (size_t)B * mcap, D, TILE_N, 128))) return rc;
+        if ((rc = make_map(ctx, &maps[1], b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (size_t)B * mcap, D, TILE_N / CG, 128))) return rc;
         P.nkb = (D * 2 + 127) / 128;
-        P.idesc = make_idesc(0);
-        return launch_tc<0, 128>(ctx, maps[0], maps[1], P, grid, stream);
+        P.idesc = make_idesc(0, CG);
+        return CG == 2 ? launch_tc<0, 128, 2>(ctx, maps[0], maps[1], P, grid, stream)
+                       : launch_tc<0, 128, 1>(ctx, maps[0], maps[1], P, grid, stream);
     }
     // TF32X3: stage depth by k-block width -- 64-byte blocks give 4 stages of 48 KB, 128-byte blocks 2 of 96 KB
     static const int kb_env = getenv("EINX_MNN_TF32_KB") ? atoi(getenv("EINX_MNN_TF32_KB")) : 0;
     const int KB = kb_env == 128 ? 128 : 64;
     if ((rc = make_map(ctx, &maps[0], d0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (size_t)B * ncap, D, TILE_M, KB))) return rc;
-    if ((rc = make_map(ctx, &maps[1], d1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (size_t)B * mcap, D, TILE_N, KB))) return rc;
+    if ((rc = make_map(ctx, &maps[1], d1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (size_t)B * mcap, D, TILE_N / CG, KB))) return rc;
     P.nkb = (D * 4 + KB - 1) / KB;
-    P.idesc = make_idesc(1);
-    return KB == 128 ? launch_tc<1, 128>(ctx, maps[0], maps[1], P, grid, stream)
-                     : launch_tc<1, 64>(ctx, maps[0], maps[1], P, grid, stream);
+    P.idesc = make_idesc(1, CG);
+    if (CG == 2)
+        return KB == 128 ? launch_tc<1, 128, 2>(ctx, maps[0], maps[1], P, grid, stream)
+                         : launch_tc<1, 64, 2>(ctx, maps[0], maps[1], P, grid, stream);
+    return KB == 128 ? launch_tc<1, 128, 1>(ctx, maps[0], maps[1], P, grid, stream)
+                     : launch_tc<1, 64, 1>(ctx, maps[0], maps[1], P, grid, stream);
 }

@@ -55,6 +55,32 @@ def bench_mnn(args):
             print(f"mnn {shape} {prec}: entry {total:.4f} ms, similarity kernel {k:.4f} ms = {flops / k / 1e9:.1f} TFLOP/s algorithmic", flush=True)
 
 
+def bench_next(args):
+    """Rows adjacent to the path (SURVEY.md section 8 f) at the sizes of a config."""
+    c = synth.CONFIGS[args.config]
+    B = args.batch
+    H, W, cell = c["H"], c["W"], c["cell"]
+    Hp, Wp, _ = synth.padded_size(H, W, cell)
+    rng = np.random.default_rng(0)
+    evs = [synth.events(rng, c["events"], H, W, c["style"], c["dt"]) for _ in range(B)]
+    x, y, t, p, off = (a.to(DEV) for a in einx.pack_events(evs))
+    nev = x.numel()
+    ms = time_ms(lambda: einx.events_image_device(x, y, off, H, W))
+    print(f"events_image {B}x{c['events']} ev -> {H}x{W}: {ms:.4f} ms = {(8 * nev + B * H * W) / ms / 1e6:.0f} GB/s algorithmic", flush=True)
+    img = einx.events_image_device(x, y, off, H, W)
+    ms = time_ms(lambda: einx.events_mask(img, cell))
+    print(f"events_mask -> {Hp}x{Wp}: {ms:.4f} ms = {(B * H * W + B * Hp * Wp) / ms / 1e6:.0f} GB/s algorithmic", flush=True)
+    if cell > 1:
+        C = cell * cell + 1
+        lo = torch.randn((B, C, Hp // cell, Wp // cell), device=DEV)
+        ms = time_ms(lambda: einx.logits_to_score(lo, cell))
+        print(f"logits_to_score {B}x{C}x{Hp // cell}x{Wp // cell}: {ms:.4f} ms = {(lo.numel() * 4 + B * Hp * Wp * 4) / ms / 1e6:.0f} GB/s algorithmic", flush=True)
+    K = c["top_k"]
+    sc = torch.randn((B, K + 1, K + 1), device=DEV) - 5
+    ms = time_ms(lambda: einx.filter_matches(sc, 0.1))
+    print(f"filter_matches {B}x{K + 1}x{K + 1}: {ms:.4f} ms = {sc.numel() * 4 / ms / 1e6:.0f} GB/s algorithmic", flush=True)
+
+
 def bench_stages(args):
     ctx = einx.context_for(DEV)
     c = synth.CONFIGS[args.config]
@@ -103,11 +129,11 @@ def bench_stages(args):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["mnn", "stages"])
+    ap.add_argument("what", choices=["mnn", "stages", "next"])
     ap.add_argument("--shapes", default="64x1024x1024x256,32x2048x2048x128,1x8192x8192x128")
     ap.add_argument("--precisions", default="tf32x3,bf16")
     ap.add_argument("--config", default="c2_ec_superpoint")
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--precision", default="tf32x3")
     a = ap.parse_args()
-    (bench_mnn if a.what == "mnn" else bench_stages)(a)
+    {"mnn": bench_mnn, "stages": bench_stages, "next": bench_next}[a.what](a)
