@@ -1,0 +1,101 @@
+"""Whole-path orchestration on the GPU: the three-stream fork/join, per-stream contexts and the
+host-streaming driver must give exactly what the serial single-stream path gives."""
+import dataclasses
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = torch.device("cuda", 0)
+KEYS = ("voxel_grid", "keypoints0", "keypoints1", "counts0", "counts1", "descriptors0", "descriptors1", "matches0",
+        "matches1", "matching_scores0", "num_matches", "matched_kpts0", "matched_kpts1")
+
+
+@pytest.fixture(scope="module")
+def einx():
+    import einx as m
+
+    m.context_for(DEV)
+    return m
+
+
+@pytest.fixture(scope="module")
+def batch(einx):
+    synth = importlib.import_module("ei-nexus_official_b200.synth")
+    cfgname, B = "c2_ec_superpoint", 6
+    c = synth.CONFIGS[cfgname]
+    evs, s0, r0, s1, r1 = [], [], [], [], []
+    for i in range(B):
+        ev, sides = synth.pair_inputs(cfgname, 100 + i, 20_000 + 1000 * i)  # ragged windows
+        evs.append(ev)
+        s0.append(sides[0][0]); r0.append(sides[0][1]); s1.append(sides[1][0]); r1.append(sides[1][1])
+    maps = [np.concatenate(a) for a in (s0, r0, s1, r1)]
+    cfg = einx.PathConfig(bins=c["bins"], height=c["H"], width=c["W"], top_k=c["top_k"], descriptor_mode=c["kind"],
+                          descriptor_scale=c["scale"], precision="tf32x3")
+    return cfg, evs, maps
+
+
+def run(einx, cfg, evs, maps):
+    pipe = einx.ExtractMatchPipeline(cfg)
+    ev = tuple(t.to(DEV) for t in einx.pack_events(evs))
+    out = pipe(ev, *(torch.from_numpy(m.copy()).to(DEV) for m in maps))
+    torch.cuda.synchronize()
+    return {k: out[k].cpu() for k in KEYS}
+
+
+def valid_rows_equal(a, b, counts):
+    return all(torch.equal(a[i, :n], b[i, :n]) for i, n in enumerate(counts.tolist()))
+
+
+def test_three_streams_match_serial(einx, batch):
+    cfg, evs, maps = batch
+    serial = run(einx, dataclasses.replace(cfg, concurrent=False), evs, maps)
+    for _ in range(3):  # repeated: a cross-stream race would not be deterministic
+        conc = run(einx, dataclasses.replace(cfg, concurrent=True), evs, maps)
+        # the voxel scatter accumulates with atomics: order-dependent to 1e-5 like the reference itself
+        assert torch.allclose(conc["voxel_grid"], serial["voxel_grid"], rtol=1e-5, atol=1e-5)
+        assert torch.equal(conc["counts0"], serial["counts0"]) and torch.equal(conc["counts1"], serial["counts1"])
+        for side in "01":
+            n = serial[f"counts{side}"]
+            assert valid_rows_equal(conc[f"keypoints{side}"], serial[f"keypoints{side}"], n)
+            assert valid_rows_equal(conc[f"descriptors{side}"], serial[f"descriptors{side}"], n)
+        assert valid_rows_equal(conc["matches0"], serial["matches0"], serial["counts0"])
+        assert torch.equal(conc["num_matches"], serial["num_matches"])
+        assert valid_rows_equal(conc["matched_kpts0"], serial["matched_kpts0"], serial["num_matches"])
+        assert valid_rows_equal(conc["matched_kpts1"], serial["matched_kpts1"], serial["num_matches"])
+
+
+def test_one_context_per_stream(einx):
+    main_ctx = einx.context_for(DEV)
+    s = torch.cuda.Stream(DEV)
+    with torch.cuda.stream(s):
+        side_ctx = einx.context_for(DEV)
+        assert einx.context_for(DEV) is side_ctx
+    assert side_ctx is not main_ctx and einx.context_for(DEV) is main_ctx
+    assert {id(main_ctx), id(side_ctx)} <= {id(c) for c in einx.contexts_of(DEV)}
+    assert einx.launch_count(DEV) >= main_ctx.launches
+
+
+@pytest.mark.parametrize("chunks", [1, 4])
+def test_host_streamer_matches_device_path(einx, batch, chunks):
+    cfg, evs, maps = batch
+    ref = run(einx, cfg, evs, maps)
+    B, K = len(evs), cfg.top_k
+    hb = einx.HostBatch(evs, *maps, chunks=chunks)
+    assert len(hb.chunks) == chunks and hb.batch == B
+    assert hb.nbytes == sum(20 * len(e["t"]) for e in evs) + 8 * (B + chunks) + sum(m.nbytes for m in maps)
+    out_host = {"matches0": torch.full((B, K), -7, dtype=torch.int64).pin_memory(),
+                "num_matches": torch.zeros((B,), dtype=torch.int32).pin_memory(),
+                "matched_kpts0": torch.zeros((B, K, 3)).pin_memory(),
+                "matched_kpts1": torch.zeros((B, K, 3)).pin_memory()}
+    streamer = einx.HostStreamer(einx.ExtractMatchPipeline(cfg), DEV)
+    for _ in range(2):  # second pass reuses the staging buffers
+        streamer.run(hb, out_host)
+    torch.cuda.synchronize()
+    assert torch.equal(out_host["num_matches"], ref["num_matches"])
+    assert valid_rows_equal(out_host["matches0"], ref["matches0"], ref["counts0"])
+    assert valid_rows_equal(out_host["matched_kpts0"], ref["matched_kpts0"], ref["num_matches"])
+    assert valid_rows_equal(out_host["matched_kpts1"], ref["matched_kpts1"], ref["num_matches"])
