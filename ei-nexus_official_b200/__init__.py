@@ -13,7 +13,7 @@ from .detection import (depth_to_space, detect, events_mask, logits_to_prob, log
 from .dist import gather_matches, pack_matches, shard_range
 from .match import NearestNeighborMatcher, filter_matches, mnn, mnn_dense
 from .patch import patch_reference
-from .pipeline import ExtractMatchPipeline, HostBatch, HostStreamer, PathConfig
+from .pipeline import CapturedStep, ExtractMatchPipeline, HostBatch, HostStreamer, PathConfig
 from .voxel import (draw_events_accumulation_image, events_image_device, events_to_voxel_grid, pack_events,
                     time_normalization, voxelize_batch, voxelize_device)
 
@@ -21,7 +21,7 @@ __all__ = [
     "EinxError", "context_for", "contexts_of", "launch_count", "events_to_voxel_grid", "time_normalization", "pack_events", "voxelize_batch",
     "voxelize_device", "detect", "prob_map_to_points_map", "prob_map_to_positions_with_prob", "sample",
     "sparsify_full_resolution_descriptors", "sparsify_low_resolution_descriptors", "NearestNeighborMatcher",
-    "mnn", "mnn_dense", "ExtractMatchPipeline", "HostBatch", "HostStreamer", "PathConfig", "patch_reference", "shard_range", "pack_matches",
+    "mnn", "mnn_dense", "ExtractMatchPipeline", "CapturedStep", "HostBatch", "HostStreamer", "PathConfig", "patch_reference", "shard_range", "pack_matches",
     "gather_matches", "logits_to_prob", "depth_to_space", "logits_to_score", "events_mask",
     "draw_events_accumulation_image", "events_image_device", "filter_matches",
 ]

@@ -39,6 +39,7 @@ class ExtractMatchPipeline:
     def __init__(self, cfg: PathConfig):
         self.cfg = cfg
         self._side_streams = {}
+        self._capture_streams = {}
 
     @torch.no_grad()
     def voxelize(self, x, y, t, p, offsets) -> torch.Tensor:
@@ -87,18 +88,56 @@ class ExtractMatchPipeline:
             k0, c0, d0 = self.extract(score0, raw0, mask0)
             main.wait_stream(s_side)
             main.wait_stream(s_vox)
-            # caching-allocator bookkeeping: tensors cross streams in both directions
-            for t in (k1, c1, d1, grid):
-                t.record_stream(main)
-            for t in (score1, raw1, mask1):
-                if t is not None:
-                    t.record_stream(s_side)
-            for t in events:
-                t.record_stream(s_vox)
+            if not torch.cuda.is_current_stream_capturing():
+                # caching-allocator bookkeeping: tensors cross streams in both directions (a captured
+                # step owns its memory pool for the lifetime of the graph instead)
+                for t in (k1, c1, d1, grid):
+                    t.record_stream(main)
+                for t in (score1, raw1, mask1):
+                    if t is not None:
+                        t.record_stream(s_side)
+                for t in events:
+                    t.record_stream(s_vox)
         out = match.mnn(d0, d1, c0, c1, k0, k1, None, None, True, self.cfg.precision)
         out.update(voxel_grid=grid, keypoints0=k0, keypoints1=k1, counts0=c0, counts1=c1,
                    descriptors0=d0, descriptors1=d1)
         return out
+
+    def capture(self, events, score0, raw0, score1, raw1, mask0=None, mask1=None) -> "CapturedStep":
+        """Record one step over these (fixed) device buffers into a CUDA graph.
+
+        The dozen launches of a step and their fork/join edges then cost one graph launch; the caller
+        refreshes the input buffers in place (or keeps one captured step per resident batch) and calls
+        ``replay()``.  Warm-up runs first on the capture stream so that every per-stream context has its
+        workspace before capture starts (cudaMalloc is not capturable)."""
+        dev = score0.device
+        cur = torch.cuda.current_stream(dev)
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
+        cap = self._capture_streams.get(key)
+        if cap is None:
+            cap = self._capture_streams[key] = torch.cuda.Stream(dev)
+        args = (events, score0, raw0, score1, raw1, mask0, mask1)
+        cap.wait_stream(cur)
+        with torch.cuda.stream(cap):
+            for _ in range(2):
+                self(*args)
+        cap.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=cap):
+            out = self(*args)
+        cur.wait_stream(cap)
+        return CapturedStep(graph, out, args)
+
+
+class CapturedStep:
+    """A step of the path frozen into a CUDA graph (see ExtractMatchPipeline.capture)."""
+
+    def __init__(self, graph, outputs, inputs):
+        self.graph, self.outputs, self.inputs = graph, outputs, inputs  # inputs kept alive: the graph reads them
+
+    def replay(self) -> Dict[str, torch.Tensor]:
+        self.graph.replay()
+        return self.outputs
 
 
 class HostBatch:

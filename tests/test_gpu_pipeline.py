@@ -99,3 +99,26 @@ def test_host_streamer_matches_device_path(einx, batch, chunks):
     assert valid_rows_equal(out_host["matches0"], ref["matches0"], ref["counts0"])
     assert valid_rows_equal(out_host["matched_kpts0"], ref["matched_kpts0"], ref["num_matches"])
     assert valid_rows_equal(out_host["matched_kpts1"], ref["matched_kpts1"], ref["num_matches"])
+
+
+def test_captured_step_replays_exactly(einx, batch):
+    cfg, evs, maps = batch
+    ref = run(einx, cfg, evs, maps)
+    pipe = einx.ExtractMatchPipeline(cfg)
+    ev = tuple(t.to(DEV) for t in einx.pack_events(evs))
+    dmaps = [torch.from_numpy(m.copy()).to(DEV) for m in maps]
+    step = pipe.capture(ev, *dmaps)
+    for _ in range(3):
+        out = step.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out["counts0"].cpu(), ref["counts0"]) and torch.equal(out["num_matches"].cpu(), ref["num_matches"])
+    assert valid_rows_equal(out["matches0"].cpu(), ref["matches0"], ref["counts0"])
+    assert valid_rows_equal(out["keypoints1"].cpu(), ref["keypoints1"], ref["counts1"])
+    assert valid_rows_equal(out["matched_kpts1"].cpu(), ref["matched_kpts1"], ref["num_matches"])
+    # refreshed inputs, same buffers: replay follows the data
+    dmaps[0].copy_(torch.from_numpy(maps[2]))   # side 0 now sees side 1's score map
+    dmaps[1].copy_(torch.from_numpy(maps[3]))
+    out = step.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out["counts0"].cpu(), ref["counts1"])
+    assert valid_rows_equal(out["keypoints0"].cpu(), ref["keypoints1"], ref["counts1"])

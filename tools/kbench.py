@@ -125,6 +125,9 @@ def bench_stages(args):
         pp = einx.ExtractMatchPipeline(dataclasses.replace(cfg, concurrent=conc))
         total = time_ms(lambda: pp(ev, s0, r0, s1, r1), iters=50)
         print(f"pipeline ({'3 streams' if conc else 'serial'}): {total:.4f} ms/step = {B / total * 1e3:.0f} pairs/s", flush=True)
+        step = pp.capture(ev, s0, r0, s1, r1)
+        total = time_ms(step.replay, iters=50)
+        print(f"pipeline ({'3 streams' if conc else 'serial'}, CUDA graph): {total:.4f} ms/step = {B / total * 1e3:.0f} pairs/s", flush=True)
 
 
 if __name__ == "__main__":
