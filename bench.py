@@ -151,7 +151,7 @@ def workload_config(args, synth):
         "mnn_precision": args.precision,
         "streams": "1 (serial)" if args.serial else "3 (voxelise | side 0 | side 1, joined before MNN)",
         "e2e_chunks": args.e2e_chunks,
-        "launch": "CUDA graph replay, one captured step per resident batch (e2e arm: eager)" if args.graph else "eager",
+        "launch": "eager" if args.no_graph else "CUDA graph replay, one captured step per resident batch (e2e arm: eager)",
         "l2_policy": f"{NUM_INPUT_SETS} distinct resident input batches rotated between steps (inputs larger than L2)",
     }
 
@@ -350,7 +350,7 @@ def run_einx(args, synth):
     # e2e arm first: eager launches through the host-facing API (graph capture below empties torch's
     # caching allocator and would leave this arm re-growing its pools inside the timed region)
     ms_e2e, _ = timed(step_e2e, args.steps, max(3, args.warmup))
-    if args.graph:
+    if not args.no_graph:
         # one captured step per resident batch: a step is then a single CUDA-graph launch
         captured.extend(pipe.capture(ev, s0, r0, s1, r1) for ev, (s0, r0, s1, r1) in dev_sets)
     ms, window = timed(step_device, args.steps, args.warmup)
@@ -477,11 +477,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="einx", choices=["einx", "reference"])
     ap.add_argument("--config", default="c2_ec_superpoint")
-    ap.add_argument("--e2e-chunks", type=int, default=4, help="sub-batches per step of the e2e arm (copy/compute overlap)")
+    ap.add_argument("--e2e-chunks", type=int, default=2, help="sub-batches per step of the e2e arm (copy/compute overlap)")
     ap.add_argument("--serial", action="store_true", help="run the stages of a step on one stream (no fork/join)")
-    ap.add_argument("--graph", action="store_true",
-                    help="replay one captured CUDA graph per resident batch instead of issuing every step eagerly "
-                         "(measured on B200: 0.424 vs 0.425 ms/step with rotating batches -- the step is not launch bound)")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="issue every step of the device arm eagerly instead of replaying one captured CUDA graph per "
+                         "resident batch (eager issue costs ~250 us of host time per step against ~420 us of GPU time, "
+                         "so a busy host CPU makes the eager arm host bound; the graph arm is one launch per step)")
     ap.add_argument("--batch", type=int, default=None, help="pairs per GPU per step")
     ap.add_argument("--precision", default=os.environ.get("EINX_MNN_PRECISION", "tf32x3"), choices=["fp32", "tf32x3", "bf16"],
                     help="MNN arithmetic: tf32x3 (default; fp32-accurate on the tensor pipe), fp32 (FFMA), bf16")

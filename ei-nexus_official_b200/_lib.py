@@ -74,6 +74,7 @@ class Context:
             msg = self.lib.einx_last_error(None)
             raise EinxError(f"einx_create({device}) failed ({rc}): {msg.decode() if msg else ''}")
         self.handle = h
+        self.stream = C.c_void_p(0)  # set by context_for: the one stream this context serves
 
     def check(self, rc: int, what: str):
         if rc != 0:
@@ -106,21 +107,36 @@ class Context:
 _contexts = {}
 
 
+def _raw_stream(idx: int) -> int:
+    import torch
+
+    try:
+        return int(torch._C._cuda_getCurrentRawStream(idx))  # one C call; the public path builds a Stream object
+    except AttributeError:  # pragma: no cover
+        return int(torch.cuda.current_stream(idx).cuda_stream)
+
+
 def context_for(device) -> Context:
     """Context of a torch device / ordinal and of the CURRENT stream on it (created on first use).
 
     One einx_ctx owns one stream-ordered workspace, so kernels issued on different streams must not
-    share it: every (device, stream) pair gets its own context and concurrent streams never alias."""
+    share it: every (device, stream) pair gets its own context and concurrent streams never alias.
+    ``ctx.stream`` is that stream as the ``einx_stream`` argument of the C ABI."""
     import torch
 
-    dev = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
-    if dev.type != "cuda":
-        raise EinxError(f"einx kernels run on CUDA sm_100a only; got device '{dev}'. There is no CPU fallback.")
-    idx = dev.index if dev.index is not None else torch.cuda.current_device()
-    key = (idx, int(torch.cuda.current_stream(idx).cuda_stream))
+    if isinstance(device, int):
+        idx = device
+    else:
+        dev = device if isinstance(device, torch.device) else torch.device(device)
+        if dev.type != "cuda":
+            raise EinxError(f"einx kernels run on CUDA sm_100a only; got device '{dev}'. There is no CPU fallback.")
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    sid = _raw_stream(idx)
+    key = (idx, sid)
     ctx = _contexts.get(key)
     if ctx is None:
         ctx = _contexts[key] = Context(idx)
+        ctx.stream = C.c_void_p(sid)
     return ctx
 
 
@@ -144,6 +160,4 @@ def ptr(t):
 
 
 def stream_of(device):
-    import torch
-
-    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    return context_for(device).stream

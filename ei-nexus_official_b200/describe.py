@@ -42,7 +42,7 @@ def sample(raw: torch.Tensor, kpts: torch.Tensor, counts: torch.Tensor, mode: in
     desc = torch.empty((B, kcap, C), dtype=torch.float32, device=dev)
     rc = ctx.lib.einx_sample(ctx.handle, _lib.ptr(raw), B, C, Hd, Wd, mode, int(image_size[0]), int(image_size[1]),
                              _lib.ptr(kpts), _lib.ptr(counts), kcap, float(scale_factor), int(bool(normalize)),
-                             _lib.ptr(desc), _lib.stream_of(dev))
+                             _lib.ptr(desc), ctx.stream)
     ctx.check(rc, "einx_sample")
     return desc
 

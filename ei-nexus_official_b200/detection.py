@@ -61,7 +61,7 @@ def detect(score: torch.Tensor, prob_thresh: float, nms_dist: int, border_dist: 
         mptr = _lib.ptr(m8)
     rc = ctx.lib.einx_detect(ctx.handle, _lib.ptr(score), mptr, B, Hp, Wp, int(nms_dist), int(border_dist),
                              float(prob_thresh), k, _lib.ptr(nms_map), _lib.ptr(kpts), kcap, _lib.ptr(counts),
-                             _lib.stream_of(dev))
+                             ctx.stream)
     ctx.check(rc, "einx_detect")
     return nms_map, kpts, counts
 
@@ -134,7 +134,7 @@ def _head(x: torch.Tensor, cell: int, mode: int) -> torch.Tensor:
     shape = (B, C, Hc, Wc) if mode == HEAD_PROB else (B, 1, Hc * cell, Wc * cell)
     out = torch.empty(shape, dtype=torch.float32, device=dev)
     rc = ctx.lib.einx_logits_to_score(ctx.handle, _lib.ptr(x), B, C, Hc, Wc, int(cell), mode, _lib.ptr(out),
-                                      _lib.stream_of(dev))
+                                      ctx.stream)
     ctx.check(rc, "einx_logits_to_score")
     return out
 
@@ -194,6 +194,6 @@ def events_mask(events_image: torch.Tensor, cell_size: int = 1) -> torch.Tensor:
     ctx = _lib.context_for(dev)
     mask = torch.empty((B, 1, Hp, Wp), dtype=torch.uint8, device=dev)
     rc = ctx.lib.einx_mask_dilate(ctx.handle, _lib.ptr(img), B, H, W, hp // 2, wp // 2, Hp, Wp, _lib.ptr(mask),
-                                  _lib.stream_of(dev))
+                                  ctx.stream)
     ctx.check(rc, "einx_mask_dilate")
     return mask.view(torch.bool)

@@ -51,7 +51,7 @@ def mnn(desc0: torch.Tensor, desc1: torch.Tensor, n0: Optional[torch.Tensor] = N
     rc = ctx.lib.einx_mnn(ctx.handle, _lib.ptr(desc0), _lib.ptr(desc1), _lib.ptr(n0), _lib.ptr(n1), B, N, M, D,
                           float(ratio_thresh or 0.0), float(distance_thresh or 0.0), int(bool(mutual)), prec,
                           _lib.ptr(m0), _lib.ptr(m1), _lib.ptr(s0), _lib.ptr(s1), _lib.ptr(kpts0), _lib.ptr(kpts1),
-                          _lib.ptr(mk0), _lib.ptr(mk1), _lib.ptr(nm), _lib.stream_of(dev))
+                          _lib.ptr(mk0), _lib.ptr(mk1), _lib.ptr(nm), ctx.stream)
     ctx.check(rc, "einx_mnn")
     out = {"matches0": m0, "matches1": m1, "matching_scores0": s0, "matching_scores1": s1}
     if kpts0 is not None:
@@ -70,7 +70,7 @@ def mnn_dense(desc0: torch.Tensor, desc1: torch.Tensor):
     sim = torch.empty((B, N, M), dtype=torch.float32, device=dev)
     la = torch.empty((B, N + 1, M + 1), dtype=torch.float32, device=dev)
     rc = ctx.lib.einx_mnn_dense(ctx.handle, _lib.ptr(desc0), _lib.ptr(desc1), B, N, M, D, _lib.ptr(sim),
-                                _lib.ptr(la), _lib.stream_of(dev))
+                                _lib.ptr(la), ctx.stream)
     ctx.check(rc, "einx_mnn_dense")
     return sim, la
 
@@ -136,6 +136,6 @@ def filter_matches(scores: torch.Tensor, th: float):
     s0 = torch.empty((B, M), dtype=torch.float32, device=dev)
     s1 = torch.empty((B, N), dtype=torch.float32, device=dev)
     rc = ctx.lib.einx_filter_matches(ctx.handle, _lib.ptr(scores), B, M, N, float(th), _lib.ptr(m0), _lib.ptr(m1),
-                                     _lib.ptr(s0), _lib.ptr(s1), _lib.stream_of(dev))
+                                     _lib.ptr(s0), _lib.ptr(s1), ctx.stream)
     ctx.check(rc, "einx_filter_matches")
     return m0, m1, s0, s1

@@ -142,7 +142,12 @@ class CapturedStep:
 
 class HostBatch:
     """Pinned host inputs of one batch of pairs, split into ``len(chunks)`` contiguous sub-batches so
-    that the host->device copy of one sub-batch overlaps the kernels of the previous one."""
+    that the host->device copy of one sub-batch overlaps the kernels of the previous one.
+
+    Every sub-batch is ONE pinned byte buffer holding its nine arrays (x, y, t, p, offsets, score0, raw0,
+    score1, raw1) back to back at 256-byte aligned offsets, so it crosses PCIe as a single large copy."""
+
+    ALIGN = 256
 
     def __init__(self, events: Sequence[dict], score0, raw0, score1, raw1, chunks: int = 4):
         B = len(events)
@@ -151,14 +156,33 @@ class HostBatch:
         self.batch = B
         self.chunks: List[tuple] = []
         for a, b in zip(bounds[:-1], bounds[1:]):
-            ev = voxel.pack_events(events[a:b], pin=True)
-            maps = tuple(torch.from_numpy(m[a:b]).pin_memory() if not torch.is_tensor(m) else m[a:b].pin_memory()
-                         for m in (score0, raw0, score1, raw1))
-            self.chunks.append((a, b, ev, maps))
+            ev = voxel.pack_events(events[a:b])
+            maps = [torch.from_numpy(m[a:b]) if not torch.is_tensor(m) else m[a:b] for m in (score0, raw0, score1, raw1)]
+            arrays = [t.contiguous() for t in (*ev, *maps)]
+            layout, off = [], 0
+            for t in arrays:
+                layout.append((off, t.dtype, tuple(t.shape)))
+                off += (t.numel() * t.element_size() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+            buf = torch.empty(off, dtype=torch.uint8).pin_memory()
+            for t, (o, dt, shape) in zip(arrays, layout):
+                n = t.numel() * t.element_size()
+                buf[o:o + n].view(dt).view(shape).copy_(t)
+            self.chunks.append((a, b, buf, layout, sum(t.numel() * t.element_size() for t in arrays)))
 
     @property
     def nbytes(self) -> int:
-        return sum(t.numel() * t.element_size() for _, _, ev, maps in self.chunks for t in (*ev, *maps))
+        """Payload bytes (without alignment padding)."""
+        return sum(c[4] for c in self.chunks)
+
+    @staticmethod
+    def views(buf: torch.Tensor, layout):
+        out = []
+        for o, dt, shape in layout:
+            n = 1
+            for d in shape:
+                n *= d
+            out.append(buf[o:o + n * torch.empty((), dtype=dt).element_size()].view(dt).view(shape))
+        return out
 
 
 RESULT_KEYS = ("matches0", "matching_scores0", "num_matches", "matched_kpts0", "matched_kpts1")
@@ -179,43 +203,28 @@ class HostStreamer:
         self._stage = {}
         self._free = [None, None]  # event: the kernels that read staging set k have finished
 
-    def _staging(self, k, ev, maps):
-        key = (k, tuple(t.shape[1:] for t in maps))
-        st = self._stage.get(key)
-        need_ev = ev[0].numel()
-        need_b = maps[0].shape[0]
-        if st is None or st["ev_cap"] < need_ev or st["b_cap"] < need_b:
-            st = self._stage[key] = {
-                "ev_cap": need_ev, "b_cap": need_b,
-                "ev": tuple(torch.empty(need_ev, dtype=t.dtype, device=self.dev) for t in ev[:4]),
-                "off": torch.empty(need_b + 1, dtype=torch.int64, device=self.dev),
-                "maps": tuple(torch.empty((need_b, *m.shape[1:]), dtype=m.dtype, device=self.dev) for m in maps),
-            }
+    def _staging(self, k, nbytes):
+        st = self._stage.get(k)
+        if st is None or st.numel() < nbytes:
+            st = self._stage[k] = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
         return st
 
     @torch.no_grad()
     def run(self, hb: HostBatch, out_host: Dict[str, torch.Tensor]) -> None:
         main = torch.cuda.current_stream(self.dev)
         self.copy_stream.wait_stream(main)
-        for i, (a, b, ev, maps) in enumerate(hb.chunks):
+        for i, (a, b, hbuf, layout, _) in enumerate(hb.chunks):
             k = i & 1
-            st = self._staging(k, ev, maps)
-            n_ev, nb = ev[0].numel(), b - a
+            dbuf = self._staging(k, hbuf.numel())[:hbuf.numel()]
             with torch.cuda.stream(self.copy_stream):
                 if self._free[k] is not None:
                     self.copy_stream.wait_event(self._free[k])
-                d_ev = tuple(d[:n_ev] for d in st["ev"])
-                for d, h in zip(d_ev, ev[:4]):
-                    d.copy_(h, non_blocking=True)
-                d_off = st["off"][:nb + 1]
-                d_off.copy_(ev[4], non_blocking=True)
-                d_maps = tuple(d[:nb] for d in st["maps"])
-                for d, h in zip(d_maps, maps):
-                    d.copy_(h, non_blocking=True)
+                dbuf.copy_(hbuf, non_blocking=True)
                 ready = torch.cuda.Event()
                 ready.record(self.copy_stream)
             main.wait_event(ready)
-            out = self.pipe((*d_ev, d_off), d_maps[0], d_maps[1], d_maps[2], d_maps[3])
+            x, y, t, p, off, s0, r0, s1, r1 = HostBatch.views(dbuf, layout)
+            out = self.pipe((x, y, t, p, off), s0, r0, s1, r1)
             for key in RESULT_KEYS:
                 if key in out_host:
                     out_host[key][a:b].copy_(out[key], non_blocking=True)

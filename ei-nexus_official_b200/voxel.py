@@ -66,7 +66,7 @@ def voxelize_device(x, y, t, p, offsets, input_size: Tuple[int, int, int], norma
     if out is None:
         out = torch.empty((B, bins, H, W), dtype=torch.float32, device=dev)
     rc = ctx.lib.einx_voxelize(ctx.handle, _lib.ptr(x), _lib.ptr(y), _lib.ptr(t), _lib.ptr(p), _lib.ptr(offsets),
-                               B, bins, H, W, int(bool(normalize)), _lib.ptr(out), _lib.stream_of(dev))
+                               B, bins, H, W, int(bool(normalize)), _lib.ptr(out), ctx.stream)
     ctx.check(rc, "einx_voxelize")
     return out
 
@@ -115,7 +115,7 @@ def events_image_device(x: torch.Tensor, y: torch.Tensor, offsets: torch.Tensor,
     out = torch.empty((B, int(height), int(width)), dtype=torch.uint8, device=dev)
     rc = ctx.lib.einx_events_image(ctx.handle, _lib.ptr(x.contiguous()), _lib.ptr(y.contiguous()),
                                    int(x.dtype == torch.float64), _lib.ptr(offsets.contiguous()), B, int(height),
-                                   int(width), _lib.ptr(out), _lib.stream_of(dev))
+                                   int(width), _lib.ptr(out), ctx.stream)
     ctx.check(rc, "einx_events_image")
     return out
 
