@@ -114,7 +114,7 @@ sample_bilinear_slab_kernel(const float* __restrict__ raw, int C, int Hd, int Wd
                             int normalize, float* __restrict__ desc, int SP) {
     extern __shared__ __align__(16) float slab[];  // [C][SP]: rows y0, y0+1 of every channel
     __shared__ Tap taps[kSlabThreads];
-    __shared__ int s_first[kSlabWarps], s_last[kSlabWarps];
+    __shared__ int s_bound[2];
     const int b = blockIdx.y;
     const int y0 = (int)blockIdx.x - 1;  // upper tap row of this CTA's keypoints, -1 .. Hd-1
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -157,29 +157,33 @@ sample_bilinear_slab_kernel(const float* __restrict__ raw, int C, int Hd, int Wd
         for (size_t i = tid; i < nz; i += kSlabThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 
-    // ---- keypoints are in raster order, so this CTA's keypoints form one contiguous run [first, last]
+    // ---- keypoints are in raster order, so floor(iy) never decreases along the list and this CTA's
+    // keypoints form one contiguous run [first, last]: two warps find its ends with a 32-ary search over
+    // the exact row expression (instead of every CTA evaluating all keypoints of the image)
     const float* kp = kpts + (size_t)b * kcap * 3;
-    int first = cnt, last = -1;
-    for (int base = 0; base < cnt; base += 4 * kSlabThreads) {
-        float py[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {  // all loads in flight before the first use
-            const int k = base + u * kSlabThreads + tid;
-            py[u] = k < cnt ? __ldg(kp + 3 * k) : 0.0f;
+    if (warp < 2) {
+        const int target = y0 + warp;  // warp 0: first k with row >= y0; warp 1: first k with row >= y0 + 1
+        int L = 0, R = cnt;
+        while (R > L) {
+            const int n = R - L, st = (n + 31) >> 5, i = L + lane * st;
+            const bool in = i < R;
+            const bool pr = in && (int)floorf(bilinear_unnormalize(__ldg(kp + 3 * i), Hp, Hd)) >= target;
+            const unsigned valid = __ballot_sync(0xffffffffu, in), hit = __ballot_sync(0xffffffffu, pr);
+            if (hit) {
+                const int j = __ffs(hit) - 1;
+                R = L + j * st;
+                if (j == 0) break;
+                L = L + (j - 1) * st + 1;
+            } else {
+                L = L + (31 - __clz(valid)) * st + 1;
+            }
+            if (st == 1) break;
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int k = base + u * kSlabThreads + tid;
-            if (k < cnt && (int)floorf(bilinear_unnormalize(py[u], Hp, Hd)) == y0) { first = min(first, k); last = max(last, k); }
-        }
+        if (lane == 0) s_bound[warp] = R;
     }
-    first = __reduce_min_sync(0xffffffffu, first);
-    last = __reduce_max_sync(0xffffffffu, last);
-    if (lane == 0) { s_first[warp] = first; s_last[warp] = last; }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-#pragma unroll
-    for (int w = 0; w < kSlabWarps; ++w) { first = min(first, s_first[w]); last = max(last, s_last[w]); }
+    const int first = s_bound[0], last = s_bound[1] - 1;
     if (last < first) return;
 
     for (int base = first; base <= last; base += kSlabThreads) {
@@ -206,36 +210,60 @@ sample_bilinear_slab_kernel(const float* __restrict__ raw, int C, int Hd, int Wd
         }
         __syncthreads();
         const int n = min(kSlabThreads, last - base + 1);
-        for (int e = warp; e < n; e += kSlabWarps) {
-            const Tap t = taps[e];
-            if (t.k < 0) continue;
-            float v[NJ];
-            float ss = 0.0f;
+        // two keypoints per warp and iteration: their tap loads, norm reductions (five dependent shuffles
+        // each) and stores interleave instead of running back to back
+        for (int e = warp; e < n; e += 2 * kSlabWarps) {
+            const Tap t0 = taps[e];
+            const bool has1 = e + kSlabWarps < n;
+            const Tap t1 = taps[has1 ? e + kSlabWarps : e];
+            const bool live0 = t0.k >= 0, live1 = has1 && t1.k >= 0;
+            if (!live0 && !live1) continue;
+            float v0[NJ], v1[NJ];
+            float ss0 = 0.0f, ss1 = 0.0f;
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
                 const int c = lane + 32 * j;
-                float acc = 0.0f;
+                float a0 = 0.0f, a1 = 0.0f;
                 if (NJ != kMaxPerLane || c < C) {
-                    const float* s = slab + c * SP;  // odd pitch: the 32 channel lanes hit 32 banks
-                    acc = __fmul_rn(s[t.xa], t.w00);
-                    acc = fmaf(s[t.xb], t.w01, acc);
-                    acc = fmaf(s[Wd + t.xa], t.w10, acc);
-                    acc = fmaf(s[Wd + t.xb], t.w11, acc);
+                    const float* sp = slab + c * SP;  // odd pitch: the 32 channel lanes hit 32 banks
+                    a0 = __fmul_rn(sp[t0.xa], t0.w00);
+                    a1 = __fmul_rn(sp[t1.xa], t1.w00);
+                    a0 = fmaf(sp[t0.xb], t0.w01, a0);
+                    a1 = fmaf(sp[t1.xb], t1.w01, a1);
+                    a0 = fmaf(sp[Wd + t0.xa], t0.w10, a0);
+                    a1 = fmaf(sp[Wd + t1.xa], t1.w10, a1);
+                    a0 = fmaf(sp[Wd + t0.xb], t0.w11, a0);
+                    a1 = fmaf(sp[Wd + t1.xb], t1.w11, a1);
                 }
-                v[j] = acc;
-                ss = fmaf(acc, acc, ss);
+                v0[j] = a0; v1[j] = a1;
+                ss0 = fmaf(a0, a0, ss0);
+                ss1 = fmaf(a1, a1, ss1);
             }
-            float mul = scale;
+            float mul0 = scale, mul1 = scale;
             if (normalize) {
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-                mul = __fdiv_rn(scale, fmaxf(sqrtf(ss), 1e-12f));
+                for (int o = 16; o > 0; o >>= 1) {
+                    ss0 += __shfl_xor_sync(0xffffffffu, ss0, o);
+                    ss1 += __shfl_xor_sync(0xffffffffu, ss1, o);
+                }
+                mul0 = __fdiv_rn(scale, fmaxf(sqrtf(ss0), 1e-12f));
+                mul1 = __fdiv_rn(scale, fmaxf(sqrtf(ss1), 1e-12f));
             }
-            float* out = desc + ((size_t)b * kcap + t.k) * C;
+            if (live0) {
+                float* out = desc + ((size_t)b * kcap + t0.k) * C;
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                const int c = lane + 32 * j;
-                if (NJ != kMaxPerLane || c < C) out[c] = v[j] * mul;
+                for (int j = 0; j < NJ; ++j) {
+                    const int c = lane + 32 * j;
+                    if (NJ != kMaxPerLane || c < C) out[c] = v0[j] * mul0;
+                }
+            }
+            if (live1) {
+                float* out = desc + ((size_t)b * kcap + t1.k) * C;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const int c = lane + 32 * j;
+                    if (NJ != kMaxPerLane || c < C) out[c] = v1[j] * mul1;
+                }
             }
         }
     }
