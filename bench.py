@@ -453,7 +453,7 @@ def run_einx(args, synth):
         line = {
             "metric": "pairs/sec (voxel+detect+MNN)", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "tf32x3", "bf16": "bf16"}[args.precision],
+            "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 split)", "fp16x3": "f32 (3xFP16 split)", "bf16": "bf16"}[args.precision],
             "data": "synthetic", "config": workload_config(args, synth),
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
@@ -484,8 +484,9 @@ def main():
                          "resident batch (eager issue costs ~250 us of host time per step against ~420 us of GPU time, "
                          "so a busy host CPU makes the eager arm host bound; the graph arm is one launch per step)")
     ap.add_argument("--batch", type=int, default=None, help="pairs per GPU per step")
-    ap.add_argument("--precision", default=os.environ.get("EINX_MNN_PRECISION", "tf32x3"), choices=["fp32", "tf32x3", "bf16"],
-                    help="MNN arithmetic: tf32x3 (default; fp32-accurate on the tensor pipe), fp32 (FFMA), bf16")
+    ap.add_argument("--precision", default=os.environ.get("EINX_MNN_PRECISION", "fp16x3"), choices=["fp32", "tf32x3", "fp16x3", "bf16"],
+                    help="MNN arithmetic: fp16x3 (default) and tf32x3 are fp32-accurate 3-term splits on the tensor pipe (index parity with "
+                         "the fp32 oracle; fp16x3 needs |descriptor| < 63, true for normalised descriptors), fp32 = FFMA, bf16 = one pass")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "einx" else args.warmup
     synth = importlib.import_module("ei-nexus_official_b200.synth")

@@ -315,7 +315,7 @@ extern "C" int einx_mnn(einx_ctx* ctx, const float* d0, const float* d1, const i
     if ((ncap > 0 && !d0) || (mcap > 0 && !d1)) return einx_fail(ctx, EINX_ERR_INVALID, "einx_mnn: NULL descriptor pointer");
     if (kpts0 && (!kpts1 || !mk0 || !mk1 || !nmatch))
         return einx_fail(ctx, EINX_ERR_INVALID, "einx_mnn: kpts0 given but kpts1/mk0/mk1/nmatch missing");
-    if (precision < EINX_MNN_FP32 || precision > EINX_MNN_BF16)
+    if (precision < EINX_MNN_FP32 || precision > EINX_MNN_FP16X3)
         return einx_fail(ctx, EINX_ERR_INVALID, "einx_mnn: unknown precision %d", precision);
     DeviceGuard guard(ctx->device);
     cudaStream_t stream = (cudaStream_t)stream_;

@@ -14,8 +14,8 @@ import torch.nn as nn
 
 from . import _lib
 
-FP32, TF32X3, BF16 = 0, 1, 2
-_PRECISION = {"fp32": FP32, "tf32x3": TF32X3, "bf16": BF16}
+FP32, TF32X3, BF16, FP16X3 = 0, 1, 2, 3
+_PRECISION = {"fp32": FP32, "tf32x3": TF32X3, "bf16": BF16, "fp16x3": FP16X3}
 
 
 @torch.no_grad()

@@ -38,6 +38,9 @@ extern "C" {
 #define EINX_MNN_FP32 0  /* FFMA tiles, fp32 accumulate: index-exact reference path */
 #define EINX_MNN_TF32X3 1 /* tcgen05 kind::tf32, 3-term split (hi*hi + hi*lo + lo*hi) */
 #define EINX_MNN_BF16 2  /* tcgen05 kind::f16 on bf16-rounded descriptors             */
+#define EINX_MNN_FP16X3 3 /* tcgen05 kind::f16, 3-term fp16 split of 2^10 * d (same 22 significant bits as
+                           * TF32X3 at twice the tensor rate); requires |d| < 63, which L2-normalised
+                           * descriptors times any scale_factor < 63 satisfy -- larger values saturate */
 
 typedef struct einx_ctx einx_ctx;
 typedef void* einx_stream; /* cudaStream_t */

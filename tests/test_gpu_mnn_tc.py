@@ -47,13 +47,15 @@ SHAPES = [(1024, 1024, 256, 1.0), (2048, 2048, 128, 1.41), (1000, 777, 128, 1.41
           (384, 512, 32, 1.0), (5, 3, 8, 1.0)]
 
 
+@pytest.mark.parametrize("precision", ["tf32x3", "fp16x3"])
 @pytest.mark.parametrize("N,M,D,scale", SHAPES)
-def test_tf32x3_index_parity_with_fp32(einx, synth, N, M, D, scale):
+def test_split_paths_index_parity_with_fp32(einx, synth, N, M, D, scale, precision):
+    """The two fp32-accurate tensor-core paths (3xTF32 and the 3-term fp16 split) against the oracle."""
     rng = np.random.default_rng(N * 3 + M)
     pairs = [synth.descriptor_pair(rng, N, M, D, scale, dups=3 if b == 0 else 0) for b in range(3)]
     d0 = cuda(np.stack([p[0] for p in pairs]))
     d1 = cuda(np.stack([p[1] for p in pairs]))
-    out = einx.mnn(d0, d1, precision="tf32x3")
+    out = einx.mnn(d0, d1, precision=precision)
     ref = einx.mnn(d0, d1, precision="fp32")
     m0, m1 = out["matches0"].cpu().numpy(), out["matches1"].cpu().numpy()
     for b in range(3):
@@ -92,7 +94,7 @@ def test_bf16_match_set_agreement(einx, synth, N, D, scale):
     assert agree >= 0.995
 
 
-@pytest.mark.parametrize("precision", ["tf32x3", "bf16"])
+@pytest.mark.parametrize("precision", ["tf32x3", "fp16x3", "bf16"])
 def test_tc_ragged_counts(einx, synth, precision):
     rng = np.random.default_rng(9)
     N, M, D = 300, 520, 64
@@ -122,7 +124,7 @@ def test_tc_ragged_counts(einx, synth, precision):
         assert np.array_equal(out["matched_kpts1"][b, :nm].cpu().numpy(), k1[b][m0[keep]])
 
 
-@pytest.mark.parametrize("precision", ["tf32x3", "fp32"])
+@pytest.mark.parametrize("precision", ["tf32x3", "fp16x3", "fp32"])
 def test_similarity_values_are_fp32_accurate(einx, precision):
     """The 3xTF32 split must reproduce fp32 similarity VALUES (not only the argmax): probe them through
     the distance threshold.  Rows are a_i*e_i against b_i*e_i, so sim(i, i) = a_i*b_i exactly; a
