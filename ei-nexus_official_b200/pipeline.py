@@ -123,7 +123,8 @@ class ExtractMatchPipeline:
                 self(*args)
         cap.synchronize()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=cap):
+        # thread_local: other threads of the process (the NCCL watchdog under torchrun, samplers) keep using CUDA
+        with torch.cuda.graph(graph, stream=cap, capture_error_mode="thread_local"):
             out = self(*args)
         cur.wait_stream(cap)
         return CapturedStep(graph, out, args)

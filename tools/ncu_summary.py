@@ -21,7 +21,8 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
 NAMES = {"voxel_scatter_kernel": "voxel_scatter", "voxel_tile_kernel": "voxel_tile", "detect_kernel": "detect",
          "sample_bilinear_slab_kernel": "sample", "sample_kernel": "sample", "mnn_tc_kernel<(int)1": "mnn_similarity_tf32x3",
          "mnn_tc_kernel<1": "mnn_similarity_tf32x3", "mnn_tc_kernel<(int)0": "mnn_similarity_bf16",
-         "mnn_tc_kernel<0": "mnn_similarity_bf16", "mnn_fp32_kernel": "mnn_similarity_fp32"}
+         "mnn_tc_kernel<0": "mnn_similarity_bf16", "mnn_tc_kernel<(int)2": "mnn_similarity_fp16x3",
+         "mnn_tc_kernel<2": "mnn_similarity_fp16x3", "mnn_fp32_kernel": "mnn_similarity_fp32"}
 
 
 def main():
