@@ -377,33 +377,42 @@ def run_einx(args, synth):
     kern_ms = {"voxel_scatter": 0.0, "detect": 0.0, "sample": 0.0, "mnn_similarity": 0.0}
     det, desc, mt = (importlib.import_module(f"ei-nexus_official_b200.{m}") for m in ("detection", "describe", "match"))
     nprof = max(3, min(args.steps, 20))
-    ctx.profile(True)
+    mode = desc.BILINEAR if cfg.descriptor_mode == "bilinear" else desc.GATHER
     for i in range(3 + nprof):
         ev, (s0, r0, s1, r1) = dev_sets[i % NUM_INPUT_SETS]
         evts = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-        mode = desc.BILINEAR if cfg.descriptor_mode == "bilinear" else desc.GATHER
         torch.cuda.synchronize(dev)
         evts[0].record()
         pipe.voxelize(*ev)
         evts[1].record()
         _, kp0, cn0 = det.detect(s0, cfg.detection_threshold, cfg.nms_radius, cfg.remove_borders, cfg.top_k, kcap=cfg.top_k)
-        k_det0 = ctx.profile_read()[1]
         _, kp1, cn1 = det.detect(s1, cfg.detection_threshold, cfg.nms_radius, cfg.remove_borders, cfg.top_k, kcap=cfg.top_k)
         evts[2].record()
         d0 = desc.sample(r0, kp0, cn0, mode, (Hp, Wp), cfg.descriptor_scale, True)
-        k_smp0 = ctx.profile_read()[2]
         d1 = desc.sample(r1, kp1, cn1, mode, (Hp, Wp), cfg.descriptor_scale, True)
         evts[3].record()
         mt.mnn(d0, d1, cn0, cn1, kp0, kp1, None, None, True, cfg.precision)
         evts[4].record()
         torch.cuda.synchronize(dev)
-        k = ctx.profile_read()
         if i >= 3:
             for j, name in enumerate(stage_ms):
                 stage_ms[name] += evts[j].elapsed_time(evts[j + 1]) / nprof
+    # kernels: timed INSIDE a long run -- bursts of 10 single-stream steps issued back to back with no host
+    # synchronisation; the library's events bracket each entry point's dominant kernel on the launching
+    # stream and the last step of every burst is read back (detect / sample: that step's second launch).
+    # Sustained conditions, hence the sustained cuBLAS figure as the tensor peak.
+    import dataclasses
+    serial = einx.ExtractMatchPipeline(dataclasses.replace(cfg, concurrent=False))
+    ctx.profile(True)
+    for rep in range(2 + nprof):
+        for j in range(10):
+            ev, (s0, r0, s1, r1) = dev_sets[(rep * 10 + j) % NUM_INPUT_SETS]
+            serial(ev, s0, r0, s1, r1)
+        k = ctx.profile_read()  # waits for the burst
+        if rep >= 2:
             kern_ms["voxel_scatter"] += k[0] / nprof
-            kern_ms["detect"] += (k_det0 + k[1]) / nprof      # two launches (both sides) per step
-            kern_ms["sample"] += (k_smp0 + k[2]) / nprof
+            kern_ms["detect"] += 2 * k[1] / nprof      # two launches (one per side) per step
+            kern_ms["sample"] += 2 * k[2] / nprof
             kern_ms["mnn_similarity"] += k[3] / nprof
     ctx.profile(False)
 
@@ -454,7 +463,8 @@ def run_einx(args, synth):
         roof = dict(kernels[dominant])
         roof["kernel"] = dominant
         roof["share_of_step"] = round(kern_ms[dominant] / (ms / args.steps), 3)
-        roof["peak_source"] = f"MEASURED_PEAKS.json ({peak_kind}; HBM copy GB/s, cuBLAS bf16 sustained TF/s)"
+        roof["peak_source"] = (f"MEASURED_PEAKS.json ({peak_kind}; HBM copy GB/s; cuBLAS bf16 SUSTAINED TF/s: kernels are timed with "
+                               "CUDA events inside bursts of back-to-back steps)")
         if dominant == "detect":
             roof["note"] = ("largest share only as the sum of its two launches (one per side); iterative NMS in shared memory is "
                             "bound by instruction issue (41 % of issue slots under ncu), not by HBM: the map is read once, "

@@ -266,7 +266,10 @@ __device__ __forceinline__ void vmax8(const float* a, float (&o)[8]) {
 }
 
 template <int R, bool SMEM>
-__global__ void __launch_bounds__(kThreads, 1) detect_kernel(const DetectParams P) {
+// 48 registers (no spills) instead of the 64 a 1024-thread launch bound allows: the CTA then leaves a quarter of the
+// register file free, so CTAs of the concurrent voxel kernels can share its SM and use the issue slots the NMS
+// rounds leave idle (the step runs voxelisation and both detect chains on three streams)
+__global__ void __maxnreg__(48) detect_kernel(const DetectParams P) {
     constexpr int PAD = Geo<R>::PAD;
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();

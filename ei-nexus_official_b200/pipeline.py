@@ -28,7 +28,7 @@ class PathConfig:
     top_k: int = 1024          # :17
     descriptor_mode: str = "bilinear"  # "bilinear" = SuperPoint type (cell 8), "gather" = SiLK type (cell 1)
     descriptor_scale: float = 1.0      # 1.0 (SP, D=256) / 1.41 (SiLK, D=128)
-    precision: str = "fp32"    # MNN arithmetic: fp32 | tf32x3 | bf16
+    precision: str = "fp32"    # MNN arithmetic: fp32 | tf32x3 | fp16x3 (both fp32-accurate tensor-core splits) | bf16
     normalize_voxels: bool = True
     concurrent: bool = True    # run voxelisation and the two sides' detect -> sample chains on three streams
 
@@ -37,6 +37,9 @@ class ExtractMatchPipeline:
     """Batched drop-in for the post-backbone part of ``EIM.forward`` (core/modules/EIM.py:89-93)."""
 
     def __init__(self, cfg: PathConfig):
+        if cfg.precision == "fp16x3" and not abs(cfg.descriptor_scale) < 60.0:
+            raise ValueError("precision='fp16x3' splits 2^10 * descriptor into fp16 pairs and needs |descriptor| < 63: "
+                             "use 'tf32x3' for descriptor_scale >= 60")
         self.cfg = cfg
         self._side_streams = {}
         self._capture_streams = {}

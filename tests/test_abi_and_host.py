@@ -128,3 +128,26 @@ def test_max_keypoints_bound():
     for r in (1, 2, 4):
         v = O.fast_nms(rng.random((2, 40, 56)).astype(np.float32), r)
         assert (v > 0).reshape(2, -1).sum(1).max() <= det.max_keypoints(40, 56, r)
+
+
+def test_fp16x3_needs_bounded_descriptors(einx):
+    with pytest.raises(ValueError):
+        einx.ExtractMatchPipeline(einx.PathConfig(precision="fp16x3", descriptor_scale=100.0))
+    einx.ExtractMatchPipeline(einx.PathConfig(precision="fp16x3", descriptor_scale=1.41))
+
+
+def test_patch_reference_swaps_adjacent_rows(einx):
+    import types
+
+    fake = types.ModuleType("fake_ref.detector_util")
+    for name in ("logits_to_prob", "depth_to_space", "prob_map_to_points_map"):
+        setattr(fake, name, lambda *a, **k: None)
+    lg = types.ModuleType("fake_ref.lightglue")
+    lg.filter_matches = lambda *a, **k: None
+    vis = types.ModuleType("fake_ref.visualize")
+    vis.draw_events_accumulation_image = lambda *a, **k: None
+    done = einx.patch_reference([fake, lg, vis])
+    assert fake.logits_to_prob is einx.logits_to_prob and fake.depth_to_space is einx.depth_to_space
+    assert lg.filter_matches is einx.filter_matches
+    assert vis.draw_events_accumulation_image is einx.draw_events_accumulation_image
+    assert set(done) == {"fake_ref.detector_util", "fake_ref.lightglue", "fake_ref.visualize"}
