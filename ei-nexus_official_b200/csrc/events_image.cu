@@ -80,6 +80,18 @@ mask_dilate_kernel(const uint8_t* __restrict__ image, int H, int W, int pad_top,
     mask[((size_t)b * Hp + yp) * Wp + xp] = any ? 1 : 0;
 }
 
+// compact wire format of integer-pixel events -> the fp32 SoA the voxeliser reads
+__global__ void __launch_bounds__(256)
+unpack_events_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ y, const int8_t* __restrict__ p, size_t n,
+                     float* __restrict__ xo, float* __restrict__ yo, float* __restrict__ po) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        xo[i] = (float)x[i];
+        yo[i] = (float)y[i];
+        po[i] = (float)p[i];
+    }
+}
+
 }  // namespace
 
 extern "C" int einx_events_image(einx_ctx* ctx, const void* x, const void* y, int coord_f64, const int64_t* ev_offsets,
@@ -120,6 +132,20 @@ extern "C" int einx_mask_dilate(einx_ctx* ctx, const uint8_t* image, int B, int 
     if (B > 65535 || Hp > 65535) return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_mask_dilate: B or Hp > 65535");
     DeviceGuard guard(ctx->device);
     mask_dilate_kernel<<<dim3((Wp + 255) / 256, Hp, B), 256, 0, (cudaStream_t)stream_>>>(image, H, W, pad_top, pad_left, Hp, Wp, mask);
+    EINX_CHECK_LAUNCH(ctx);
+    return EINX_OK;
+}
+
+extern "C" int einx_unpack_events(einx_ctx* ctx, const uint16_t* x, const uint16_t* y, const int8_t* p, int64_t n, float* xo,
+                                  float* yo, float* po, einx_stream stream_) {
+    if (!ctx) return EINX_ERR_INVALID;
+    if (n < 0) return einx_fail(ctx, EINX_ERR_INVALID, "einx_unpack_events: n=%lld", (long long)n);
+    if (n == 0) return EINX_OK;
+    if (!x || !y || !p || !xo || !yo || !po) return einx_fail(ctx, EINX_ERR_INVALID, "einx_unpack_events: NULL pointer argument");
+    DeviceGuard guard(ctx->device);
+    size_t blocks = ((size_t)n + 255) / 256;
+    if (blocks > (size_t)ctx->num_sms * 16) blocks = (size_t)ctx->num_sms * 16;
+    unpack_events_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(x, y, p, (size_t)n, xo, yo, po);
     EINX_CHECK_LAUNCH(ctx);
     return EINX_OK;
 }

@@ -13,7 +13,7 @@ from typing import Dict, List, Optional, Sequence
 
 import torch
 
-from . import describe, detection as _detect, match, voxel
+from . import _lib, describe, detection as _detect, match, voxel
 
 
 @dataclass
@@ -153,25 +153,52 @@ class HostBatch:
 
     ALIGN = 256
 
-    def __init__(self, events: Sequence[dict], score0, raw0, score1, raw1, chunks: int = 4):
+    def __init__(self, events: Sequence[dict], score0, raw0, score1, raw1, chunks: int = 4, compact_events: bool = True):
+        import numpy as np
+
         B = len(events)
         chunks = max(1, min(int(chunks), B))
         bounds = [B * i // chunks for i in range(chunks + 1)]
         self.batch = B
+        # integer-pixel events (EC: datasets/rectify_ec.py:66-83; any raw sensor stream) cross PCIe as uint16 x, y and
+        # int8 p -- 13 instead of 20 bytes per event with the fp64 timestamp -- when that is lossless for the whole batch
+        self.compact = bool(compact_events) and all(self._lossless(ev) for ev in events)
         self.chunks: List[tuple] = []
         for a, b in zip(bounds[:-1], bounds[1:]):
-            ev = voxel.pack_events(events[a:b])
+            if self.compact:
+                sub = events[a:b]
+                off = np.zeros(len(sub) + 1, dtype=np.int64)
+                np.cumsum([len(ev["t"]) for ev in sub], out=off[1:])
+                ev = (torch.from_numpy(np.concatenate([np.asarray(e["x"]) for e in sub]).astype(np.uint16)),
+                      torch.from_numpy(np.concatenate([np.asarray(e["y"]) for e in sub]).astype(np.uint16)),
+                      torch.from_numpy(np.concatenate([np.asarray(e["t"], dtype=np.float64) for e in sub])),
+                      torch.from_numpy(np.concatenate([np.asarray(e["p"]) for e in sub]).astype(np.int8)),
+                      torch.from_numpy(off))
+            else:
+                ev = voxel.pack_events(events[a:b])
             maps = [torch.from_numpy(m[a:b]) if not torch.is_tensor(m) else m[a:b] for m in (score0, raw0, score1, raw1)]
             arrays = [t.contiguous() for t in (*ev, *maps)]
-            layout, off = [], 0
+            layout, off_b = [], 0
             for t in arrays:
-                layout.append((off, t.dtype, tuple(t.shape)))
-                off += (t.numel() * t.element_size() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
-            buf = torch.empty(off, dtype=torch.uint8).pin_memory()
+                layout.append((off_b, t.dtype, tuple(t.shape)))
+                off_b += (t.numel() * t.element_size() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+            buf = torch.empty(off_b, dtype=torch.uint8).pin_memory()
             for t, (o, dt, shape) in zip(arrays, layout):
                 n = t.numel() * t.element_size()
                 buf[o:o + n].view(dt).view(shape).copy_(t)
             self.chunks.append((a, b, buf, layout, sum(t.numel() * t.element_size() for t in arrays)))
+
+    @staticmethod
+    def _lossless(ev) -> bool:
+        import numpy as np
+
+        if len(ev["t"]) == 0:
+            return False
+        for key, lo, hi in (("x", 0, 65535), ("y", 0, 65535), ("p", -128, 127)):
+            v = np.asarray(ev[key])
+            if not (np.all(v == np.floor(v)) and v.min() >= lo and v.max() <= hi):
+                return False
+        return True
 
     @property
     def nbytes(self) -> int:
@@ -205,6 +232,7 @@ class HostStreamer:
         self.dev = torch.device(device)
         self.copy_stream = torch.cuda.Stream(self.dev)
         self._stage = {}
+        self._unpacked = {}
         self._free = [None, None]  # event: the kernels that read staging set k have finished
 
     def _staging(self, k, nbytes):
@@ -228,6 +256,15 @@ class HostStreamer:
                 ready.record(self.copy_stream)
             main.wait_event(ready)
             x, y, t, p, off, s0, r0, s1, r1 = HostBatch.views(dbuf, layout)
+            if hb.compact:  # expand the 13-byte wire format to the fp32 SoA the voxeliser reads
+                n = x.numel()
+                f = self._unpacked.get(k)
+                if f is None or f.shape[1] < n:
+                    f = self._unpacked[k] = torch.empty((3, n), dtype=torch.float32, device=self.dev)
+                ctx = _lib.context_for(self.dev)
+                ctx.check(ctx.lib.einx_unpack_events(ctx.handle, _lib.ptr(x), _lib.ptr(y), _lib.ptr(p), n, _lib.ptr(f[0]),
+                                                     _lib.ptr(f[1]), _lib.ptr(f[2]), ctx.stream), "einx_unpack_events")
+                x, y, p = f[0, :n], f[1, :n], f[2, :n]
             out = self.pipe((x, y, t, p, off), s0, r0, s1, r1)
             for key in RESULT_KEYS:
                 if key in out_host:

@@ -147,6 +147,16 @@ int einx_events_image(einx_ctx* ctx, const void* x, const void* y, int coord_f64
                       einx_stream stream);
 
 /*
+ * Compact host->device wire format for integer-pixel events (what the sensor and the EC dataset
+ * deliver: datasets/rectify_ec.py:66-83 rounds to pixels, polarity 0/1): x, y as uint16 and p as int8
+ * expand to the fp32 arrays einx_voxelize reads -- exactly the values the reference's
+ * astype(float32) of representations.py:73-75 produces -- so an event crosses PCIe in 13 bytes
+ * (with its fp64 timestamp) instead of 20.  The host layer only chooses this format when it is lossless.
+ */
+int einx_unpack_events(einx_ctx* ctx, const uint16_t* x, const uint16_t* y, const int8_t* p, int64_t n,
+                       float* xo, float* yo, float* po, einx_stream stream);
+
+/*
  * Event mask for the detector.  Replaces `events_image > 0` (train_extractor.py:225), the constant
  * padding of Padder.pad for bool tensors (core/modules/utils/util.py:17-32) and the 3x3 box
  * convolution + `> 0` of core/modules/event_extractors/EventExtractors.py:357-363, i.e. a 3x3 binary

@@ -79,14 +79,20 @@ def test_one_context_per_stream(einx):
     assert einx.launch_count(DEV) >= main_ctx.launches
 
 
-@pytest.mark.parametrize("chunks", [1, 4])
-def test_host_streamer_matches_device_path(einx, batch, chunks):
+@pytest.mark.parametrize("chunks,compact", [(1, True), (4, True), (2, False)])
+def test_host_streamer_matches_device_path(einx, batch, chunks, compact):
+    """Sub-batch streaming from pinned host memory, with the 13-byte wire format for integer-pixel events
+    (x, y uint16, p int8, t fp64) and with the plain 20-byte one, must reproduce the device-resident path."""
     cfg, evs, maps = batch
     ref = run(einx, cfg, evs, maps)
     B, K = len(evs), cfg.top_k
-    hb = einx.HostBatch(evs, *maps, chunks=chunks)
-    assert len(hb.chunks) == chunks and hb.batch == B
-    assert hb.nbytes == sum(20 * len(e["t"]) for e in evs) + 8 * (B + chunks) + sum(m.nbytes for m in maps)
+    hb = einx.HostBatch(evs, *maps, chunks=chunks, compact_events=compact)
+    assert len(hb.chunks) == chunks and hb.batch == B and hb.compact == compact  # EC-style events are integral
+    per_event = 13 if compact else 20
+    assert hb.nbytes == sum(per_event * len(e["t"]) for e in evs) + 8 * (B + chunks) + sum(m.nbytes for m in maps)
+    sub = dict(evs[0])
+    sub["x"] = sub["x"] + 0.25  # sub-pixel coordinates: the compact format would lose them
+    assert not einx.HostBatch([sub] + list(evs[1:]), *maps, chunks=1).compact
     out_host = {"matches0": torch.full((B, K), -7, dtype=torch.int64).pin_memory(),
                 "num_matches": torch.zeros((B,), dtype=torch.int32).pin_memory(),
                 "matched_kpts0": torch.zeros((B, K, 3)).pin_memory(),
