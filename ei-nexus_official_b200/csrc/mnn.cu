@@ -258,6 +258,77 @@ mnn_gather_kernel(const int64_t* __restrict__ m0, const float* __restrict__ k0, 
     if (tid == 0) nmatch[b] = run_s;
 }
 
+// Finalisation and matched-keypoint compaction in one launch: one 1024-thread CTA per pair decides its
+// rows and columns chunk by chunk (same arithmetic as mnn_finalize_kernel) and compacts the matched
+// keypoint rows of the chunk in ascending i with a block scan -- the two tiny kernels this replaces sat
+// back to back on the critical path of a step behind the similarity kernel.
+constexpr int kFinThreads = 1024;
+
+__global__ void __launch_bounds__(kFinThreads)
+mnn_finalize_gather_kernel(const FinalizeParams P, const float* __restrict__ k0, const float* __restrict__ k1,
+                           float* __restrict__ mk0, float* __restrict__ mk1, int32_t* __restrict__ nmatch) {
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = P.n0 ? min(P.n0[b], P.ncap) : P.ncap;
+    const int M = P.n1 ? min(P.n1[b], P.mcap) : P.mcap;
+    const unsigned long long* rk = P.rowkey + (size_t)b * P.ncap;
+    const unsigned long long* ck = P.colkey + (size_t)b * P.mcap;
+    const unsigned long long* r2 = P.row2 ? P.row2 + (size_t)b * P.ncap : nullptr;
+    const unsigned long long* c2 = P.col2 ? P.col2 + (size_t)b * P.mcap : nullptr;
+    __shared__ int wsum[kFinThreads / 32];
+    __shared__ int run_s;
+    if (tid == 0) run_s = 0;
+    __syncthreads();
+    const int mx = max(P.ncap, P.mcap);
+    for (int base = 0; base < mx; base += kFinThreads) {
+        const int t = base + tid;
+        int m = -1;
+        if (t < P.ncap) {
+            if (t < N) {
+                m = nn_from_keys(rk, r2, t, P);
+                if (P.mutual && m >= 0 && nn_from_keys(ck, c2, m, P) != t) m = -1;  // mutual_check, MNN.py:25-32
+            }
+            P.m0[(size_t)b * P.ncap + t] = m;
+            P.s0[(size_t)b * P.ncap + t] = m >= 0 ? 1.0f : 0.0f;
+        }
+        if (t < P.mcap) {
+            int mm = -1;
+            if (t < M) {
+                mm = nn_from_keys(ck, c2, t, P);
+                if (P.mutual && mm >= 0 && nn_from_keys(rk, r2, mm, P) != t) mm = -1;
+            }
+            P.m1[(size_t)b * P.mcap + t] = mm;
+            P.s1[(size_t)b * P.mcap + t] = mm >= 0 ? 1.0f : 0.0f;
+        }
+        // matched_kpts0 = kpts0[m0 > -1], matched_kpts1 = kpts1[m0[m0 > -1]] in ascending i (MNN.py:103-129)
+        const bool keep = m >= 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) wsum[warp] = __popc(bal);
+        __syncthreads();
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < kFinThreads / 32; ++w) {
+            const int c = wsum[w];
+            if (w < warp) woff += c;
+            tot += c;
+        }
+        const int run = run_s;
+        if (keep) {
+            const int pos = run + woff + __popc(bal & ((1u << lane) - 1u));
+            const float* a = k0 + ((size_t)b * P.ncap + t) * 3;
+            const float* c = k1 + ((size_t)b * P.mcap + m) * 3;
+            float* oa = mk0 + ((size_t)b * P.ncap + pos) * 3;
+            float* oc = mk1 + ((size_t)b * P.ncap + pos) * 3;
+            oa[0] = a[0]; oa[1] = a[1]; oa[2] = a[2];
+            oc[0] = c[0]; oc[1] = c[1]; oc[2] = c[2];
+        }
+        __syncthreads();
+        if (tid == 0) run_s = run + tot;
+        __syncthreads();
+    }
+    if (tid == 0) nmatch[b] = run_s;
+}
+
 // ---- opt-in dense by-products -------------------------------------------------------------- //
 __global__ void lse_rows_kernel(const float* __restrict__ sim, int N, int M, float* __restrict__ lse) {
     const int b = blockIdx.y, i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -363,6 +434,11 @@ extern "C" int einx_mnn(einx_ctx* ctx, const float* d0, const float* d1, const i
     F.dist_sq = (float)((double)distance_thresh * (double)distance_thresh);
     F.m0 = m0; F.m1 = m1; F.s0 = s0; F.s1 = s1;
     const int mx = ncap > mcap ? ncap : mcap;
+    if (kpts0 && mx > 0) {
+        mnn_finalize_gather_kernel<<<B, kFinThreads, 0, stream>>>(F, kpts0, kpts1, mk0, mk1, nmatch);
+        EINX_CHECK_LAUNCH(ctx);
+        return EINX_OK;
+    }
     if (mx > 0) {
         mnn_finalize_kernel<<<dim3((mx + 255) / 256, B), 256, 0, stream>>>(F);
         EINX_CHECK_LAUNCH(ctx);

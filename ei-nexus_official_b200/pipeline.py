@@ -244,7 +244,9 @@ class HostStreamer:
     @torch.no_grad()
     def run(self, hb: HostBatch, out_host: Dict[str, torch.Tensor]) -> None:
         main = torch.cuda.current_stream(self.dev)
-        self.copy_stream.wait_stream(main)
+        # (the copy stream never waits for the compute stream as a whole -- only, through `_free`, for the kernels
+        # that last read the staging set it is about to overwrite -- so uploads of the next call start while the
+        # last sub-batch of this one still computes)
         for i, (a, b, hbuf, layout, _) in enumerate(hb.chunks):
             k = i & 1
             dbuf = self._staging(k, hbuf.numel())[:hbuf.numel()]
