@@ -76,9 +76,8 @@ struct Cfg {
     static constexpr int kColsPerWarp = TILE_N / (kEpiWarps / 4);
     // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4.. epilogue, then converters
     static constexpr int kThreads = 32 * (kEpilogueWarp0 + kEpiWarps + kConvWarps);
-    // alignment slack + barriers + column-merge buffer + one 32x32 transpose tile per epilogue warp
-    static constexpr size_t kFixedSmem = 1024 + 256 + 4 * TILE_N * sizeof(unsigned long long) +
-                                         (size_t)kEpiWarps * 32 * kScratchPitch * sizeof(float);
+    // alignment slack + barriers + one 32x32 transpose tile per epilogue warp (reused for the column-key merge)
+    static constexpr size_t kFixedSmem = 1024 + 256 + (size_t)kEpiWarps * 32 * kScratchPitch * sizeof(float);
     static constexpr int kStagesFit = (int)((227 * 1024 - kFixedSmem) / kStageBytes);
     static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
     static constexpr size_t kSmem = kFixedSmem + (size_t)kStages * kStageBytes;
@@ -292,13 +291,12 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     constexpr int A_BYTES = C::kABytes, B_BYTES = C::kBBytes, RAW_BYTES = C::kRawBytes, STAGES = C::kStages,
                   STAGE_BYTES = C::kStageBytes;
     extern __shared__ __align__(1024) unsigned char smem[];
-    // carve: [stages x (A | B [| A lo | B lo])] 1024-aligned, then barriers, then the column-merge buffer
+    // carve: [stages x (A | B [| A lo | B lo])] 1024-aligned, then barriers, then the epilogue warps' transpose tiles
     // (offset arithmetic on the shared array, not an integer round trip: the compiler must keep the
     // shared address space, or every access below becomes a generic LD.E/ST.E)
     unsigned char* tiles = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);
     Barriers* bars = reinterpret_cast<Barriers*>(tiles + (size_t)STAGES * STAGE_BYTES);
-    unsigned long long* colpart = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(bars) + 256);
-    float* scratch_all = reinterpret_cast<float*>(colpart + 4 * TILE_N);
+    float* scratch_all = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;  // which 128-row half of the pair's tile
@@ -547,6 +545,7 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             constexpr int kChunksPerWarp = C::kColsPerWarp / 32;
             // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is reduced
             uint32_t v[2][32];
+            unsigned long long ckey[kChunksPerWarp];  // this lane's column of every chunk: best (value, row) so far
             tc_ld32_issue(taddr, v[0]);
 #pragma unroll
             for (int c = 0; c < kChunksPerWarp; ++c) {
@@ -579,13 +578,12 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     int cr;
                     argmax32(g, cv, cr);
                     const bool col_ok = (jc + lane < M) && (cv > -INFINITY);
-                    colpart[q * TILE_N + C::kColsPerWarp * part + 32 * c + lane] =
-                        col_ok ? (((unsigned long long)f32_orderable((KIND == 2 ? cv * P.out_scale : cv) + 0.0f) << 32) |
-                                  (0xffffffffu - (uint32_t)(i0 + 32 * q + cr)))
-                               : 0ull;
+                    ckey[c] = col_ok ? (((unsigned long long)f32_orderable((KIND == 2 ? cv * P.out_scale : cv) + 0.0f) << 32) |
+                                        (0xffffffffu - (uint32_t)(i0 + 32 * q + cr)))
+                                     : 0ull;
                     __syncwarp();  // the tile is rewritten by the next chunk
                 } else {
-                    colpart[q * TILE_N + C::kColsPerWarp * part + 32 * c + lane] = 0ull;
+                    ckey[c] = 0ull;
                 }
             }
             // TMEM accumulator fully read by this warp: hand it back to the MMA warp (the leader's)
@@ -599,18 +597,29 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 atomicMax(P.rowkey + (size_t)b * P.ncap + row,
                           ((unsigned long long)f32_orderable((KIND == 2 ? best * P.out_scale : best) + 0.0f) << 32) |
                               (0xffffffffu - (uint32_t)best_j));
-            // merge the 4 lane quarters' column keys
+            // merge the 4 lane quarters' column keys: every warp parks its keys in its own (now idle) transpose
+            // tile, then the threads of the epilogue group take the maximum over the four quarters of a column
+            {
+                unsigned long long* mine = reinterpret_cast<unsigned long long*>(scratch);
+#pragma unroll
+                for (int c = 0; c < kChunksPerWarp; ++c) mine[32 * c + lane] = ckey[c];
+            }
             asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiWarps * 32) : "memory");
             for (int cidx = threadIdx.x - kEpilogueWarp0 * 32; cidx < TILE_N; cidx += C::kEpiWarps * 32) {
                 const int j = j0 + cidx;
                 if (j < M) {
-                    unsigned long long m = colpart[cidx];
+                    const int pp = cidx / C::kColsPerWarp, within = cidx - pp * C::kColsPerWarp;  // owning part, slot
+                    unsigned long long m = 0ull;
 #pragma unroll
-                    for (int w = 1; w < 4; ++w) m = max(m, colpart[w * TILE_N + cidx]);
+                    for (int w = 0; w < 4; ++w) {  // epilogue warp (4 * pp + w) holds lane quarter w of that part
+                        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(
+                            scratch_all + (size_t)(4 * pp + w) * 32 * kScratchPitch);
+                        m = max(m, src[within]);
+                    }
                     if (m) atomicMax(P.colkey + (size_t)b * P.mcap + j, m);
                 }
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiWarps * 32) : "memory");  // colpart is reused by the next tile
+            asm volatile("bar.sync 1, %0;" ::"n"(C::kEpiWarps * 32) : "memory");  // the tiles are rewritten by the next tile
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
@@ -767,12 +776,9 @@ int einx_mnn_tc(einx_ctx* ctx, const float* d0, const float* d1, const int32_t* 
         P.idesc = make_idesc(2, CG);
         P.in_scale = 1024.0f;
         P.out_scale = 1.0f / (1024.0f * 1024.0f);
-        // pair form: 8 converter warps + 4 epilogue warps and three 64 KB stages when the k-loop dominates
-        // (D >= 256: 112 vs 137 us on C2), 8 epilogue warps and two stages when the argmax epilogue does
-        // (D = 128: 141 vs 161 us on the C3 shape, 75 vs 90 us on C4)
-        if (CG == 2)
-            return D >= 256 ? launch_tc<2, 128, 2, 4>(ctx, maps[0], maps[1], P, grid, stream)
-                            : launch_tc<2, 128, 2, 8>(ctx, maps[0], maps[1], P, grid, stream);
+        // pair form: 8 epilogue + 8 converter warps (640 threads, 94 registers) and three 64 KB stages -- the column
+        // keys live in registers and merge through the idle transpose tiles, which is what lets the third stage fit
+        if (CG == 2) return launch_tc<2, 128, 2, 8>(ctx, maps[0], maps[1], P, grid, stream);
         return launch_tc<2, 128, 1>(ctx, maps[0], maps[1], P, grid, stream);
     }
     // TF32X3: 16-element k-blocks (64-byte rows)
