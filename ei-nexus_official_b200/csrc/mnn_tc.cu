@@ -33,6 +33,9 @@ constexpr int kEpilogueWarp0 = 4;
 #ifndef EINX_SPLIT_EPI_WARPS
 #define EINX_SPLIT_EPI_WARPS 8
 #endif
+#ifndef EINX_BF16_EPI_WARPS
+#define EINX_BF16_EPI_WARPS 8
+#endif
 #ifndef EINX_FP16_EPI_WARPS
 #define EINX_FP16_EPI_WARPS 8
 #endif
@@ -70,7 +73,7 @@ struct Cfg {
     static constexpr int kOpABytes = TILE_M * kOpKB;
     static constexpr int kOpBBytes = kBRows * kOpKB;
     // (single-CTA split kernels keep 4 + 8: their stages are 1.5x larger and two must fit beside the scratch)
-    static constexpr int kEpiWarps = KIND == 0 ? 8 : (CG == 1 ? 4 : (KIND == 1 ? EINX_SPLIT_EPI_WARPS : (EW ? EW : EINX_FP16_EPI_WARPS)));
+    static constexpr int kEpiWarps = KIND == 0 ? EINX_BF16_EPI_WARPS : (CG == 1 ? 4 : (KIND == 1 ? EINX_SPLIT_EPI_WARPS : (EW ? EW : EINX_FP16_EPI_WARPS)));
     static constexpr int kConvWarps = !kConvert ? 0 : (CG == 1 ? 8 : (KIND == 1 ? EINX_SPLIT_CONV_WARPS : 8));
     static constexpr int kConvWarp0 = kEpilogueWarp0 + kEpiWarps;
     static constexpr int kColsPerWarp = TILE_N / (kEpiWarps / 4);
