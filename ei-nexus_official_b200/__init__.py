@@ -14,8 +14,9 @@ from .dist import gather_matches, pack_matches, shard_range
 from .match import NearestNeighborMatcher, filter_matches, mnn, mnn_dense
 from .patch import patch_reference
 from .pipeline import CapturedStep, ExtractMatchPipeline, HostBatch, HostStreamer, PathConfig
-from .voxel import (draw_events_accumulation_image, events_image_device, events_to_voxel_grid, pack_events,
-                    time_normalization, voxelize_batch, voxelize_device)
+from .voxel import (draw_events_accumulation_image, event_stack_device, events_image_device, events_to_event_stack,
+                    events_to_time_surface, events_to_voxel_grid, pack_events, time_normalization, time_surface_device,
+                    voxelize_batch, voxelize_device)
 
 __all__ = [
     "EinxError", "context_for", "contexts_of", "launch_count", "events_to_voxel_grid", "time_normalization", "pack_events", "voxelize_batch",
@@ -23,5 +24,6 @@ __all__ = [
     "sparsify_full_resolution_descriptors", "sparsify_low_resolution_descriptors", "NearestNeighborMatcher",
     "mnn", "mnn_dense", "ExtractMatchPipeline", "CapturedStep", "HostBatch", "HostStreamer", "PathConfig", "patch_reference", "shard_range", "pack_matches",
     "gather_matches", "logits_to_prob", "depth_to_space", "logits_to_score", "events_mask",
-    "draw_events_accumulation_image", "events_image_device", "filter_matches",
+    "draw_events_accumulation_image", "events_image_device", "filter_matches", "events_to_event_stack",
+    "events_to_time_surface", "event_stack_device", "time_surface_device",
 ]

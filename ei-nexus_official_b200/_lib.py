@@ -30,6 +30,8 @@ SIGNATURES = {
                            C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "einx_mnn_dense": (C.c_int, [c_ctx, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "einx_events_image": (C.c_int, [c_ctx, _P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "einx_event_stack": (C.c_int, [c_ctx, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "einx_time_surface": (C.c_int, [c_ctx, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "einx_unpack_events": (C.c_int, [c_ctx, _P, _P, _P, C.c_int64, _P, _P, _P, _P]),
     "einx_mask_dilate": (C.c_int, [c_ctx, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "einx_logits_to_score": (C.c_int, [c_ctx, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),

@@ -22,6 +22,8 @@ _FUNCS = {
     "NearestNeighborMatcher": match.NearestNeighborMatcher,
     # adjacent rows (SURVEY.md section 8 f)
     "draw_events_accumulation_image": voxel.draw_events_accumulation_image,
+    "events_to_event_stack": voxel.events_to_event_stack,
+    "events_to_time_surface": voxel.events_to_time_surface,
     "logits_to_prob": detect.logits_to_prob,
     "depth_to_space": detect.depth_to_space,
     "filter_matches": match.filter_matches,

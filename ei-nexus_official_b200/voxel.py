@@ -132,3 +132,54 @@ def draw_events_accumulation_image(events, image_shape, device="cuda") -> np.nda
     y = torch.from_numpy(np.ascontiguousarray(events["y"], dtype=np.float64)).to(dev)
     off = torch.tensor([0, x.numel()], dtype=torch.int64, device=dev)
     return events_image_device(x, y, off, image_shape[1], image_shape[0])[0].cpu().numpy()
+
+
+# --------------------------------------------------------------------------------------------- #
+# adjacent row (SURVEY.md section 8 f): the reference's other scatter representations
+# --------------------------------------------------------------------------------------------- #
+def _binned(entry: str, x, y, t, p, offsets, input_size) -> torch.Tensor:
+    bins, H, W = (int(v) for v in input_size)
+    dev = x.device
+    if not x.is_cuda:
+        raise _lib.EinxError(f"{entry}: expected CUDA tensors (there is no CPU fallback)")
+    for name, ten, dt in (("x", x, torch.float32), ("y", y, torch.float32), ("p", p, torch.float32),
+                          ("t", t, torch.float64), ("offsets", offsets, torch.int64)):
+        if ten.dtype != dt or not ten.is_contiguous() or ten.device != dev:
+            raise ValueError(f"{name}: expected contiguous {dt} on {dev}")
+    ctx = _lib.context_for(dev)
+    B = offsets.numel() - 1
+    out = torch.empty((B, bins, H, W), dtype=torch.float32, device=dev)
+    rc = getattr(ctx.lib, entry)(ctx.handle, _lib.ptr(x), _lib.ptr(y), _lib.ptr(t), _lib.ptr(p), _lib.ptr(offsets),
+                                 B, bins, H, W, _lib.ptr(out), ctx.stream)
+    ctx.check(rc, entry)
+    return out
+
+
+def event_stack_device(x, y, t, p, offsets, input_size) -> torch.Tensor:
+    """einx_event_stack on device-resident SoA events -> (B, bins, H, W) fp32."""
+    return _binned("einx_event_stack", x, y, t, p, offsets, input_size)
+
+
+def time_surface_device(x, y, t, p, offsets, input_size) -> torch.Tensor:
+    """einx_time_surface on device-resident SoA events -> (B, bins, H, W) fp32."""
+    return _binned("einx_time_surface", x, y, t, p, offsets, input_size)
+
+
+def _single(events: Dict, fn, input_size, device) -> torch.Tensor:
+    dev = torch.device(device)
+    x, y, t, p, off = (a.to(dev) for a in pack_events([events]))
+    grid = fn(x, y, t, p, off, input_size)[0].cpu()
+    time_normalization(events)  # the reference mutates the caller's dict (:183, :31)
+    return grid
+
+
+@torch.no_grad()
+def events_to_event_stack(events: Dict, input_size: Tuple, device="cuda") -> torch.Tensor:
+    """Drop-in for ``datasets/representations.py:177-214``: CPU fp32 (bins, H, W); ``events['t']`` is normalised."""
+    return _single(events, event_stack_device, input_size, device)
+
+
+@torch.no_grad()
+def events_to_time_surface(events: Dict, input_size: Tuple, device="cuda") -> torch.Tensor:
+    """Drop-in for ``datasets/representations.py:25-63``: CPU fp32 (bins, H, W); ``events['t']`` is normalised."""
+    return _single(events, time_surface_device, input_size, device)

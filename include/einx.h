@@ -147,6 +147,27 @@ int einx_events_image(einx_ctx* ctx, const void* x, const void* y, int coord_f64
                       einx_stream stream);
 
 /*
+ * The reference's other scatter representations, selectable through `representation_type`
+ * (datasets/MVSEC.py:706-718).  Same ragged SoA events as einx_voxelize (x, y, p fp32; t fp64, time-sorted);
+ * time_normalization (datasets/representations.py:8-22) runs on the device in fp64, and an event belongs to
+ * bin i iff  i*dt <= t <= i*dt + dt  with both ends inclusive -- exactly np.searchsorted(.., 'left') ..
+ * searchsorted(.., 'right') of the reference, so boundary events count in two bins.  Events outside
+ * [0,W)x[0,H) are skipped.
+ *   einx_event_stack : datasets/representations.py:177-214 -- out (B, bins, H, W) fp32, the integer sum of
+ *                      2*int(p) - 1 per cell.  Bit-exact.
+ *   einx_time_surface: datasets/representations.py:25-63  -- out (B, bins, H, W) fp32 with bins // 2 time
+ *                      bins; channel 2*i + int(p) holds the latest normalised time of that polarity (the
+ *                      reference's last-write-wins fancy assignment on time-sorted events = the maximum).
+ *                      Polarities other than 0/1 have no channel and are skipped.  Bit-exact.
+ */
+int einx_event_stack(einx_ctx* ctx, const float* x, const float* y, const double* t, const float* p,
+                     const int64_t* ev_offsets, int B, int bins, int H, int W, float* out,
+                     einx_stream stream);
+int einx_time_surface(einx_ctx* ctx, const float* x, const float* y, const double* t, const float* p,
+                      const int64_t* ev_offsets, int B, int bins, int H, int W, float* out,
+                      einx_stream stream);
+
+/*
  * Compact host->device wire format for integer-pixel events (what the sensor and the EC dataset
  * deliver: datasets/rectify_ec.py:66-83 rounds to pixels, polarity 0/1): x, y as uint16 and p as int8
  * expand to the fp32 arrays einx_voxelize reads -- exactly the values the reference's

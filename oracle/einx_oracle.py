@@ -505,3 +505,39 @@ def filter_matches(scores, th):
     valid0 = mutual0 & (ms0 > F32(th))
     valid1 = mutual1 & valid0[bi, m1]
     return np.where(valid0, m0, -1), np.where(valid1, m1, -1), ms0, ms1
+
+
+def _bin_slices(tn, nbins):
+    """np.searchsorted bounds of the reference's per-bin loops (representations.py:44-47, 196-199):
+    bin i owns events with i*dt <= t <= i*dt + dt, both ends inclusive."""
+    dt = 1.0 / nbins
+    for i in range(nbins):
+        t0 = i * dt
+        t1 = t0 + dt
+        yield i, np.searchsorted(tn, t0, side="left"), np.searchsorted(tn, t1, side="right")
+
+
+def events_to_event_stack(x, y, t, p, bins, H, W):
+    """Per-bin sum of 2*int(p) - 1 at (int(y), int(x)) (datasets/representations.py:177-214); fp32 (bins, H, W)."""
+    tn = time_normalization(t)
+    x0, y0 = np.asarray(x).astype(np.int32), np.asarray(y).astype(np.int32)
+    p0 = 2 * np.asarray(p).astype(np.int32) - 1
+    out = np.zeros((bins, H, W), dtype=np.float32)
+    for i, a, b in _bin_slices(tn, bins):
+        xs, ys, ps = x0[a:b], y0[a:b], p0[a:b]
+        ok = (xs >= 0) & (xs < W) & (ys >= 0) & (ys < H)  # :209
+        np.add.at(out[i], (ys[ok], xs[ok]), ps[ok].astype(np.float32))
+    return out
+
+
+def events_to_time_surface(x, y, t, p, bins, H, W):
+    """Latest normalised time per (2*bin + int(p), int(y), int(x)) over bins // 2 time bins
+    (datasets/representations.py:25-63; the fancy assignment at :57 keeps the last, i.e. latest, event).
+    In-range events with polarity 0/1 only (anything else indexes another channel in the reference)."""
+    nb = bins // 2
+    tn = time_normalization(t)
+    x0, y0, p0 = (np.asarray(v).astype(np.int32) for v in (x, y, p))
+    out = np.zeros((bins, H, W), dtype=np.float32)
+    for i, a, b in _bin_slices(tn, nb):
+        out[2 * i + p0[a:b], y0[a:b], x0[a:b]] = tn[a:b]
+    return out

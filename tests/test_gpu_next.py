@@ -136,3 +136,37 @@ def test_filter_matches_config_size(einx):
         i = np.nonzero(a[k] >= 0)[0]
         assert np.array_equal(b[k][a[k][i]], i) and (a[k] >= 0).sum() == (b[k] >= 0).sum()
         assert (a[k] >= 0).sum() >= 400
+
+
+# ------------------------------------------------ event stack / time surface ---- #
+def test_event_stack_and_time_surface_golden(einx, golden):
+    """Bit-exact against the reference's own outputs (integer sums; fp32-rounded fp64 times), including events
+    that sit exactly on bin boundaries and therefore count in two bins."""
+    g = golden["repr"]
+    for ci in range(int(g["ncases"])):
+        bins, H, W = (int(v) for v in g[f"c{ci}_shape"])
+        ev = {k: g[f"c{ci}_{k}"].copy() for k in "xytp"}
+        stack = einx.events_to_event_stack(dict(ev), (bins, H, W), DEV)
+        assert stack.dtype == torch.float32 and np.array_equal(stack.numpy(), g[f"c{ci}_stack"]), ci
+        mutated = dict(ev)
+        surf = einx.events_to_time_surface(mutated, (bins, H, W), DEV)
+        assert np.array_equal(surf.numpy(), g[f"c{ci}_surface"]), ci
+        assert mutated["t"][0] == 0.0 and mutated["t"][-1] < 1.0  # the reference normalises the caller's dict
+
+
+def test_binned_representations_batch_vs_oracle(einx):
+    import importlib
+
+    synth = importlib.import_module("ei-nexus_official_b200.synth")
+    rng = np.random.default_rng(21)
+    H, W, bins = 180, 240, 8
+    evs = [synth.events(rng, n, H, W, "ec") for n in (60_000, 1, 5_000, 777)]
+    x, y, t, p, off = (a.to(DEV) for a in einx.pack_events(evs))
+    stack = einx.event_stack_device(x, y, t, p, off, (bins, H, W)).cpu().numpy()
+    surf = einx.time_surface_device(x, y, t, p, off, (bins, H, W)).cpu().numpy()
+    for i, ev in enumerate(evs):
+        assert np.array_equal(stack[i], O.events_to_event_stack(ev["x"], ev["y"], ev["t"], ev["p"], bins, H, W)), i
+        assert np.array_equal(surf[i], O.events_to_time_surface(ev["x"], ev["y"], ev["t"], ev["p"], bins, H, W)), i
+    # every event lands in at least one bin: |stack| sums to >= the event count only when no +1/-1 cancel, so check the
+    # polarity balance instead: sum over bins and pixels = sum(2p - 1) + boundary duplicates (none for random times)
+    assert stack[0].sum() == (2 * evs[0]["p"].astype(np.int32) - 1).sum()

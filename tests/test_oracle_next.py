@@ -32,3 +32,12 @@ def test_filter_matches_matches_reference(golden):
         assert np.array_equal(m0, g[f"fm{ci}_m0"]) and np.array_equal(m1, g[f"fm{ci}_m1"])
         np.testing.assert_allclose(s0, g[f"fm{ci}_s0"], rtol=2e-6)
         np.testing.assert_allclose(s1, g[f"fm{ci}_s1"], rtol=2e-6)
+
+
+def test_event_stack_and_time_surface_match_reference(golden):
+    g = golden["repr"]
+    for ci in range(int(g["ncases"])):
+        bins, H, W = (int(v) for v in g[f"c{ci}_shape"])
+        ev = [g[f"c{ci}_{k}"] for k in "xytp"]
+        assert np.array_equal(O.events_to_event_stack(*ev, bins, H, W), g[f"c{ci}_stack"])
+        assert np.array_equal(O.events_to_time_surface(*ev, bins, H, W), g[f"c{ci}_surface"])
