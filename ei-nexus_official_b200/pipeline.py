@@ -72,8 +72,9 @@ class ExtractMatchPipeline:
 
         The three branches of the step share no data until the matcher: voxelisation (L2-reduction bound)
         and the second side's detect -> sample chain are forked onto two side streams, each with its own
-        einx context (workspace), and joined before the MNN kernel -- so the latency-bound NMS rounds of
-        one side overlap the other side's sampling and the event scatter instead of queueing behind them."""
+        einx context (workspace); the side chain joins before the MNN kernel, the voxel stream after it -- so the
+        latency-bound NMS rounds of one side overlap the other side's sampling and the event scatter instead of
+        queueing behind them."""
         if not self.cfg.concurrent:
             grid = self.voxelize(*events)
             k0, c0, d0 = self.extract(score0, raw0, mask0)
@@ -90,7 +91,6 @@ class ExtractMatchPipeline:
                 grid = self.voxelize(*events)
             k0, c0, d0 = self.extract(score0, raw0, mask0)
             main.wait_stream(s_side)
-            main.wait_stream(s_vox)
             if not torch.cuda.is_current_stream_capturing():
                 # caching-allocator bookkeeping: tensors cross streams in both directions (a captured
                 # step owns its memory pool for the lifetime of the graph instead)
@@ -102,6 +102,10 @@ class ExtractMatchPipeline:
                 for t in events:
                     t.record_stream(s_vox)
         out = match.mnn(d0, d1, c0, c1, k0, k1, None, None, True, self.cfg.precision)
+        if self.cfg.concurrent:
+            # the matcher does not read the voxel grid: its stream joins only here, so a late event scatter never
+            # holds the MNN kernel back
+            torch.cuda.current_stream(score0.device).wait_stream(s_vox)
         out.update(voxel_grid=grid, keypoints0=k0, keypoints1=k1, counts0=c0, counts1=c1,
                    descriptors0=d0, descriptors1=d1)
         return out
