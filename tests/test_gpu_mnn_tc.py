@@ -149,3 +149,17 @@ def test_similarity_values_are_fp32_accurate(einx, precision):
     assert must.sum() > 500 and must_not.sum() > 500
     assert got[must].all(), f"{(~got[must]).sum()} rows above the threshold were dropped"
     assert not got[must_not].any(), f"{got[must_not].sum()} rows below the threshold were kept"
+
+
+@pytest.mark.parametrize("precision", ["fp16x3", "tf32x3"])
+def test_split_paths_at_c4_size(einx, synth, precision):
+    """BASELINE configs[3]: 8192 x 8192 keypoints, 128-d.  Index parity with the fp32 oracle (near-ties excluded) and the
+    size-independent properties: mutual consistency and equal match counts on both sides."""
+    rng = np.random.default_rng(8192)
+    d0, d1 = synth.descriptor_pair(rng, 8192, 8192, 128, 1.41, dups=5)
+    out = einx.mnn(cuda(d0[None]), cuda(d1[None]), precision=precision)
+    m0, m1 = out["matches0"][0].cpu().numpy(), out["matches1"][0].cpu().numpy()
+    check_against(m0, m1, d0, d1)
+    keep = m0 > -1
+    assert keep.sum() == (m1 > -1).sum() > 3000
+    assert np.array_equal(m1[m0[keep]], np.nonzero(keep)[0])
