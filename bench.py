@@ -467,7 +467,7 @@ def run_einx(args, synth):
                                "CUDA events inside bursts of back-to-back steps)")
         if dominant == "detect":
             roof["note"] = ("largest share only as the sum of its two launches (one per side); iterative NMS in shared memory is "
-                            "bound by instruction issue (41 % of issue slots under ncu), not by HBM: the map is read once, "
+                            "bound by instruction issue (48 % of issue slots under ncu), not by HBM: the map is read once, "
                             "12 MB per launch.  Per launch the MNN kernel is the longest: see kernels.mnn_similarity")
         log("timing the CPU baseline (oracle port) ...")
         cores = os.cpu_count() or 1

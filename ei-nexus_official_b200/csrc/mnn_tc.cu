@@ -3,19 +3,21 @@
 // Semantics: reference core/modules/matchers/MNN.py:88-92 (einsum + 2x topk(1)); the thresholds and
 // the mutual check run in mnn.cu's finalisation kernel on the keys this kernel produces.
 //
-// Persistent, warp-specialised CTA (one per SM):
-//   warp 0   TMA producer   -- A tile 128 rows x 128 B, B tile 256 rows x 128 B per k-block
-//   warp 1   MMA issuer     -- one lane issues tcgen05.mma (M=128, N=256, K=32 bytes) x4 per k-block
-//   warp 2   TMEM allocator -- 512 columns = two 128x256 fp32 accumulators (double buffered)
-//   warps 4-11 epilogue     -- tcgen05.ld 32 columns at a time; per-row running max in registers,
-//                              per-column max through a padded 32x32 shared-memory transpose, then
-//                              one 64-bit atomicMax per row / column into the global key arrays
+// Persistent, warp-specialised CTA (one per SM; the two CTAs of a cluster share a 256-row tile in the pair form):
+//   warp 0      TMA producer   -- per k-block an A tile of 128 rows and a B tile of 256 (pair form: 128) rows
+//   warp 1      MMA issuer     -- one lane issues tcgen05.mma (M = 128 or 256 across the pair, N = 256, K = 32 bytes)
+//   warp 2      TMEM allocator -- 512 columns = two 128x256 fp32 accumulators (double buffered)
+//   warps 4..   epilogue       -- tcgen05.ld 32 columns at a time, one chunk ahead; row argmax as a tournament over
+//                                 the chunk's 32 registers, column argmax the same way after a padded 32x32
+//                                 shared-memory transpose; one 64-bit atomicMax per row / column into the key arrays
+//   then        converters     -- split modes only: derive the low-order operand tiles in shared memory
 // The similarity matrix therefore never leaves the SM.
 //
-// Precision modes (include/einx.h): BF16 rounds the descriptors to bf16 (kind::f16); TF32X3 splits
-// every fp32 descriptor into hi = tf32(x) and lo = x - hi and accumulates hi*hi + hi*lo + lo*hi
-// (kind::tf32) by running the k-loop three times over different operand pairs -- fp32-accurate to
-// a few 1e-7 while staying on the tensor pipe.
+// Precision modes (include/einx.h): BF16 rounds the descriptors to bf16 (kind::f16).  TF32X3 splits every fp32
+// descriptor into hi = tf32(x) and lo = x - hi and accumulates hi*hi + hi*lo + lo*hi (kind::tf32) by running the
+// k-loop three times over different operand pairs.  FP16X3 does the same with hi = fp16(2^10 x), lo = fp16(2^10 x - hi)
+// (kind::f16): the same 22 significant bits at the fp16 tensor rate and half the operand bytes.  Both splits are
+// fp32-accurate to a few 1e-7 while staying on the tensor pipe.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -29,7 +31,7 @@ namespace {
 constexpr int TILE_M = 128;          // rows of d0 per tile  (UMMA M, TMEM lanes)
 constexpr int TILE_N = 256;          // rows of d1 per tile  (UMMA N, TMEM columns)
 constexpr int kEpilogueWarp0 = 4;
-// warp budget of the split-precision kernels (3xTF32, FP16X3): epilogue + converter warps share 16 slots
+// warp budgets (build knobs; the defaults are the measured optimum on B200)
 #ifndef EINX_SPLIT_EPI_WARPS
 #define EINX_SPLIT_EPI_WARPS 8
 #endif
