@@ -489,17 +489,17 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     // four floats of raw chunk c become the (c & 1) half of fp16 chunk c >> 1.
                     static_assert(KIND != 2 || KB == 128, "FP16X3 stages 32-element k-blocks");
                     unsigned char* ops = tiles + (size_t)stage * STAGE_BYTES + RAW_BYTES;
-                    constexpr int kAChunks = A_BYTES / 16;
+                    constexpr int kConvThreads = KIND == 2 ? C::kConvWarps * 32 : 256;  // (the branch is dead for the other kinds)
+                    constexpr int kAIters = A_BYTES / 16 / kConvThreads, kBIters = B_BYTES / 16 / kConvThreads;
+                    static_assert(KIND != 2 || (kConvThreads == 256 && kAIters * kConvThreads * 16 == A_BYTES &&
+                                                kBIters * kConvThreads * 16 == B_BYTES),
+                                  "a thread's chunks are 32 rows apart: its swizzle terms are loop invariant");
                     const float sc = P.in_scale;
-#pragma unroll 4
-                    for (int i = ct; i < kChunks; i += C::kConvWarps * 32) {
-                        const float4 v = raw[i];
-                        const bool isB = i >= kAChunks;
-                        const int li = isB ? i - kAChunks : i;
-                        const int r = li >> 3, c = (li & 7) ^ (r & 7);
-                        const uint32_t off = (uint32_t)r * 64u + (uint32_t)(((c >> 1) ^ ((r >> 1) & 3)) << 4) + (uint32_t)((c & 1) << 3);
-                        unsigned char* hi_t = ops + (isB ? C::kOpABytes : 0);
-                        unsigned char* lo_t = hi_t + C::kOpABytes + C::kOpBBytes;
+                    // thread ct owns raw chunk ct of every 32-row slab: row r0 + 32 n, physical chunk ct & 7, so the
+                    // logical chunk c and both swizzle terms depend on ct only and the destination advances 2 KB per slab
+                    const int r0 = ct >> 3, c = (ct & 7) ^ (r0 & 7);
+                    const uint32_t off0 = (uint32_t)r0 * 64u + (uint32_t)(((c >> 1) ^ ((r0 >> 1) & 3)) << 4) + (uint32_t)((c & 1) << 3);
+                    auto split4 = [&](const float4 v, unsigned char* hi_t, unsigned char* lo_t, uint32_t off) {
                         const float x0 = v.x * sc, x1 = v.y * sc, x2 = v.z * sc, x3 = v.w * sc;
                         const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
                         const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
@@ -509,7 +509,15 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                         lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
                         *reinterpret_cast<uint2*>(hi_t + off) = hv;
                         *reinterpret_cast<uint2*>(lo_t + off) = lv;
-                    }
+                    };
+                    unsigned char* a_hi = ops;
+                    unsigned char* b_hi = ops + C::kOpABytes;
+                    constexpr int kLoOff = C::kOpABytes + C::kOpBBytes;
+#pragma unroll
+                    for (int n = 0; n < kAIters; ++n) split4(raw[ct + n * kConvThreads], a_hi, a_hi + kLoOff, off0 + 2048u * n);
+#pragma unroll 4
+                    for (int n = 0; n < kBIters; ++n)
+                        split4(raw[A_BYTES / 16 + ct + n * kConvThreads], b_hi, b_hi + kLoOff, off0 + 2048u * n);
                 }
                 // generic-proxy writes must be visible to the tensor core's async-proxy reads
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
