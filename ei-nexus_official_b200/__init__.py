@@ -11,7 +11,7 @@ from .describe import sample, sparsify_full_resolution_descriptors, sparsify_low
 from .detection import (depth_to_space, detect, events_mask, logits_to_prob, logits_to_score, prob_map_to_points_map,
                         prob_map_to_positions_with_prob)
 from .dist import gather_matches, pack_matches, shard_range
-from .match import NearestNeighborMatcher, filter_matches, mnn, mnn_dense
+from .match import NearestNeighborMatcher, filter_matches, mnn, mnn_dense, sigmoid_log_double_softmax
 from .patch import patch_reference
 from .pipeline import CapturedStep, ExtractMatchPipeline, HostBatch, HostStreamer, PathConfig
 from .voxel import (draw_events_accumulation_image, event_stack_device, events_image_device, events_to_event_stack,
@@ -25,5 +25,5 @@ __all__ = [
     "mnn", "mnn_dense", "ExtractMatchPipeline", "CapturedStep", "HostBatch", "HostStreamer", "PathConfig", "patch_reference", "shard_range", "pack_matches",
     "gather_matches", "logits_to_prob", "depth_to_space", "logits_to_score", "events_mask",
     "draw_events_accumulation_image", "events_image_device", "filter_matches", "events_to_event_stack",
-    "events_to_time_surface", "event_stack_device", "time_surface_device",
+    "events_to_time_surface", "event_stack_device", "time_surface_device", "sigmoid_log_double_softmax",
 ]

@@ -139,3 +139,33 @@ def filter_matches(scores: torch.Tensor, th: float):
                                      _lib.ptr(s0), _lib.ptr(s1), ctx.stream)
     ctx.check(rc, "einx_filter_matches")
     return m0, m1, s0, s1
+
+
+@torch.no_grad()
+def sigmoid_log_double_softmax(sim: torch.Tensor, z0: torch.Tensor, z1: torch.Tensor) -> torch.Tensor:
+    """Drop-in for ``core/modules/matchers/lightglue.py:365-377``: the (B, M+1, N+1) log-assignment matrix from
+    similarities (B, M, N) and matchability logits z0 (B, M, 1), z1 (B, N, 1) (einx_log_double_softmax: row and
+    column log-sum-exp in one pass, the matrix written in a second pass out of L2).  Inference only (no autograd)."""
+    for name, v in (("sim", sim), ("z0", z0), ("z1", z1)):
+        if v.dtype != torch.float32 or not v.is_cuda:
+            raise _lib.EinxError(f"sigmoid_log_double_softmax: {name} must be a float32 CUDA tensor (there is no CPU fallback)")
+    if sim.dim() != 3:
+        raise ValueError("sigmoid_log_double_softmax: expected sim of shape (B, M, N)")
+    B, M, N = sim.shape
+    if z0.numel() != B * M or z1.numel() != B * N:
+        raise ValueError("sigmoid_log_double_softmax: z0 / z1 must be (B, M, 1) / (B, N, 1)")
+    dev = sim.device
+    scores = torch.empty((B, M + 1, N + 1), dtype=torch.float32, device=dev)
+    if M == 0 or N == 0:  # nothing to normalise: only the unmatched row / column (torch accepts this shape)
+        scores.zero_()
+        if M:
+            scores[:, :-1, -1] = torch.nn.functional.logsigmoid(-z0.reshape(B, M))
+        if N:
+            scores[:, -1, :-1] = torch.nn.functional.logsigmoid(-z1.reshape(B, N))
+        return scores
+    sim, z0, z1 = sim.contiguous(), z0.reshape(B, M).contiguous(), z1.reshape(B, N).contiguous()
+    ctx = _lib.context_for(dev)
+    rc = ctx.lib.einx_log_double_softmax(ctx.handle, _lib.ptr(sim), _lib.ptr(z0), _lib.ptr(z1), B, M, N, _lib.ptr(scores),
+                                         ctx.stream)
+    ctx.check(rc, "einx_log_double_softmax")
+    return scores

@@ -27,6 +27,7 @@ _FUNCS = {
     "logits_to_prob": detect.logits_to_prob,
     "depth_to_space": detect.depth_to_space,
     "filter_matches": match.filter_matches,
+    "sigmoid_log_double_softmax": match.sigmoid_log_double_softmax,
 }
 
 _MODULE_HINTS = ("representations", "detector_util", "descriptor_util", "MNN", "EventExtractors",

@@ -213,6 +213,20 @@ int einx_logits_to_score(einx_ctx* ctx, const float* logits, int B, int C, int H
 int einx_filter_matches(einx_ctx* ctx, const float* scores, int B, int M, int N, float th,
                         int64_t* m0, int64_t* m1, float* ms0, float* ms1, einx_stream stream);
 
+/*
+ * LightGlue log-assignment matrix.  Replaces core/modules/matchers/lightglue.py:365-377
+ * (sigmoid_log_double_softmax, called from MatchAssignment.forward :393):
+ *   scores[b, i, j] = log_softmax(sim, 2)[b, i, j] + log_softmax(sim, 1)[b, i, j]
+ *                     + logsigmoid(z0[b, i]) + logsigmoid(z1[b, j])          i < M, j < N
+ *   scores[b, i, N] = logsigmoid(-z0[b, i]);  scores[b, M, j] = logsigmoid(-z1[b, j]);  scores[b, M, N] = 0
+ *   sim (B, M, N), z0 (B, M), z1 (B, N), scores (B, M+1, N+1), all fp32 and contiguous.
+ * Row and column (max, log-sum-exp) statistics in one pass over sim, the matrix written in a second
+ * pass served by L2 (the entry point walks the batch in chunks of <= 32 MB of similarities).
+ * fp32 exp / log / summation order: agrees with torch to ~1e-6 of the magnitude, not bit-exact.
+ */
+int einx_log_double_softmax(einx_ctx* ctx, const float* sim, const float* z0, const float* z1,
+                            int B, int M, int N, float* scores, einx_stream stream);
+
 /* Number of kernel launches issued through `ctx` so far (bench.py's gpu_launches). */
 int64_t einx_launch_count(const einx_ctx* ctx);
 

@@ -507,6 +507,33 @@ def filter_matches(scores, th):
     return np.where(valid0, m0, -1), np.where(valid1, m1, -1), ms0, ms1
 
 
+def _log_sigmoid(x):
+    """torch's logsigmoid: min(x, 0) - log1p(exp(-|x|)); fp32."""
+    x = np.asarray(x, dtype=F32)
+    return (np.minimum(x, F32(0)) - np.log1p(np.exp(-np.abs(x)))).astype(F32)
+
+
+def _log_softmax(x, axis):
+    x = np.asarray(x, dtype=F32)
+    s = x - x.max(axis=axis, keepdims=True)
+    return (s - np.log(np.exp(s).sum(axis=axis, keepdims=True, dtype=F32))).astype(F32)
+
+
+def sigmoid_log_double_softmax(sim, z0, z1):
+    """LightGlue log-assignment matrix (core/modules/matchers/lightglue.py:365-377): row + column log-softmax of the
+    similarities plus the matchability certainties; unmatched row / column logsigmoid(-z); corner 0.  fp32."""
+    sim = np.asarray(sim, dtype=F32)
+    b, m, n = sim.shape
+    z0 = np.asarray(z0, dtype=F32).reshape(b, m)
+    z1 = np.asarray(z1, dtype=F32).reshape(b, n)
+    cert = _log_sigmoid(z0)[:, :, None] + _log_sigmoid(z1)[:, None, :]
+    out = np.zeros((b, m + 1, n + 1), dtype=F32)
+    out[:, :m, :n] = (_log_softmax(sim, 2) + _log_softmax(sim, 1)) + cert
+    out[:, :-1, -1] = _log_sigmoid(-z0)
+    out[:, -1, :-1] = _log_sigmoid(-z1)
+    return out
+
+
 def _bin_slices(tn, nbins):
     """np.searchsorted bounds of the reference's per-bin loops (representations.py:44-47, 196-199):
     bin i owns events with i*dt <= t <= i*dt + dt, both ends inclusive."""

@@ -170,3 +170,45 @@ def test_binned_representations_batch_vs_oracle(einx):
     # every event lands in at least one bin: |stack| sums to >= the event count only when no +1/-1 cancel, so check the
     # polarity balance instead: sum over bins and pixels = sum(2p - 1) + boundary duplicates (none for random times)
     assert stack[0].sum() == (2 * evs[0]["p"].astype(np.int32) - 1).sum()
+
+
+# ------------------------------------------------------- sigmoid_log_double_softmax ---- #
+LDS_TOL = 2e-6  # of max(1, |ref|): fp32 exp / log / summation order (the oracle itself is within 4e-7 of torch)
+
+
+def test_log_double_softmax_golden(einx, golden):
+    g = golden["lg"]
+    for ci in range(int(g["ncases"])):
+        ref = g[f"c{ci}_scores"]
+        out = einx.sigmoid_log_double_softmax(cuda(g[f"c{ci}_sim"]), cuda(g[f"c{ci}_z0"]), cuda(g[f"c{ci}_z1"]))
+        assert out.shape == ref.shape and out.dtype == torch.float32
+        out = out.cpu().numpy()
+        assert np.all(np.abs(out - ref) <= LDS_TOL * np.maximum(1.0, np.abs(ref))), (ci, np.abs(out - ref).max())
+        assert out[:, -1, -1].tolist() == [0.0] * ref.shape[0]
+        # chained with filter_matches: the reference's matches come out of our matrix
+        m0, m1, s0, s1 = einx.filter_matches(cuda(out), float(g[f"c{ci}_th"]))
+        assert np.array_equal(m0.cpu().numpy(), g[f"c{ci}_m0"]) and np.array_equal(m1.cpu().numpy(), g[f"c{ci}_m1"])
+        np.testing.assert_allclose(s0.cpu().numpy(), g[f"c{ci}_s0"], rtol=1e-4, atol=1e-30)
+
+
+def test_log_double_softmax_config_size(einx):
+    """C2 keypoint count, several batch chunks (32 MB of similarities per chunk = 8 items), ragged last chunk."""
+    rng = np.random.default_rng(21)
+    B, M, N = 19, 1024, 1000
+    sim = (6.0 * rng.standard_normal((B, M, N))).astype(np.float32)
+    z0 = (2.0 * rng.standard_normal((B, M, 1))).astype(np.float32)
+    z1 = (2.0 * rng.standard_normal((B, N, 1))).astype(np.float32)
+    out = einx.sigmoid_log_double_softmax(cuda(sim), cuda(z0), cuda(z1)).cpu().numpy()
+    for b in (0, 7, 8, 18):
+        ref = O.sigmoid_log_double_softmax(sim[b:b + 1], z0[b:b + 1], z1[b:b + 1])
+        assert np.all(np.abs(out[b:b + 1] - ref) <= LDS_TOL * np.maximum(1.0, np.abs(ref))), b
+    # size-independent property: exp(row log-softmax) sums to one  <=>  logsumexp_j(scores - col terms) ...
+    # checked in the simplest form: scores - certainties = row log-softmax + column log-softmax <= 0
+    t = torch.from_numpy(out[:, :-1, :-1])
+    cert = torch.nn.functional.logsigmoid(torch.from_numpy(z0)) + torch.nn.functional.logsigmoid(torch.from_numpy(z1)).transpose(1, 2)
+    assert float((t - cert).max()) <= 1e-5
+
+
+def test_log_double_softmax_rejects_cpu(einx):
+    with pytest.raises(einx.EinxError):
+        einx.sigmoid_log_double_softmax(torch.zeros(1, 2, 2), torch.zeros(1, 2, 1), torch.zeros(1, 2, 1))

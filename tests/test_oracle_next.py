@@ -41,3 +41,16 @@ def test_event_stack_and_time_surface_match_reference(golden):
         ev = [g[f"c{ci}_{k}"] for k in "xytp"]
         assert np.array_equal(O.events_to_event_stack(*ev, bins, H, W), g[f"c{ci}_stack"])
         assert np.array_equal(O.events_to_time_surface(*ev, bins, H, W), g[f"c{ci}_surface"])
+
+
+def test_log_double_softmax_matches_reference(golden):
+    g = golden["lg"]
+    for ci in range(int(g["ncases"])):
+        ref = g[f"c{ci}_scores"]
+        out = O.sigmoid_log_double_softmax(g[f"c{ci}_sim"], g[f"c{ci}_z0"], g[f"c{ci}_z1"])
+        assert out.shape == ref.shape and out.dtype == np.float32
+        # fp32 exp / log / summation order: 1e-6 of the magnitude (measured 4e-7)
+        assert np.all(np.abs(out - ref) <= 1e-6 * np.maximum(1.0, np.abs(ref))), ci
+        # the reference's own filter_matches output on its own matrix is reproduced from the oracle's matrix
+        m0, m1, s0, s1 = O.filter_matches(ref, float(g[f"c{ci}_th"]))
+        assert np.array_equal(m0, g[f"c{ci}_m0"]) and np.array_equal(m1, g[f"c{ci}_m1"])

@@ -79,6 +79,18 @@ def bench_next(args):
     sc = torch.randn((B, K + 1, K + 1), device=DEV) - 5
     ms = time_ms(lambda: einx.filter_matches(sc, 0.1))
     print(f"filter_matches {B}x{K + 1}x{K + 1}: {ms:.4f} ms = {sc.numel() * 4 / ms / 1e6:.0f} GB/s algorithmic", flush=True)
+    sim = 4 * torch.randn((B, K, K), device=DEV)
+    z0, z1 = torch.randn((B, K, 1), device=DEV), torch.randn((B, K, 1), device=DEV)
+    for mb in ("8", "16", "32", "64", "100000"):
+        os.environ["EINX_LDS_CHUNK_MB"] = mb
+        ms = time_ms(lambda: einx.sigmoid_log_double_softmax(sim, z0, z1))
+        print(f"sigmoid_log_double_softmax {B}x{K}x{K}, {mb} MB of similarities per chunk: {ms:.4f} ms = "
+              f"{(sim.numel() * 4 + sc.numel() * 4) / ms / 1e6:.0f} GB/s algorithmic (sim read once + matrix written once)", flush=True)
+    os.environ.pop("EINX_LDS_CHUNK_MB")
+    ref = lambda: (torch.log_softmax(sim, 2) + torch.log_softmax(sim, 1) + torch.nn.functional.logsigmoid(z0)
+                   + torch.nn.functional.logsigmoid(z1).transpose(1, 2))
+    ms = time_ms(ref)
+    print(f"  torch (log_softmax over rows + over columns + certainties, interior only, for scale): {ms:.4f} ms", flush=True)
 
 
 def bench_stages(args):
