@@ -9,11 +9,11 @@
 //                           max / rescaled sum), the row statistics of each block come out of a padded
 //                           shared-memory transpose (lane = row) and are merged across the CTA's 8 warps.
 //                           Partials (max, sum) go to the workspace: M/128 per column, N/256 per row.
-//   2. lds_merge_kernel   : folds the partials; leaves (max, log sum, logsigmoid(z), logsigmoid(-z)) per row / column.
-//   3. lds_write_kernel   : second read of sim, one coalesced write of the (M+1) x (N+1) matrix incl. the
-//                           unmatched row / column and the zero corner.
-// The host loop issues the three per chunk of batch items whose similarities fit a fraction of L2, so the
-// second read is served by L2: HBM sees sim once and scores once (8 B per element instead of 12).
+//   2. lds_merge_kernel   : folds the partials; leaves (max, log sum, logsigmoid(z)) per row / column and writes the
+//                           unmatched row / column, logsigmoid(-z), and the zero corner of the matrix.
+//   3. lds_write_kernel   : second read of sim, one coalesced write of the M x N interior of the matrix.
+// HBM sees sim twice and scores once: 12 B per element (walking the batch in L2-sized chunks so that the second
+// read hits L2 was measured and lost to the smaller launches; see the entry point).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -37,34 +37,30 @@ __device__ __forceinline__ void lse_merge(float& m, float& s, float m2, float s2
 // torch: min(x, 0) - log1p(exp(-|x|))
 __device__ __forceinline__ float log_sigmoid(float x) { return fminf(x, 0.0f) - log1pf(expf(-fabsf(x))); }
 
-__global__ void __launch_bounds__(kThreads, 2)
-lds_stats_kernel(const float* __restrict__ sim, int M, int N, int nrt, int nct, float2* __restrict__ rowpart,
-                 float2* __restrict__ colpart) {
-    const int b = blockIdx.z;
-    const int i0 = blockIdx.y * kTileRows;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int j = blockIdx.x * kTileCols + warp * 32 + lane;
-    const float* S = sim + (size_t)b * M * N;
-    __shared__ float scratch[kWarps][32 * kPitch];
-    __shared__ float2 rowred[kTileRows / 32][kWarps][32];
-    float* sc = scratch[warp];
-    float cm = -INFINITY, cs = 0.0f;
+// exp of a non-positive difference inside the sums: ex2.approx(d * log2 e), 2 + |1.17 d| ulp -- the terms that carry
+// the sum have d near 0 (2 ulp), the ones with a large |d| weigh exp(d); expf() here made the pass issue bound
+__device__ __forceinline__ float exp_term(float d) { return __expf(d); }
+
+template <bool FULL>
+__device__ __forceinline__ void lds_stats_tile(const float* __restrict__ S, int M, int N, int i0, int j, int warp, int lane,
+                                               float* sc, float2 (*rowred)[kWarps][32], float& cm, float& cs) {
 #pragma unroll 1
     for (int rb = 0; rb < kTileRows / 32; ++rb) {
         const int r0 = i0 + rb * 32;
+        const float* p = S + (size_t)r0 * N + j;
         float v[32];
 #pragma unroll
-        for (int r = 0; r < 32; ++r) v[r] = (r0 + r < M && j < N) ? __ldg(S + (size_t)(r0 + r) * N + j) : -INFINITY;
+        for (int r = 0; r < 32; ++r) v[r] = (FULL || (r0 + r < M && j < N)) ? __ldg(p + (size_t)r * N) : -INFINITY;
 #pragma unroll
         for (int r = 0; r < 32; ++r) sc[r * kPitch + lane] = v[r];
         // column j over these 32 rows
         float bm = v[0];
 #pragma unroll
         for (int r = 1; r < 32; ++r) bm = fmaxf(bm, v[r]);
-        if (bm > -INFINITY) {
+        if (FULL || bm > -INFINITY) {
             float bs = 0.0f;
 #pragma unroll
-            for (int r = 0; r < 32; ++r) bs += expf(v[r] - bm);
+            for (int r = 0; r < 32; ++r) bs += exp_term(v[r] - bm);
             lse_merge(cm, cs, bm, bs);
         }
         __syncwarp();
@@ -76,13 +72,30 @@ lds_stats_kernel(const float* __restrict__ sim, int M, int N, int nrt, int nct, 
 #pragma unroll
         for (int k = 1; k < 32; ++k) rm = fmaxf(rm, g[k]);
         float rs = 0.0f;
-        if (rm > -INFINITY) {
+        if (FULL || rm > -INFINITY) {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) rs += expf(g[k] - rm);
+            for (int k = 0; k < 32; ++k) rs += exp_term(g[k] - rm);
         }
         rowred[rb][warp][lane] = make_float2(rm, rs);
         __syncwarp();
     }
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+lds_stats_kernel(const float* __restrict__ sim, int M, int N, int nrt, int nct, float2* __restrict__ rowpart,
+                 float2* __restrict__ colpart) {
+    const int b = blockIdx.z;
+    const int i0 = blockIdx.y * kTileRows;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * kTileCols + warp * 32 + lane;
+    const float* S = sim + (size_t)b * M * N;
+    __shared__ float scratch[kWarps][32 * kPitch];
+    __shared__ float2 rowred[kTileRows / 32][kWarps][32];
+    float cm = -INFINITY, cs = 0.0f;
+    if (i0 + kTileRows <= M && (blockIdx.x + 1) * kTileCols <= N)  // CTA-uniform: interior tiles skip the bounds tests
+        lds_stats_tile<true>(S, M, N, i0, j, warp, lane, scratch[warp], rowred, cm, cs);
+    else
+        lds_stats_tile<false>(S, M, N, i0, j, warp, lane, scratch[warp], rowred, cm, cs);
     if (j < N) colpart[((size_t)b * nrt + blockIdx.y) * N + j] = make_float2(cm, cs);
     __syncthreads();
     if (threadIdx.x < kTileRows) {
@@ -98,13 +111,15 @@ lds_stats_kernel(const float* __restrict__ sim, int M, int N, int nrt, int nct, 
     }
 }
 
-// stat = (max, log(sum exp(x - max)), logsigmoid(z), logsigmoid(-z)) per row (t < M) or column (t >= M)
+// Folds the partials: stat = (max, log(sum exp(x - max)), logsigmoid(z)) per row (t < M) or column (M <= t < M + N);
+// also writes the unmatched column / row of the matrix, logsigmoid(-z), and the zero corner (t == M + N).
 __global__ void __launch_bounds__(256)
 lds_merge_kernel(const float2* __restrict__ rowpart, const float2* __restrict__ colpart, const float* __restrict__ z0,
                  const float* __restrict__ z1, int M, int N, int nrt, int nct, float4* __restrict__ rowstat,
-                 float4* __restrict__ colstat) {
+                 float4* __restrict__ colstat, float* __restrict__ scores) {
     const int b = blockIdx.y;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    float* O = scores + (size_t)b * (M + 1) * ((size_t)N + 1);
     if (t < M) {
         float m = -INFINITY, s = 0.0f;
         for (int c = 0; c < nct; ++c) {
@@ -112,7 +127,8 @@ lds_merge_kernel(const float2* __restrict__ rowpart, const float2* __restrict__ 
             lse_merge(m, s, p.x, p.y);
         }
         const float z = z0[(size_t)b * M + t];
-        rowstat[(size_t)b * M + t] = make_float4(m, logf(s), log_sigmoid(z), log_sigmoid(-z));
+        rowstat[(size_t)b * M + t] = make_float4(m, logf(s), log_sigmoid(z), 0.0f);
+        O[(size_t)t * (N + 1) + N] = log_sigmoid(-z);
     } else if (t < M + N) {
         const int j = t - M;
         float m = -INFINITY, s = 0.0f;
@@ -121,47 +137,51 @@ lds_merge_kernel(const float2* __restrict__ rowpart, const float2* __restrict__ 
             lse_merge(m, s, p.x, p.y);
         }
         const float z = z1[(size_t)b * N + j];
-        colstat[(size_t)b * N + j] = make_float4(m, logf(s), log_sigmoid(z), log_sigmoid(-z));
+        colstat[(size_t)b * N + j] = make_float4(m, logf(s), log_sigmoid(z), 0.0f);
+        O[(size_t)M * (N + 1) + j] = log_sigmoid(-z);
+    } else if (t == M + N) {
+        O[(size_t)M * (N + 1) + N] = 0.0f;
     }
 }
 
-constexpr int kWriteRows = 16;
+// Rows per CTA of the write pass (= loads in flight per thread).  Measured on B200, C2 shape, whole entry point:
+// 4 rows 0.180 ms, 8 rows 0.170 ms, 16 rows 0.187 ms, 32 rows 0.204 ms; streaming (.cs) loads / stores change nothing.
+constexpr int kWriteRows = 8;
 
+template <bool FULL>
+__device__ __forceinline__ void lds_write_tile(const float* __restrict__ p, const float4* __restrict__ rs, const float4 c, int rows,
+                                               int N, float* __restrict__ o) {
+    float v[kWriteRows];
+#pragma unroll
+    for (int r = 0; r < kWriteRows; ++r) v[r] = (FULL || r < rows) ? __ldg(p + (size_t)r * N) : 0.0f;
+#pragma unroll
+    for (int r = 0; r < kWriteRows; ++r) {
+        if (FULL || r < rows) {
+            const float4 q = rs[r];
+            // (log_softmax over j) + (log_softmax over i) + (logsigmoid(z0) + logsigmoid(z1)), torch's association
+            const float s0 = __fsub_rn(__fsub_rn(v[r], q.x), q.y);
+            const float s1 = __fsub_rn(__fsub_rn(v[r], c.x), c.y);
+            o[(size_t)r * (N + 1)] = __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(q.z, c.z));
+        }
+    }
+}
+
+// interior of the matrix: thread = column, kWriteRows rows per CTA
 __global__ void __launch_bounds__(256)
 lds_write_kernel(const float* __restrict__ sim, const float4* __restrict__ rowstat, const float4* __restrict__ colstat, int M,
                  int N, float* __restrict__ scores) {
     const int b = blockIdx.z;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i0 = blockIdx.y * kWriteRows;
-    if (j > N) return;
-    const float* S = sim + (size_t)b * M * N;
-    float* O = scores + (size_t)b * (M + 1) * ((size_t)N + 1);
-    const float4* rs = rowstat + (size_t)b * M;
-    if (j == N) {  // unmatched column: logsigmoid(-z0), corner 0
-#pragma unroll 4
-        for (int r = 0; r < kWriteRows; ++r) {
-            const int i = i0 + r;
-            if (i <= M) O[(size_t)i * (N + 1) + N] = i < M ? rs[i].w : 0.0f;
-        }
-        return;
-    }
+    if (j >= N) return;
+    const float* p = sim + ((size_t)b * M + i0) * N + j;
+    float* o = scores + ((size_t)b * (M + 1) + i0) * ((size_t)N + 1) + j;
+    const float4* rs = rowstat + (size_t)b * M + i0;
     const float4 c = colstat[(size_t)b * N + j];
-    float v[kWriteRows];
-#pragma unroll
-    for (int r = 0; r < kWriteRows; ++r) v[r] = (i0 + r < M) ? __ldg(S + (size_t)(i0 + r) * N + j) : 0.0f;
-#pragma unroll
-    for (int r = 0; r < kWriteRows; ++r) {
-        const int i = i0 + r;
-        if (i < M) {
-            const float4 q = rs[i];
-            // (log_softmax over j) + (log_softmax over i) + (logsigmoid(z0) + logsigmoid(z1)), torch's association
-            const float s0 = __fsub_rn(__fsub_rn(v[r], q.x), q.y);
-            const float s1 = __fsub_rn(__fsub_rn(v[r], c.x), c.y);
-            O[(size_t)i * (N + 1) + j] = __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(q.z, c.z));
-        } else if (i == M) {
-            O[(size_t)i * (N + 1) + j] = c.w;  // unmatched row: logsigmoid(-z1)
-        }
-    }
+    if (i0 + kWriteRows <= M)
+        lds_write_tile<true>(p, rs, c, kWriteRows, N, o);
+    else
+        lds_write_tile<false>(p, rs, c, M - i0, N, o);
 }
 
 }  // namespace
@@ -176,17 +196,19 @@ extern "C" int einx_log_double_softmax(einx_ctx* ctx, const float* sim, const fl
     DeviceGuard guard(ctx->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int nrt = (M + kTileRows - 1) / kTileRows, nct = (N + kTileCols - 1) / kTileCols;
-    const int wrt = (M + 1 + kWriteRows - 1) / kWriteRows, wct = (N + 1 + 255) / 256;
+    const int wrt = (M + kWriteRows - 1) / kWriteRows, wct = (N + 255) / 256;
     if (nrt > 65535 || wrt > 65535) return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_log_double_softmax: M=%d too large", M);
-    // batch items per chunk: similarities of a chunk <= 32 MB, so that the write pass re-reads them from L2
-    // (EINX_LDS_CHUNK_MB overrides the 32 MB: a measurement knob, see tools/kbench.py next)
+    // One chunk = the whole batch by default.  EINX_LDS_CHUNK_MB (a measurement knob, tools/kbench.py next) walks the
+    // batch in chunks of that many MB of similarities so that the write pass re-reads them from L2; measured on B200
+    // (C2 shape, 64 x 1024 x 1024) the smaller launches cost more than the saved HBM read: 0.34 ms at 32 MB, 0.28 ms at
+    // 64 MB against 0.22 ms for the whole batch (0.26 / 0.23 against 0.19 ms with the
+    // final kernels).
     const size_t item = sizeof(float) * (size_t)M * N;
-    size_t budget = (size_t)32 << 20;
+    int chunk = B;
     if (const char* e = getenv("EINX_LDS_CHUNK_MB")) {
         const long mb = atol(e);
-        if (mb > 0) budget = (size_t)mb << 20;
+        if (mb > 0) chunk = (int)(((size_t)mb << 20) / item);
     }
-    int chunk = (int)(budget / item);
     chunk = chunk < 1 ? 1 : (chunk > B ? B : chunk);
     if (chunk > 65535) chunk = 65535;
     const size_t rowpart_b = align_up(sizeof(float2) * (size_t)chunk * nct * M, 256);
@@ -205,10 +227,11 @@ extern "C" int einx_log_double_softmax(einx_ctx* ctx, const float* sim, const fl
         const float* S = sim + (size_t)b0 * M * N;
         lds_stats_kernel<<<dim3(nct, nrt, nb), kThreads, 0, stream>>>(S, M, N, nrt, nct, rowpart, colpart);
         EINX_CHECK_LAUNCH(ctx);
-        lds_merge_kernel<<<dim3((M + N + 255) / 256, nb), 256, 0, stream>>>(rowpart, colpart, z0 + (size_t)b0 * M, z1 + (size_t)b0 * N,
-                                                                          M, N, nrt, nct, rowstat, colstat);
+        float* O = scores + (size_t)b0 * (M + 1) * ((size_t)N + 1);
+        lds_merge_kernel<<<dim3((M + N + 1 + 255) / 256, nb), 256, 0, stream>>>(rowpart, colpart, z0 + (size_t)b0 * M, z1 + (size_t)b0 * N,
+                                                                              M, N, nrt, nct, rowstat, colstat, O);
         EINX_CHECK_LAUNCH(ctx);
-        lds_write_kernel<<<dim3(wct, wrt, nb), 256, 0, stream>>>(S, rowstat, colstat, M, N, scores + (size_t)b0 * (M + 1) * ((size_t)N + 1));
+        lds_write_kernel<<<dim3(wct, wrt, nb), 256, 0, stream>>>(S, rowstat, colstat, M, N, O);
         EINX_CHECK_LAUNCH(ctx);
     }
     return EINX_OK;

@@ -141,11 +141,14 @@ def filter_matches(scores: torch.Tensor, th: float):
     return m0, m1, s0, s1
 
 
-@torch.no_grad()
 def sigmoid_log_double_softmax(sim: torch.Tensor, z0: torch.Tensor, z1: torch.Tensor) -> torch.Tensor:
     """Drop-in for ``core/modules/matchers/lightglue.py:365-377``: the (B, M+1, N+1) log-assignment matrix from
     similarities (B, M, N) and matchability logits z0 (B, M, 1), z1 (B, N, 1) (einx_log_double_softmax: row and
-    column log-sum-exp in one pass, the matrix written in a second pass out of L2).  Inference only (no autograd)."""
+    column log-sum-exp in one pass, the matrix written in a second pass).  Forward only: raises when a
+    gradient is required (LightGlue training keeps the reference's function)."""
+    if torch.is_grad_enabled() and (sim.requires_grad or z0.requires_grad or z1.requires_grad):
+        raise _lib.EinxError("sigmoid_log_double_softmax: forward only -- call it under torch.no_grad(), or keep the "
+                             "reference's function when training the matcher")
     for name, v in (("sim", sim), ("z0", z0), ("z1", z1)):
         if v.dtype != torch.float32 or not v.is_cuda:
             raise _lib.EinxError(f"sigmoid_log_double_softmax: {name} must be a float32 CUDA tensor (there is no CPU fallback)")

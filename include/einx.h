@@ -221,7 +221,7 @@ int einx_filter_matches(einx_ctx* ctx, const float* scores, int B, int M, int N,
  *   scores[b, i, N] = logsigmoid(-z0[b, i]);  scores[b, M, j] = logsigmoid(-z1[b, j]);  scores[b, M, N] = 0
  *   sim (B, M, N), z0 (B, M), z1 (B, N), scores (B, M+1, N+1), all fp32 and contiguous.
  * Row and column (max, log-sum-exp) statistics in one pass over sim, the matrix written in a second
- * pass served by L2 (the entry point walks the batch in chunks of <= 32 MB of similarities).
+ * pass (12 bytes of HBM traffic per element).
  * fp32 exp / log / summation order: agrees with torch to ~1e-6 of the magnitude, not bit-exact.
  */
 int einx_log_double_softmax(einx_ctx* ctx, const float* sim, const float* z0, const float* z1,

@@ -514,9 +514,12 @@ def _log_sigmoid(x):
 
 
 def _log_softmax(x, axis):
+    """(x - max) - log(sum exp(x - max)) in fp32; the sum of the fp32 exponentials is accumulated in fp64 and rounded
+    once (torch's vectorised fp32 sum is within an ulp of that; numpy's fp32 sum along a strided axis is sequential and
+    drifts by 3e-6 over 1000 terms)."""
     x = np.asarray(x, dtype=F32)
     s = x - x.max(axis=axis, keepdims=True)
-    return (s - np.log(np.exp(s).sum(axis=axis, keepdims=True, dtype=F32))).astype(F32)
+    return (s - np.log(np.exp(s).sum(axis=axis, keepdims=True, dtype=np.float64).astype(F32))).astype(F32)
 
 
 def sigmoid_log_double_softmax(sim, z0, z1):

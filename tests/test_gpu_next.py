@@ -173,7 +173,9 @@ def test_binned_representations_batch_vs_oracle(einx):
 
 
 # ------------------------------------------------------- sigmoid_log_double_softmax ---- #
-LDS_TOL = 2e-6  # of max(1, |ref|): fp32 exp / log / summation order (the oracle itself is within 4e-7 of torch)
+# of max(1, |ref|): fp32 exp / log / summation order.  Measured on B200 at the C2 size: 4.2e-7 against an fp64
+# evaluation, 6e-7 against torch's CPU result (which is itself 5.3e-7 from the fp64 one).
+LDS_TOL = 2e-6
 
 
 def test_log_double_softmax_golden(einx, golden):
@@ -191,8 +193,10 @@ def test_log_double_softmax_golden(einx, golden):
         np.testing.assert_allclose(s0.cpu().numpy(), g[f"c{ci}_s0"], rtol=1e-4, atol=1e-30)
 
 
-def test_log_double_softmax_config_size(einx):
-    """C2 keypoint count, several batch chunks (32 MB of similarities per chunk = 8 items), ragged last chunk."""
+@pytest.mark.parametrize("chunk_mb", ["", "32"])
+def test_log_double_softmax_config_size(einx, monkeypatch, chunk_mb):
+    """C2 keypoint count; EINX_LDS_CHUNK_MB=32 walks the batch in chunks of 8 items with a ragged last chunk."""
+    monkeypatch.setenv("EINX_LDS_CHUNK_MB", chunk_mb) if chunk_mb else monkeypatch.delenv("EINX_LDS_CHUNK_MB", raising=False)
     rng = np.random.default_rng(21)
     B, M, N = 19, 1024, 1000
     sim = (6.0 * rng.standard_normal((B, M, N))).astype(np.float32)
@@ -201,7 +205,9 @@ def test_log_double_softmax_config_size(einx):
     out = einx.sigmoid_log_double_softmax(cuda(sim), cuda(z0), cuda(z1)).cpu().numpy()
     for b in (0, 7, 8, 18):
         ref = O.sigmoid_log_double_softmax(sim[b:b + 1], z0[b:b + 1], z1[b:b + 1])
-        assert np.all(np.abs(out[b:b + 1] - ref) <= LDS_TOL * np.maximum(1.0, np.abs(ref))), b
+        err = np.abs(out[b:b + 1] - ref) / np.maximum(1.0, np.abs(ref))
+        print(f"log_double_softmax item {b}: max error {err.max():.3g} of max(1, |ref|)")
+        assert err.max() <= LDS_TOL, b
     # size-independent property: exp(row log-softmax) sums to one  <=>  logsumexp_j(scores - col terms) ...
     # checked in the simplest form: scores - certainties = row log-softmax + column log-softmax <= 0
     t = torch.from_numpy(out[:, :-1, :-1])
