@@ -163,3 +163,33 @@ def test_split_paths_at_c4_size(einx, synth, precision):
     keep = m0 > -1
     assert keep.sum() == (m1 > -1).sum() > 3000
     assert np.array_equal(m1[m0[keep]], np.nonzero(keep)[0])
+
+
+def test_c5_keypoint_extreme(einx, synth):
+    """BASELINE configs[4], top of the keypoint sweep: one pair with 16384 x 16384 keypoints (fp32-accurate default mode)."""
+    rng = np.random.default_rng(16384)
+    d0, d1 = synth.descriptor_pair(rng, 16384, 16384, 128, 1.41, dups=3)
+    out = einx.mnn(cuda(d0[None]), cuda(d1[None]), precision="fp16x3")
+    m0, m1 = out["matches0"][0].cpu().numpy(), out["matches1"][0].cpu().numpy()
+    check_against(m0, m1, d0, d1)
+    keep = m0 > -1
+    assert keep.sum() == (m1 > -1).sum() > 6000
+    assert np.array_equal(m1[m0[keep]], np.nonzero(keep)[0])
+
+
+@pytest.mark.parametrize("precision", ["fp16x3", "tf32x3", "bf16"])
+def test_c5_batch_extreme(einx, synth, precision):
+    """BASELINE configs[4], top of the batch sweep: 1024 pairs with 512 keypoints each; every 97th pair is checked
+    against the oracle, all of them for equal match counts on both sides."""
+    rng = np.random.default_rng(1024)
+    B, K, D = 1024, 512, 64
+    pairs = [synth.descriptor_pair(rng, K, K, D, 1.0) for _ in range(12)]
+    if precision == "bf16":  # the bf16 kernel is exact on bf16-representable inputs
+        pairs = [(bf16_round(a), bf16_round(b)) for a, b in pairs]
+    a = np.stack([pairs[i % 12][0] for i in range(B)])
+    b = np.stack([pairs[(i * 5 + i // 12) % 12][1] for i in range(B)])
+    out = einx.mnn(cuda(a), cuda(b), precision=precision)
+    g0, g1 = out["matches0"].cpu().numpy(), out["matches1"].cpu().numpy()
+    for i in range(0, B, 97):
+        check_against(g0[i], g1[i], a[i], b[i], min_stable=0.99)
+    assert ((g0 > -1).sum(1) == (g1 > -1).sum(1)).all()

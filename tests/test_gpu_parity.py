@@ -162,6 +162,7 @@ def test_detect_reference_property_tests(einx, golden):
 @pytest.mark.parametrize("B,Hp,Wp,k,kind", [(3, 184, 240, 1024, "uniform"), (5, 264, 352, 2048, "uniform"),
                                             (2, 260, 346, 2048, "ties"), (2, 184, 240, 300, "ties"),
                                             (1, 720, 1280, 8192, "uniform"), (1, 720, 1280, 512, "ties"),
+                                            (1, 720, 1280, 16384, "uniform"),  # top of the C5 keypoint sweep
                                             (150, 64, 96, 100, "uniform"), (2, 37, 1000, 64, "uniform")])
 def test_detect_vs_oracle_config_sizes(einx, synth, B, Hp, Wp, k, kind):
     rng = np.random.default_rng(Hp * 7 + k)
