@@ -472,7 +472,7 @@ def run_einx(args, synth):
         log("timing the CPU baseline (oracle port) ...")
         cores = os.cpu_count() or 1
         cpu_pairs = max(cores, min(2 * cores, 64))
-        cpu_val, cpu_cores, cpu_secs, cpu_done = (cpu_pairs_per_sec(synth, args.config, cpu_pairs) if world == 1
+        cpu_val, cpu_cores, cpu_secs, cpu_done = (cpu_pairs_per_sec(synth, args.config, cpu_pairs) if world == 1 and not args.skip_cpu
                                                   else (None, None, None, None))
         line = {
             "metric": "pairs/sec (voxel+detect+MNN)", "value": value, "unit": "pairs/s", "n_gpus": world,
@@ -508,6 +508,7 @@ def main():
                          "resident batch (eager issue costs ~250 us of host time per step against ~420 us of GPU time, "
                          "so a busy host CPU makes the eager arm host bound; the graph arm is one launch per step)")
     ap.add_argument("--batch", type=int, default=None, help="pairs per GPU per step")
+    ap.add_argument("--skip-cpu", action="store_true", help="profiling aid: skip the CPU baseline leg (12 s of host time under ncu)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling aid: skip the end-to-end arm (its sub-batch launches would mix into an ncu capture)")
     ap.add_argument("--precision", default=os.environ.get("EINX_MNN_PRECISION", "fp16x3"), choices=["fp32", "tf32x3", "fp16x3", "bf16"],
                     help="MNN arithmetic: fp16x3 (default) and tf32x3 are fp32-accurate 3-term splits on the tensor pipe (index parity with "
