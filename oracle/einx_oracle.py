@@ -531,7 +531,8 @@ def sigmoid_log_double_softmax(sim, z0, z1):
     z1 = np.asarray(z1, dtype=F32).reshape(b, n)
     cert = _log_sigmoid(z0)[:, :, None] + _log_sigmoid(z1)[:, None, :]
     out = np.zeros((b, m + 1, n + 1), dtype=F32)
-    out[:, :m, :n] = (_log_softmax(sim, 2) + _log_softmax(sim, 1)) + cert
+    if m and n:  # torch's log_softmax over an empty dimension returns an empty tensor; numpy's max raises
+        out[:, :m, :n] = (_log_softmax(sim, 2) + _log_softmax(sim, 1)) + cert
     out[:, :-1, -1] = _log_sigmoid(-z0)
     out[:, -1, :-1] = _log_sigmoid(-z1)
     return out

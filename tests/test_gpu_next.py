@@ -215,6 +215,19 @@ def test_log_double_softmax_config_size(einx, monkeypatch, chunk_mb):
     assert float((t - cert).max()) <= 1e-5
 
 
+@pytest.mark.parametrize("M,N", [(0, 5), (7, 0), (0, 0)])
+def test_log_double_softmax_empty_side(einx, M, N):
+    """No keypoints on one side: only the unmatched row / column exists (the reference's torch ops accept the shape)."""
+    rng = np.random.default_rng(M + 10 * N)
+    sim = np.zeros((2, M, N), np.float32)
+    z0 = rng.standard_normal((2, M, 1)).astype(np.float32)
+    z1 = rng.standard_normal((2, N, 1)).astype(np.float32)
+    out = einx.sigmoid_log_double_softmax(cuda(sim), cuda(z0), cuda(z1)).cpu().numpy()
+    ref = O.sigmoid_log_double_softmax(sim, z0, z1)
+    assert out.shape == ref.shape == (2, M + 1, N + 1)
+    np.testing.assert_allclose(out, ref, rtol=2e-6, atol=1e-7)
+
+
 def test_log_double_softmax_rejects_cpu(einx):
     with pytest.raises(einx.EinxError):
         einx.sigmoid_log_double_softmax(torch.zeros(1, 2, 2), torch.zeros(1, 2, 1), torch.zeros(1, 2, 1))
