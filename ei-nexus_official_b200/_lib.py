@@ -36,7 +36,8 @@ SIGNATURES = {
     "einx_mask_dilate": (C.c_int, [c_ctx, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "einx_logits_to_score": (C.c_int, [c_ctx, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "einx_filter_matches": (C.c_int, [c_ctx, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P, _P]),
-    "einx_log_double_softmax": (C.c_int, [c_ctx, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "einx_log_double_softmax": (C.c_int, [c_ctx, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "einx_filter_matches_keys": (C.c_int, [c_ctx, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

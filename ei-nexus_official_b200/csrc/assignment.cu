@@ -110,3 +110,20 @@ extern "C" int einx_filter_matches(einx_ctx* ctx, const float* scores, int B, in
     EINX_CHECK_LAUNCH(ctx);
     return EINX_OK;
 }
+
+// The same filter on keys that einx_log_double_softmax left while writing the matrix (no pass over the matrix).
+extern "C" int einx_filter_matches_keys(einx_ctx* ctx, const uint64_t* best_keys, int B, int M, int N, float th, int64_t* m0,
+                                        int64_t* m1, float* ms0, float* ms1, einx_stream stream_) {
+    if (!ctx) return EINX_ERR_INVALID;
+    if (B < 0 || M <= 0 || N <= 0) return einx_fail(ctx, EINX_ERR_INVALID, "einx_filter_matches_keys: bad shape B=%d M=%d N=%d", B, M, N);
+    if (B == 0) return EINX_OK;
+    if (!best_keys || !m0 || !m1 || !ms0 || !ms1) return einx_fail(ctx, EINX_ERR_INVALID, "einx_filter_matches_keys: NULL pointer argument");
+    if (B > 65535) return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_filter_matches_keys: B=%d > 65535", B);
+    DeviceGuard guard(ctx->device);
+    const unsigned long long* rowkey = (const unsigned long long*)best_keys;
+    const unsigned long long* colkey = rowkey + (size_t)B * M;
+    const int mx = M > N ? M : N;
+    assignment_filter_kernel<<<dim3((mx + 255) / 256, B), 256, 0, (cudaStream_t)stream_>>>(rowkey, colkey, M, N, th, m0, m1, ms0, ms1);
+    EINX_CHECK_LAUNCH(ctx);
+    return EINX_OK;
+}

@@ -144,32 +144,51 @@ lds_merge_kernel(const float2* __restrict__ rowpart, const float2* __restrict__ 
     }
 }
 
-// Rows per CTA of the write pass (= loads in flight per thread).  Measured on B200, C2 shape, whole entry point:
-// 4 rows 0.180 ms, 8 rows 0.170 ms, 16 rows 0.187 ms, 32 rows 0.204 ms; streaming (.cs) loads / stores change nothing.
+// Rows in flight per thread of the write pass.  Measured on B200, C2 shape, whole entry point: 4 rows 0.180 ms,
+// 8 rows 0.170 ms, 16 rows 0.187 ms, 32 rows 0.204 ms; streaming (.cs) loads / stores change nothing.
 constexpr int kWriteRows = 8;
+// Rows per CTA when the pass also reduces the row / column maxima (KEYS): taller tiles mean fewer 64-bit atomics per
+// column (M / 64) and per row (N / 256).
+constexpr int kKeyTileRows = 64;
 
-template <bool FULL>
-__device__ __forceinline__ void lds_write_tile(const float* __restrict__ p, const float4* __restrict__ rs, const float4 c, int rows,
-                                               int N, float* __restrict__ o) {
+// Interior of the matrix: thread = column, kWriteRows rows in flight.  KEYS: the values being written are also reduced
+// to (max, first index) per row and per column -- exactly what filter_matches (lightglue.py:402-418) would recompute
+// from the stored matrix -- as 64-bit (orderable value, ~index) keys, the format of the MNN matcher.
+template <bool KEYS, bool FULL>
+__device__ __forceinline__ void lds_write_rows(const float* __restrict__ p, const float4* __restrict__ rs, const float4 c, int rows,
+                                               int N, float* __restrict__ o, bool valid, int j, int row0, int ib,
+                                               unsigned long long* rowred, float& cb, int& ci) {
     float v[kWriteRows];
 #pragma unroll
     for (int r = 0; r < kWriteRows; ++r) v[r] = (FULL || r < rows) ? __ldg(p + (size_t)r * N) : 0.0f;
 #pragma unroll
     for (int r = 0; r < kWriteRows; ++r) {
-        if (FULL || r < rows) {
+        if (FULL || r < rows) {  // CTA-uniform
             const float4 q = rs[r];
             // (log_softmax over j) + (log_softmax over i) + (logsigmoid(z0) + logsigmoid(z1)), torch's association
             const float s0 = __fsub_rn(__fsub_rn(v[r], q.x), q.y);
             const float s1 = __fsub_rn(__fsub_rn(v[r], c.x), c.y);
-            o[(size_t)r * (N + 1)] = __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(q.z, c.z));
+            const float out = __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(q.z, c.z));
+            if (!KEYS || valid) o[(size_t)r * (N + 1)] = out;
+            if (KEYS) {
+                const uint32_t ord = valid ? f32_orderable(out + 0.0f) : 0u;
+                const uint32_t mx = __reduce_max_sync(0xffffffffu, ord);
+                const uint32_t eq = __ballot_sync(0xffffffffu, valid && ord == mx);
+                // (max, first column holding it) of this warp's 32 columns, merged over the CTA's warps in shared memory
+                // (keeping the keys in registers until the end of the tile was measured slower: 0.247 vs 0.222 ms)
+                if ((threadIdx.x & 31) == 0 && eq)
+                    atomicMax(&rowred[row0 + r],
+                              ((unsigned long long)mx << 32) | (unsigned long long)(0xffffffffu - (uint32_t)(j + __ffs(eq) - 1)));
+                if (out > cb) { cb = out; ci = ib + r; }  // rows ascend: strict > keeps the first
+            }
         }
     }
 }
 
-// interior of the matrix: thread = column, kWriteRows rows per CTA
+// interior of the matrix without the reductions: thread = column, one group of kWriteRows rows per CTA
 __global__ void __launch_bounds__(256)
-lds_write_kernel(const float* __restrict__ sim, const float4* __restrict__ rowstat, const float4* __restrict__ colstat, int M,
-                 int N, float* __restrict__ scores) {
+lds_write_plain_kernel(const float* __restrict__ sim, const float4* __restrict__ rowstat, const float4* __restrict__ colstat, int M,
+                       int N, float* __restrict__ scores) {
     const int b = blockIdx.z;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i0 = blockIdx.y * kWriteRows;
@@ -178,16 +197,55 @@ lds_write_kernel(const float* __restrict__ sim, const float4* __restrict__ rowst
     float* o = scores + ((size_t)b * (M + 1) + i0) * ((size_t)N + 1) + j;
     const float4* rs = rowstat + (size_t)b * M + i0;
     const float4 c = colstat[(size_t)b * N + j];
+    float cb = 0.0f;
+    int ci = 0;
     if (i0 + kWriteRows <= M)
-        lds_write_tile<true>(p, rs, c, kWriteRows, N, o);
+        lds_write_rows<false, true>(p, rs, c, kWriteRows, N, o, true, j, 0, i0, nullptr, cb, ci);
     else
-        lds_write_tile<false>(p, rs, c, M - i0, N, o);
+        lds_write_rows<false, false>(p, rs, c, M - i0, N, o, true, j, 0, i0, nullptr, cb, ci);
+}
+
+template <bool KEYS>
+__global__ void __launch_bounds__(256)
+lds_write_kernel(const float* __restrict__ sim, const float4* __restrict__ rowstat, const float4* __restrict__ colstat, int M,
+                 int N, float* __restrict__ scores, unsigned long long* __restrict__ rowkey, unsigned long long* __restrict__ colkey) {
+    constexpr int TILE = KEYS ? kKeyTileRows : kWriteRows;
+    const int b = blockIdx.z;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i0 = blockIdx.y * TILE;
+    const bool valid = j < N;
+    if (!KEYS && !valid) return;
+    __shared__ unsigned long long rowred[KEYS ? kKeyTileRows : 1];
+    if (KEYS) {
+        if (threadIdx.x < kKeyTileRows) rowred[threadIdx.x] = 0ull;
+        __syncthreads();
+    }
+    const int jc = valid ? j : N - 1;  // invalid lanes of a KEYS launch shadow the last column (never stored)
+    const float4 c = colstat[(size_t)b * N + jc];
+    float cb = -INFINITY;
+    int ci = 0;
+#pragma unroll 1
+    for (int ib = i0; ib < min(i0 + TILE, M); ib += kWriteRows) {
+        const float* p = sim + ((size_t)b * M + ib) * N + jc;
+        float* o = scores + ((size_t)b * (M + 1) + ib) * ((size_t)N + 1) + jc;
+        const float4* rs = rowstat + (size_t)b * M + ib;
+        if (ib + kWriteRows <= M)
+            lds_write_rows<KEYS, true>(p, rs, c, kWriteRows, N, o, valid, j, ib - i0, ib, rowred, cb, ci);
+        else
+            lds_write_rows<KEYS, false>(p, rs, c, M - ib, N, o, valid, j, ib - i0, ib, rowred, cb, ci);
+    }
+    if (KEYS) {
+        if (valid && cb > -INFINITY) atomicMax(colkey + (size_t)b * N + j, pack_best(cb, (uint32_t)ci));
+        __syncthreads();
+        if (threadIdx.x < kKeyTileRows && i0 + threadIdx.x < M && rowred[threadIdx.x])
+            atomicMax(rowkey + (size_t)b * M + i0 + threadIdx.x, rowred[threadIdx.x]);
+    }
 }
 
 }  // namespace
 
 extern "C" int einx_log_double_softmax(einx_ctx* ctx, const float* sim, const float* z0, const float* z1, int B, int M, int N,
-                                       float* scores, einx_stream stream_) {
+                                       float* scores, uint64_t* best_keys, einx_stream stream_) {
     if (!ctx) return EINX_ERR_INVALID;
     if (B < 0 || M <= 0 || N <= 0)
         return einx_fail(ctx, EINX_ERR_INVALID, "einx_log_double_softmax: bad shape B=%d M=%d N=%d", B, M, N);
@@ -196,7 +254,11 @@ extern "C" int einx_log_double_softmax(einx_ctx* ctx, const float* sim, const fl
     DeviceGuard guard(ctx->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int nrt = (M + kTileRows - 1) / kTileRows, nct = (N + kTileCols - 1) / kTileCols;
-    const int wrt = (M + kWriteRows - 1) / kWriteRows, wct = (N + 255) / 256;
+    const int wtile = best_keys ? kKeyTileRows : kWriteRows;
+    const int wrt = (M + wtile - 1) / wtile, wct = (N + 255) / 256;
+    unsigned long long* rowkey = (unsigned long long*)best_keys;
+    unsigned long long* colkey = rowkey ? rowkey + (size_t)B * M : nullptr;
+    if (best_keys) EINX_CUDA(ctx, cudaMemsetAsync(best_keys, 0, sizeof(uint64_t) * (size_t)B * ((size_t)M + N), stream));
     if (nrt > 65535 || wrt > 65535) return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_log_double_softmax: M=%d too large", M);
     // One chunk = the whole batch by default.  EINX_LDS_CHUNK_MB (a measurement knob, tools/kbench.py next) walks the
     // batch in chunks of that many MB of similarities so that the write pass re-reads them from L2; measured on B200
@@ -231,7 +293,11 @@ extern "C" int einx_log_double_softmax(einx_ctx* ctx, const float* sim, const fl
         lds_merge_kernel<<<dim3((M + N + 1 + 255) / 256, nb), 256, 0, stream>>>(rowpart, colpart, z0 + (size_t)b0 * M, z1 + (size_t)b0 * N,
                                                                               M, N, nrt, nct, rowstat, colstat, O);
         EINX_CHECK_LAUNCH(ctx);
-        lds_write_kernel<<<dim3(wct, wrt, nb), 256, 0, stream>>>(S, rowstat, colstat, M, N, O);
+        if (best_keys)
+            lds_write_kernel<true><<<dim3(wct, wrt, nb), 256, 0, stream>>>(S, rowstat, colstat, M, N, O, rowkey + (size_t)b0 * M,
+                                                                          colkey + (size_t)b0 * N);
+        else
+            lds_write_plain_kernel<<<dim3(wct, wrt, nb), 256, 0, stream>>>(S, rowstat, colstat, M, N, O);
         EINX_CHECK_LAUNCH(ctx);
     }
     return EINX_OK;

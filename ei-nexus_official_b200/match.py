@@ -127,6 +127,7 @@ def filter_matches(scores: torch.Tensor, th: float):
         raise _lib.EinxError("filter_matches: expected a float32 CUDA tensor (there is no CPU fallback)")
     if scores.dim() != 3:
         raise ValueError("filter_matches: expected (B, M+1, N+1)")
+    carried = getattr(scores, "_einx_best_keys", None)  # left by sigmoid_log_double_softmax on this very tensor
     scores = scores.contiguous()
     B, M, N = scores.shape[0], scores.shape[1] - 1, scores.shape[2] - 1
     dev = scores.device
@@ -135,17 +136,27 @@ def filter_matches(scores: torch.Tensor, th: float):
     m1 = torch.empty((B, N), dtype=torch.int64, device=dev)
     s0 = torch.empty((B, M), dtype=torch.float32, device=dev)
     s1 = torch.empty((B, N), dtype=torch.float32, device=dev)
+    if carried is not None and carried[1] == scores._version and carried[0].numel() == B * (M + N) and M > 0 and N > 0:
+        # the row / column maxima were reduced while the matrix was written and it has not been modified since
+        rc = ctx.lib.einx_filter_matches_keys(ctx.handle, _lib.ptr(carried[0]), B, M, N, float(th), _lib.ptr(m0), _lib.ptr(m1),
+                                              _lib.ptr(s0), _lib.ptr(s1), ctx.stream)
+        ctx.check(rc, "einx_filter_matches_keys")
+        return m0, m1, s0, s1
     rc = ctx.lib.einx_filter_matches(ctx.handle, _lib.ptr(scores), B, M, N, float(th), _lib.ptr(m0), _lib.ptr(m1),
                                      _lib.ptr(s0), _lib.ptr(s1), ctx.stream)
     ctx.check(rc, "einx_filter_matches")
     return m0, m1, s0, s1
 
 
-def sigmoid_log_double_softmax(sim: torch.Tensor, z0: torch.Tensor, z1: torch.Tensor) -> torch.Tensor:
+def sigmoid_log_double_softmax(sim: torch.Tensor, z0: torch.Tensor, z1: torch.Tensor, carry_best: bool = True) -> torch.Tensor:
     """Drop-in for ``core/modules/matchers/lightglue.py:365-377``: the (B, M+1, N+1) log-assignment matrix from
     similarities (B, M, N) and matchability logits z0 (B, M, 1), z1 (B, N, 1) (einx_log_double_softmax: row and
     column log-sum-exp in one pass, the matrix written in a second pass).  Forward only: raises when a
-    gradient is required (LightGlue training keeps the reference's function)."""
+    gradient is required (LightGlue training keeps the reference's function).
+
+    ``carry_best``: the write pass also reduces the row / column maxima of the values it stores and the returned
+    tensor carries them (``_einx_best_keys``); ``filter_matches`` called on that same, unmodified tensor -- what
+    LightGlue.forward does next (lightglue.py:393 -> :402) -- then skips its pass over the matrix."""
     if torch.is_grad_enabled() and (sim.requires_grad or z0.requires_grad or z1.requires_grad):
         raise _lib.EinxError("sigmoid_log_double_softmax: forward only -- call it under torch.no_grad(), or keep the "
                              "reference's function when training the matcher")
@@ -168,7 +179,10 @@ def sigmoid_log_double_softmax(sim: torch.Tensor, z0: torch.Tensor, z1: torch.Te
         return scores
     sim, z0, z1 = sim.contiguous(), z0.reshape(B, M).contiguous(), z1.reshape(B, N).contiguous()
     ctx = _lib.context_for(dev)
+    keys = torch.empty((B * (M + N),), dtype=torch.int64, device=dev) if carry_best else None
     rc = ctx.lib.einx_log_double_softmax(ctx.handle, _lib.ptr(sim), _lib.ptr(z0), _lib.ptr(z1), B, M, N, _lib.ptr(scores),
-                                         ctx.stream)
+                                         _lib.ptr(keys), ctx.stream)
     ctx.check(rc, "einx_log_double_softmax")
+    if carry_best:
+        scores._einx_best_keys = (keys, scores._version)
     return scores

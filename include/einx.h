@@ -223,9 +223,17 @@ int einx_filter_matches(einx_ctx* ctx, const float* scores, int B, int M, int N,
  * Row and column (max, log-sum-exp) statistics in one pass over sim, the matrix written in a second
  * pass (12 bytes of HBM traffic per element).
  * fp32 exp / log / summation order: agrees with torch to ~1e-6 of the magnitude, not bit-exact.
+ *   best_keys : optional (B*M + B*N) uint64, NULL to skip.  The write pass then also reduces the values it
+ *               stores to (max, first index) per row and per column of scores[:, :-1, :-1]: what
+ *               filter_matches (:402-418) would recompute from the matrix.  einx_filter_matches_keys()
+ *               turns them into matches without another pass over the matrix, with results identical
+ *               to einx_filter_matches() on `scores`.  Opaque layout: rows of all items, then columns.
  */
 int einx_log_double_softmax(einx_ctx* ctx, const float* sim, const float* z0, const float* z1,
-                            int B, int M, int N, float* scores, einx_stream stream);
+                            int B, int M, int N, float* scores, uint64_t* best_keys,
+                            einx_stream stream);
+int einx_filter_matches_keys(einx_ctx* ctx, const uint64_t* best_keys, int B, int M, int N, float th,
+                             int64_t* m0, int64_t* m1, float* ms0, float* ms1, einx_stream stream);
 
 /* Number of kernel launches issued through `ctx` so far (bench.py's gpu_launches). */
 int64_t einx_launch_count(const einx_ctx* ctx);

@@ -215,6 +215,37 @@ def test_log_double_softmax_config_size(einx, monkeypatch, chunk_mb):
     assert float((t - cert).max()) <= 1e-5
 
 
+@pytest.mark.parametrize("B,M,N", [(3, 70, 90), (2, 1024, 1000), (5, 129, 513), (1, 1, 1), (2, 64, 256), (1, 300, 31)])
+def test_filter_matches_on_carried_keys(einx, B, M, N):
+    """The maxima reduced while the matrix is written give exactly the matches of a separate pass over the stored
+    matrix (ties included: duplicated rows / columns), and the carried keys are dropped once the tensor is modified."""
+    rng = np.random.default_rng(B * 1000 + M + N)
+    sim = (3.0 * rng.standard_normal((B, M, N))).astype(np.float32)
+    if M > 12 and N > 8:
+        sim[:, :, 7] = sim[:, :, 3]
+        sim[:, 11, :] = sim[:, 2, :]
+    z0 = rng.standard_normal((B, M, 1)).astype(np.float32)
+    z1 = rng.standard_normal((B, N, 1)).astype(np.float32)
+    if M > 12 and N > 8:
+        z0[:, 11], z1[:, 7] = z0[:, 2], z1[:, 3]  # exact duplicates: identical scores, first index must win
+    carried = einx.sigmoid_log_double_softmax(cuda(sim), cuda(z0), cuda(z1))
+    plain = einx.sigmoid_log_double_softmax(cuda(sim), cuda(z0), cuda(z1), carry_best=False)
+    assert torch.equal(carried, plain) and hasattr(carried, "_einx_best_keys") and not hasattr(plain, "_einx_best_keys")
+    before = einx.launch_count(DEV)
+    fused = einx.filter_matches(carried, 0.1)
+    assert einx.launch_count(DEV) - before == 1  # only the filter kernel: no pass over the matrix
+    ref = einx.filter_matches(plain, 0.1)
+    for a, b in zip(fused, ref):
+        assert torch.equal(a, b)
+    o0, o1, _, _ = O.filter_matches(plain.cpu().numpy(), 0.1)
+    assert np.array_equal(fused[0].cpu().numpy(), o0) and np.array_equal(fused[1].cpu().numpy(), o1)
+    carried[:, 0, 0] += 100.0  # in-place edit: the carried keys are stale and must not be used
+    before = einx.launch_count(DEV)
+    edited = einx.filter_matches(carried, 0.1)
+    assert einx.launch_count(DEV) - before > 1
+    assert int(edited[0][0, 0]) == 0 and int(edited[1][0, 0]) == 0
+
+
 @pytest.mark.parametrize("M,N", [(0, 5), (7, 0), (0, 0)])
 def test_log_double_softmax_empty_side(einx, M, N):
     """No keypoints on one side: only the unmatched row / column exists (the reference's torch ops accept the shape)."""

@@ -87,6 +87,11 @@ def bench_next(args):
         print(f"sigmoid_log_double_softmax {B}x{K}x{K}, {mb + ' MB of similarities per chunk' if mb else 'whole batch per launch'}: "
               f"{ms:.4f} ms = {(2 * sim.numel() * 4 + sc.numel() * 4) / ms / 1e6:.0f} GB/s (sim read twice + matrix written once)", flush=True)
     os.environ.pop("EINX_LDS_CHUNK_MB")
+    ms = time_ms(lambda: einx.sigmoid_log_double_softmax(sim, z0, z1, carry_best=False))
+    print(f"  without the carried row / column maxima: {ms:.4f} ms", flush=True)
+    ms = time_ms(lambda: einx.filter_matches(einx.sigmoid_log_double_softmax(sim, z0, z1), 0.1))
+    ms2 = time_ms(lambda: einx.filter_matches(einx.sigmoid_log_double_softmax(sim, z0, z1, carry_best=False), 0.1))
+    print(f"  sigmoid_log_double_softmax + filter_matches: {ms:.4f} ms with carried maxima, {ms2:.4f} ms as two passes", flush=True)
     ref = lambda: (torch.log_softmax(sim, 2) + torch.log_softmax(sim, 1) + torch.nn.functional.logsigmoid(z0)
                    + torch.nn.functional.logsigmoid(z1).transpose(1, 2))
     ms = time_ms(ref)
