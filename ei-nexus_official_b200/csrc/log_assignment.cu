@@ -148,8 +148,9 @@ lds_merge_kernel(const float2* __restrict__ rowpart, const float2* __restrict__ 
 // 8 rows 0.170 ms, 16 rows 0.187 ms, 32 rows 0.204 ms; streaming (.cs) loads / stores change nothing.
 constexpr int kWriteRows = 8;
 // Rows per CTA when the pass also reduces the row / column maxima (KEYS): taller tiles mean fewer 64-bit atomics per
-// column (M / 64) and per row (N / 256).
-constexpr int kKeyTileRows = 64;
+// column (M / tile); measured flat on B200 (C2 shape, entry point: 16 and 32 rows 0.219 ms, 64 rows 0.224, 128 rows
+// 0.232, 256 rows 0.244).
+constexpr int kKeyTileRows = 32;
 
 // Interior of the matrix: thread = column, kWriteRows rows in flight.  KEYS: the values being written are also reduced
 // to (max, first index) per row and per column -- exactly what filter_matches (lightglue.py:402-418) would recompute
@@ -205,19 +206,19 @@ lds_write_plain_kernel(const float* __restrict__ sim, const float4* __restrict__
         lds_write_rows<false, false>(p, rs, c, M - i0, N, o, true, j, 0, i0, nullptr, cb, ci);
 }
 
-template <bool KEYS>
+template <bool KEYS, int KT = kKeyTileRows>
 __global__ void __launch_bounds__(256)
 lds_write_kernel(const float* __restrict__ sim, const float4* __restrict__ rowstat, const float4* __restrict__ colstat, int M,
                  int N, float* __restrict__ scores, unsigned long long* __restrict__ rowkey, unsigned long long* __restrict__ colkey) {
-    constexpr int TILE = KEYS ? kKeyTileRows : kWriteRows;
+    constexpr int TILE = KEYS ? KT : kWriteRows;
     const int b = blockIdx.z;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i0 = blockIdx.y * TILE;
     const bool valid = j < N;
     if (!KEYS && !valid) return;
-    __shared__ unsigned long long rowred[KEYS ? kKeyTileRows : 1];
+    __shared__ unsigned long long rowred[KEYS ? KT : 1];
     if (KEYS) {
-        if (threadIdx.x < kKeyTileRows) rowred[threadIdx.x] = 0ull;
+        if (threadIdx.x < KT) rowred[threadIdx.x] = 0ull;
         __syncthreads();
     }
     const int jc = valid ? j : N - 1;  // invalid lanes of a KEYS launch shadow the last column (never stored)
@@ -237,7 +238,7 @@ lds_write_kernel(const float* __restrict__ sim, const float4* __restrict__ rowst
     if (KEYS) {
         if (valid && cb > -INFINITY) atomicMax(colkey + (size_t)b * N + j, pack_best(cb, (uint32_t)ci));
         __syncthreads();
-        if (threadIdx.x < kKeyTileRows && i0 + threadIdx.x < M && rowred[threadIdx.x])
+        if (threadIdx.x < KT && i0 + threadIdx.x < M && rowred[threadIdx.x])
             atomicMax(rowkey + (size_t)b * M + i0 + threadIdx.x, rowred[threadIdx.x]);
     }
 }
