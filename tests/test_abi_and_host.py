@@ -144,10 +144,28 @@ def test_patch_reference_swaps_adjacent_rows(einx):
         setattr(fake, name, lambda *a, **k: None)
     lg = types.ModuleType("fake_ref.lightglue")
     lg.filter_matches = lambda *a, **k: None
+    lg.sigmoid_log_double_softmax = lambda *a, **k: None
     vis = types.ModuleType("fake_ref.visualize")
     vis.draw_events_accumulation_image = lambda *a, **k: None
     done = einx.patch_reference([fake, lg, vis])
     assert fake.logits_to_prob is einx.logits_to_prob and fake.depth_to_space is einx.depth_to_space
     assert lg.filter_matches is einx.filter_matches
+    assert lg.sigmoid_log_double_softmax is einx.sigmoid_log_double_softmax
     assert vis.draw_events_accumulation_image is einx.draw_events_accumulation_image
     assert set(done) == {"fake_ref.detector_util", "fake_ref.lightglue", "fake_ref.visualize"}
+
+
+def test_log_double_softmax_host_checks(einx):
+    """No CPU fallback, no silent loss of the autograd graph, shape errors before anything reaches the library."""
+    import torch
+
+    sim, z0, z1 = torch.zeros(1, 3, 2), torch.zeros(1, 3, 1), torch.zeros(1, 2, 1)
+    with pytest.raises(einx.EinxError, match="CUDA"):
+        einx.sigmoid_log_double_softmax(sim, z0, z1)
+    with pytest.raises(einx.EinxError, match="forward only"):
+        einx.sigmoid_log_double_softmax(sim.clone().requires_grad_(), z0, z1)
+    with torch.no_grad():  # under no_grad a leaf that requires grad is fine for the reference too: only the device check fires
+        with pytest.raises(einx.EinxError, match="CUDA"):
+            einx.sigmoid_log_double_softmax(sim.clone().requires_grad_(), z0, z1)
+    with pytest.raises(einx.EinxError):
+        einx.filter_matches(torch.zeros(1, 4, 3), 0.1)
