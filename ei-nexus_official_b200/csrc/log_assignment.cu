@@ -11,7 +11,8 @@
 //                           Partials (max, sum) go to the workspace: M/128 per column, N/256 per row.
 //   2. lds_merge_kernel   : folds the partials; leaves (max, log sum, logsigmoid(z)) per row / column and writes the
 //                           unmatched row / column, logsigmoid(-z), and the zero corner of the matrix.
-//   3. lds_write_kernel   : second read of sim, one coalesced write of the M x N interior of the matrix.
+//   3. lds_write_plain_kernel / lds_write_keys_kernel : second read of sim, one coalesced write of the M x N interior
+//                           of the matrix; the keys form also reduces what it writes for filter_matches.
 // HBM sees sim twice and scores once: 12 B per element (walking the batch in L2-sized chunks so that the second
 // read hits L2 was measured and lost to the smaller launches; see the entry point).
 #include <stdlib.h>
@@ -206,41 +207,36 @@ lds_write_plain_kernel(const float* __restrict__ sim, const float4* __restrict__
         lds_write_rows<false, false>(p, rs, c, M - i0, N, o, true, j, 0, i0, nullptr, cb, ci);
 }
 
-template <bool KEYS, int KT = kKeyTileRows>
+// interior of the matrix with the reductions: thread = column, kKeyTileRows rows per CTA in groups of kWriteRows
 __global__ void __launch_bounds__(256)
-lds_write_kernel(const float* __restrict__ sim, const float4* __restrict__ rowstat, const float4* __restrict__ colstat, int M,
-                 int N, float* __restrict__ scores, unsigned long long* __restrict__ rowkey, unsigned long long* __restrict__ colkey) {
-    constexpr int TILE = KEYS ? KT : kWriteRows;
+lds_write_keys_kernel(const float* __restrict__ sim, const float4* __restrict__ rowstat, const float4* __restrict__ colstat, int M,
+                      int N, float* __restrict__ scores, unsigned long long* __restrict__ rowkey,
+                      unsigned long long* __restrict__ colkey) {
     const int b = blockIdx.z;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i0 = blockIdx.y * TILE;
-    const bool valid = j < N;
-    if (!KEYS && !valid) return;
-    __shared__ unsigned long long rowred[KEYS ? KT : 1];
-    if (KEYS) {
-        if (threadIdx.x < KT) rowred[threadIdx.x] = 0ull;
-        __syncthreads();
-    }
-    const int jc = valid ? j : N - 1;  // invalid lanes of a KEYS launch shadow the last column (never stored)
+    const int i0 = blockIdx.y * kKeyTileRows;
+    const bool valid = j < N;  // invalid lanes stay for the warp collectives and the barriers
+    __shared__ unsigned long long rowred[kKeyTileRows];
+    if (threadIdx.x < kKeyTileRows) rowred[threadIdx.x] = 0ull;
+    __syncthreads();
+    const int jc = valid ? j : N - 1;  // invalid lanes shadow the last column (never stored, never reduced)
     const float4 c = colstat[(size_t)b * N + jc];
     float cb = -INFINITY;
     int ci = 0;
 #pragma unroll 1
-    for (int ib = i0; ib < min(i0 + TILE, M); ib += kWriteRows) {
+    for (int ib = i0; ib < min(i0 + kKeyTileRows, M); ib += kWriteRows) {
         const float* p = sim + ((size_t)b * M + ib) * N + jc;
         float* o = scores + ((size_t)b * (M + 1) + ib) * ((size_t)N + 1) + jc;
         const float4* rs = rowstat + (size_t)b * M + ib;
         if (ib + kWriteRows <= M)
-            lds_write_rows<KEYS, true>(p, rs, c, kWriteRows, N, o, valid, j, ib - i0, ib, rowred, cb, ci);
+            lds_write_rows<true, true>(p, rs, c, kWriteRows, N, o, valid, j, ib - i0, ib, rowred, cb, ci);
         else
-            lds_write_rows<KEYS, false>(p, rs, c, M - ib, N, o, valid, j, ib - i0, ib, rowred, cb, ci);
+            lds_write_rows<true, false>(p, rs, c, M - ib, N, o, valid, j, ib - i0, ib, rowred, cb, ci);
     }
-    if (KEYS) {
-        if (valid && cb > -INFINITY) atomicMax(colkey + (size_t)b * N + j, pack_best(cb, (uint32_t)ci));
-        __syncthreads();
-        if (threadIdx.x < KT && i0 + threadIdx.x < M && rowred[threadIdx.x])
-            atomicMax(rowkey + (size_t)b * M + i0 + threadIdx.x, rowred[threadIdx.x]);
-    }
+    if (valid && cb > -INFINITY) atomicMax(colkey + (size_t)b * N + j, pack_best(cb, (uint32_t)ci));
+    __syncthreads();
+    if (threadIdx.x < kKeyTileRows && i0 + threadIdx.x < M && rowred[threadIdx.x])
+        atomicMax(rowkey + (size_t)b * M + i0 + threadIdx.x, rowred[threadIdx.x]);
 }
 
 }  // namespace
@@ -295,8 +291,8 @@ extern "C" int einx_log_double_softmax(einx_ctx* ctx, const float* sim, const fl
                                                                               M, N, nrt, nct, rowstat, colstat, O);
         EINX_CHECK_LAUNCH(ctx);
         if (best_keys)
-            lds_write_kernel<true><<<dim3(wct, wrt, nb), 256, 0, stream>>>(S, rowstat, colstat, M, N, O, rowkey + (size_t)b0 * M,
-                                                                          colkey + (size_t)b0 * N);
+            lds_write_keys_kernel<<<dim3(wct, wrt, nb), 256, 0, stream>>>(S, rowstat, colstat, M, N, O, rowkey + (size_t)b0 * M,
+                                                                         colkey + (size_t)b0 * N);
         else
             lds_write_plain_kernel<<<dim3(wct, wrt, nb), 256, 0, stream>>>(S, rowstat, colstat, M, N, O);
         EINX_CHECK_LAUNCH(ctx);
