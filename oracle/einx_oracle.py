@@ -572,3 +572,46 @@ def events_to_time_surface(x, y, t, p, bins, H, W):
     for i, a, b in _bin_slices(tn, nb):
         out[2 * i + p0[a:b], y0[a:b], x0[a:b]] = tn[a:b]
     return out
+
+
+# OpenCV's 3x3 chamfer weights for DIST_L2 (axial, diagonal), as fp32
+_CHAMFER_A, _CHAMFER_B = np.float32(0.955), np.float32(1.3693)
+
+
+def chamfer_3x3(event_map):
+    """cv.distanceTransform(1 - event_map, cv.DIST_L2, 3): the 3x3 chamfer distance to the nearest event pixel.
+
+    The two-pass raster algorithm computes the shortest 8-connected path with weights (a, b); on an unobstructed grid
+    that is min over event pixels of  b * min(|dx|, |dy|) + a * (max(|dx|, |dy|) - min(|dx|, |dy|))  (b < 2a).  Evaluated
+    here in fp64 and rounded once.  OpenCV's result depends on its build: the IPP path accumulates fp32 weights along the
+    path (1 ulp on dense maps, 4.2e-7 relative at distances of tens of pixels: measured on opencv 4.13), the plain C path uses 16.16 fixed-point weights (2e-6
+    relative off).  A map without events yields FLT_MAX everywhere (opencv 4.13)."""
+    m = np.asarray(event_map) > 0
+    H, W = m.shape
+    if not m.any():
+        return np.full((H, W), np.finfo(np.float32).max, dtype=F32)
+    ys, xs = np.nonzero(m)
+    out = np.empty((H, W), dtype=F32)
+    a, b = float(_CHAMFER_A), float(_CHAMFER_B)
+    for y in range(H):  # row by row keeps the (W, n_events) temporaries small
+        dy = np.abs(y - ys)[None, :]
+        dx = np.abs(np.arange(W)[:, None] - xs[None, :])
+        mn, mx = np.minimum(dx, dy), np.maximum(dx, dy)
+        out[y] = (b * mn + a * (mx - mn)).min(axis=1).astype(F32)
+    return out
+
+
+def events_to_distance_map(x, y, t, p, bins, H, W):
+    """Per time bin, the chamfer distance of every pixel to the nearest event of the bin
+    (datasets/representations.py:215-248).  Bin i owns events with i/bins <= t <= (i + 1)/bins, both ends inclusive
+    (searchsorted 'left' ... 'right'); coordinates truncate like astype(int32); polarity is not used."""
+    tn = time_normalization(t)
+    x0, y0 = np.asarray(x).astype(np.int32), np.asarray(y).astype(np.int32)
+    ct = 1 / bins
+    out = np.zeros((bins, H, W), dtype=F32)
+    for i in range(bins):
+        a_, b_ = np.searchsorted(tn, i * ct, side="left"), np.searchsorted(tn, (i + 1) * ct, side="right")
+        em = np.zeros((H, W), dtype=np.uint8)
+        em[y0[a_:b_], x0[a_:b_]] = 1
+        out[i] = chamfer_3x3(em)
+    return out

@@ -19,6 +19,7 @@ def main():
     rng = np.random.default_rng(20241019)
     g = {}
     cases = [("ec", 4000, 6, 30, 40), ("ec", 600, 4, 12, 16), ("mvsec01", 3000, 10, 36, 52), ("ec", 50, 2, 8, 8)]
+    # (the distance-map fixture of case 3 has sparse bins: distances of tens of pixels)
     for ci, (style, n, bins, H, W) in enumerate(cases):
         ev = synth_events(rng, n, H, W, "ec" if style == "ec" else "mvsec", dt=0.04)
         if style == "mvsec01":
@@ -34,6 +35,15 @@ def main():
         g[f"c{ci}_shape"] = np.array([bins, H, W])
         g[f"c{ci}_stack"] = rep.events_to_event_stack({k: v.copy() for k, v in ev.items()}, (bins, H, W)).numpy()
         g[f"c{ci}_surface"] = rep.events_to_time_surface({k: v.copy() for k, v in ev.items()}, (bins, H, W)).numpy()
+        # events_to_distance_map (:215-248; cv.distanceTransform of this container's opencv, an IPP build)
+        g[f"c{ci}_distance"] = rep.events_to_distance_map({k: v.copy() for k, v in ev.items()}, (bins, H, W)).numpy()
+    # distance map only: a sparse window -- distances of tens of pixels and bins without any event (FLT_MAX everywhere)
+    ev = synth_events(rng, 24, 40, 56, "ec", dt=0.04)
+    ev["t"][8:] += 0.02  # a gap in time: the middle bins stay empty
+    for k in "xytp":
+        g[f"sparse_{k}"] = ev[k]
+    g["sparse_shape"] = np.array([8, 40, 56])
+    g["sparse_distance"] = rep.events_to_distance_map({k: v.copy() for k, v in ev.items()}, (8, 40, 56)).numpy()
     g["ncases"] = np.array(len(cases))
     np.savez_compressed(f"{OUT}/repr.npz", **g)
     print("repr", os.path.getsize(f"{OUT}/repr.npz") // 1024, "KiB")

@@ -54,3 +54,20 @@ def test_log_double_softmax_matches_reference(golden):
         # the reference's own filter_matches output on its own matrix is reproduced from the oracle's matrix
         m0, m1, s0, s1 = O.filter_matches(ref, float(g[f"c{ci}_th"]))
         assert np.array_equal(m0, g[f"c{ci}_m0"]) and np.array_equal(m1, g[f"c{ci}_m1"])
+
+
+def test_distance_map_matches_reference(golden):
+    """events_to_distance_map (representations.py:215-248): the oracle's closed-form chamfer distance against the
+    reference's cv.distanceTransform output.  The IPP build of opencv 4.13 accumulates the fp32 weights along the path:
+    1 ulp on dense windows, 4.2e-7 relative at distances of tens of pixels; bar 1e-6 (the plain C build of OpenCV, with
+    16.16 fixed-point weights, is 2e-6 from either)."""
+    g = golden["repr"]
+    cases = [(f"c{ci}", ) for ci in range(int(g["ncases"]))] + [("sparse",)]
+    for (key,) in cases:
+        bins, H, W = (int(v) for v in g[f"{key}_shape"])
+        out = O.events_to_distance_map(*[g[f"{key}_{k}"] for k in "xytp"], bins, H, W)
+        ref = g[f"{key}_distance"]
+        empty = ref > 1e30  # bins without events: FLT_MAX everywhere
+        assert np.array_equal(out > 1e30, empty)
+        np.testing.assert_allclose(out[~empty], ref[~empty], rtol=1e-6, atol=0)
+    assert (g["sparse_distance"] > 1e30).any() and g["sparse_distance"][g["sparse_distance"] < 1e30].max() > 20
