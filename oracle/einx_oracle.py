@@ -615,3 +615,41 @@ def events_to_distance_map(x, y, t, p, bins, H, W):
         em[y0[a_:b_], x0[a_:b_]] = 1
         out[i] = chamfer_3x3(em)
     return out
+
+
+def _warp_points(pts, hom):
+    """core/metrics/util.py:5-39: (2, n) points through a 3 x 3 homography, fp32."""
+    h = np.asarray(hom, dtype=F32)
+    p = np.vstack([np.asarray(pts, dtype=F32)[:2], np.ones((1, pts.shape[1]), dtype=F32)])
+    q = (h @ p).astype(F32)
+    return np.vstack([q[0] / q[2], q[1] / q[2]]).astype(F32)
+
+
+def _keep_true_points(pts, hom, shape):
+    """core/metrics/util.py:43-104: keep the points whose warp lands inside (H, W)."""
+    w = _warp_points(pts, hom)
+    mask = (w[0] >= 0) & (w[0] < shape[1]) & (w[1] >= 0) & (w[1] < shape[0])
+    return pts[:, mask]
+
+
+def repeatability(points1, points2, img1_shape, img2_shape, homography, distance_thresh=3, ordering="xy"):
+    """Repeatability.update_one (core/metrics/keypoints_metrics.py:57-128).  points (N, >=2) rows in `ordering`; returns
+    (value or None, min over side 1 per side-2 point, min over side 2 per warped side-1 point): the N x M Euclidean
+    distance matrix of :110-113 reduced along both axes, counts of minima <= threshold over the number of points."""
+    sel = [0, 1] if ordering == "xy" else [1, 0]
+    q1 = np.asarray(points1, dtype=F32).T[sel]
+    q2 = np.asarray(points2, dtype=F32).T[sel]
+    h = np.asarray(homography, dtype=F32)
+    q2 = _keep_true_points(q2, np.linalg.inv(h).astype(F32), img1_shape)
+    q1 = _keep_true_points(q1, h, img2_shape)
+    wp = _warp_points(q1, h).T
+    q2 = q2.T
+    n, m = wp.shape[0], q2.shape[0]
+    d = wp[:, None, :] - q2[None, :, :]
+    norm = np.sqrt((d.astype(np.float64) ** 2).sum(-1)).astype(F32)  # torch's CPU norm accumulates in fp64
+    min1 = norm.min(0) if n else np.zeros(0, F32)
+    min2 = norm.min(1) if m else np.zeros(0, F32)
+    c1 = int((min1 <= distance_thresh).sum()) if n else 0
+    c2 = int((min2 <= distance_thresh).sum()) if m else 0
+    value = (c1 + c2) / (n + m) if n + m > 0 else None
+    return value, min1, min2

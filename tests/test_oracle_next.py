@@ -71,3 +71,20 @@ def test_distance_map_matches_reference(golden):
         assert np.array_equal(out > 1e30, empty)
         np.testing.assert_allclose(out[~empty], ref[~empty], rtol=1e-6, atol=0)
     assert (g["sparse_distance"] > 1e30).any() and g["sparse_distance"][g["sparse_distance"] < 1e30].max() > 20
+
+
+def test_repeatability_matches_reference(golden):
+    """Repeatability.update_one (keypoints_metrics.py:57-128): the value exactly (counts over counts), the two min
+    reductions of the N x M distance matrix within fp32 rounding of the homography warp."""
+    g = golden["metrics"]
+    for ci in range(int(g["ncases"])):
+        H, W, thr, xy = (int(v) for v in g[f"c{ci}_cfg"])
+        value, min1, min2 = O.repeatability(g[f"c{ci}_p1"], g[f"c{ci}_p2"], (H, W), (H, W), g[f"c{ci}_hom"], thr, "xy" if xy else "yx")
+        ref = float(g[f"c{ci}_value"])
+        if np.isnan(ref):  # no point on either side: the reference reports nothing
+            assert value is None
+        else:
+            assert np.float32(value) == np.float32(ref), ci  # the reference divides fp32 count tensors
+        assert min1.shape == g[f"c{ci}_min_over_1"].shape and min2.shape == g[f"c{ci}_min_over_2"].shape
+        np.testing.assert_allclose(min1, g[f"c{ci}_min_over_1"], rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(min2, g[f"c{ci}_min_over_2"], rtol=1e-5, atol=1e-4)
