@@ -1,84 +1,110 @@
 // Detection post-processing: border removal -> iterative NMS fixpoint -> top-k threshold ->
 // raster-ordered keypoint rows.  Semantics: reference core/modules/utils/detector_util.py:80-135,
-// :138-164, :243-337, :451-484 (see include/einx.h); bit-exact for non-negative maps.
+// :138-164, :243-337, :451-484 (see include/einx.h); bit-exact for non-negative, NaN-free maps.
 //
-// One thread-block CLUSTER per image.  Each CTA owns a band of rows of the score map in shared
-// memory (with an R-row halo refreshed from the neighbouring CTAs' shared memory over DSMEM every
-// round), so an NMS round never touches HBM: the map is read once and the keypoints written once.
+// One image per CTA (or per thread-block CLUSTER of row bands when the map does not fit one CTA's
+// shared memory); the map is read from HBM once, lives in shared memory through all rounds, and the
+// keypoints are written once.
 //
-// A round (detector_util.py:286-335 restated):
-//   lm(p)  = v(p) > 0  and  v(p) >= every window value  and  no equal value earlier in raster order
-//   v(p)   = 0 for every p that has a local maximum in its window and is not one itself
-// Local maxima are monotone (values only decrease), and an undecided pixel (positive, not a maximum,
-// not suppressed) has no maximum in its window, so only the undecided pixels matter after a round.
-// Dense rounds are separable: pass A takes the horizontal window maximum of 4 pixels per thread from
-// float4 loads, pass B the vertical one of 8 rows per thread and decides the pixel; suppression is a
-// dilation of the maxima bitmap on 32-bit words.  As soon as the undecided pixels of a band fit the
-// worklist (i.i.d. maps: 21 % undecided after round 0, 4 % after round 1, 0.4 %, ...), rounds visit those
-// pixels only.  The worklists live in the shared-memory rows of the horizontal maxima, which are dead
-// outside the dense passes, so a round writes nothing to global memory and the cluster barriers have
-// no stores to drain.  (Measured and rejected: following only the still-positive neighbours through a
-// bitmap in worklist rounds -- the dependent bit-scan/load chains cost 4x the 81 independent loads.)
-// The loop ends when no pixel of the image is undecided -- the same fixpoint the reference reaches
-// when its batch-wide count of maxima stops changing.
+// The fixpoint of detector_util.py:286-335 is greedy NMS in (value desc,
+// raster asc) order, so the rounds only have to respect two facts: a pixel that is the first-occurrence
+// maximum of its CURRENT window is selected for good, and everything else in that window is dead for
+// good.  State per pixel: V (value; zeroed once dead, in dense rounds), LM (selected), UB (undecided =
+// positive, not selected, no selected pixel in its window).
+//
+//   dense round   one sweep per thread over 4 columns x a run of rows: the horizontal window maxima of a
+//                 row come from three float4 loads, the vertical ones from a register ring of 3-row
+//                 partial maxima (9 = 3 x 3 rows), ~9 instructions per pixel, no second plane in shared
+//                 memory.  A pixel equal to its window maximum (rare) takes the slow path: exact
+//                 first-occurrence test, LM bit, entry in the list of new maxima.  Then every new maximum
+//                 zeroes its window in V and clears it in UB (a scatter over list x window rows); the
+//                 count of undecided pixels is kept exact from the bits those atomics actually cleared.
+//   sparse round  once the undecided pixels fit the worklist: per undecided pixel, look only at the
+//                 undecided neighbours (UB bits of the 2R+1 window rows; selected pixels can not be in
+//                 the window of an undecided one), then clear the windows of the new maxima in UB.  V is
+//                 no longer touched.
+//
+// The loop ends when no pixel is undecided -- the same fixpoint the reference reaches when its
+// batch-wide count of maxima stops changing.  Bands of a cluster keep R-row copies of their neighbours'
+// edge rows; every write goes to all copies (distributed shared memory), so there is no halo refresh.
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
+#include "detect_common.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int kThreads = 1024;
+constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxCluster = 8;
-constexpr int kWorklistCap = 4096;  // late NMS rounds visit only the still-undecided pixels (per CTA)
 
-struct DetectParams {
+struct NmsParams {
     float* score;
     const uint8_t* mask;
     float* nms_map;
     float* kpts;
     int32_t* counts;
     int B, Hp, Wp, border, kcap;
-    int CS;      // CTAs per image (cluster size)
-    int S;       // 32-column strips per row
-    int WS;      // padded row stride of V in floats: 32*S + 2*PAD
-    int RBmax;   // max own rows of a band
-    int vec4;    // rows of `score` (and `mask`) can be moved as float4 (uchar4)
-    int wl_smem; // worklists alias the shared-memory row maxima (bands large enough to host them)
-    unsigned magic_s, magic_ch;  // ceil(2^32 / S), ceil(2^32 / (8*S)): t / S == umulhi(t, magic_s) for t < 2^20
+    int T;        // CTAs (row bands) per image
+    int W4;       // float4 column groups per row: ceil(Wp / 4)
+    int NCW;      // warps across a row: ceil(W4 / 32)
+    int WS;       // row pitch of V in floats: 4 * W4 + 2 * PAD
+    int SB;       // row pitch of the bitmaps in words: 4 * NCW + 2 (one zero word on either side)
+    int RB;       // rows of the largest band
+    int NSEG, SR; // a band is swept as NSEG runs of SR rows per column warp
+    int LC;       // entries of the list buffer (new maxima of a dense round / two worklist halves)
+    int vec;      // pixels per global access: 4, 2 or 1 (row alignment of `score`)
+    int tail_smem;  // the survivor lists of the tail fit the shared-memory scratch (single-CTA images)
     float prob_thresh;
-    int use_topk;  // 1: threshold from order statistics rank_lo / rank_hi; 2: top_k >= n (thr_k = 0)
+    int use_topk;   // 1: threshold from order statistics rank_lo / rank_hi; 2: top_k >= n (thr_k = 0)
     int rank_lo, rank_hi;
-    int scap;  // survivor list capacity per image
+    int scap;       // survivor list capacity per image
     float* surv_val;
     int32_t* surv_idx;
-    unsigned int* worklists;  // [B * CS][2][kWorklistCap] entries (local row << 16 | x), L2-resident
-    // global-memory variant (maps too large for a cluster's shared memory)
-    float* gV;
-    float* gH;
-    uint32_t* gLM;
-    uint32_t* gRD;
-    uint32_t* gPS;
     long long* trace;  // developer aid (EINX_DETECT_TRACE=1): clock64() at phase boundaries of CTA 0
 };
 
-#define EINX_TRACE(slot)                                                          \
-    do {                                                                          \
-        if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && (slot) < 128) P.trace[(slot)] = clock64(); \
+#define EINX_TRACE(slot)                                                                                  \
+    do {                                                                                                  \
+        if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && (slot) < 126) P.trace[(slot)] = clock64(); \
     } while (0)
 
 struct Shared {
-    int flags[2];
+    int und;        // undecided pixels in own rows, exact
+    int n_new[2];   // new maxima appended by the dense pass of round k -> n_new[k & 1]
+    int wl_n[2];    // worklist lengths (two halves of the list buffer)
     int xcnt[2];
     int warp_scan[kWarps + 1];
     unsigned int hist[256];
     unsigned int sel_prefix, sel_rank, sel_min, sel_cnt;
-    float thr;
-    int wl_n[2];  // undecided pixels found by the last suppression pass (list valid while <= kWorklistCap)
 };
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }  // one FMNMX3
+
+// shared-memory loads from a 32-bit shared-window address: one register + immediate per access in the sweep
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
 
 __device__ __forceinline__ int block_excl_scan(int v, int* scratch, int& total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -92,14 +118,14 @@ __device__ __forceinline__ int block_excl_scan(int v, int* scratch, int& total) 
     if (lane == 31) scratch[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-        int w = scratch[lane];
+        int w = lane < kWarps ? scratch[lane] : 0;
         int winc = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             int n = __shfl_up_sync(0xffffffffu, winc, o);
             if (lane >= o) winc += n;
         }
-        scratch[lane] = winc - w;
+        if (lane < kWarps) scratch[lane] = winc - w;
         if (lane == 31) scratch[kWarps] = winc;
     }
     __syncthreads();
@@ -109,17 +135,21 @@ __device__ __forceinline__ int block_excl_scan(int v, int* scratch, int& total) 
 
 // j-th smallest (0-based) of the positive floats in list[0..n) via 4 radix passes on their bit
 // patterns, then the next order statistic; every thread returns the same (a, b).
-__device__ void select_two(const float* __restrict__ list, int n, int j, bool need_next, Shared& sh, float& a_out,
-                           float& b_out) {
+template <bool GLOBAL>
+__device__ __forceinline__ float list_ld(const float* list, int i) {
+    return GLOBAL ? __ldcg(list + i) : list[i];  // global lists are written by other CTAs of the cluster: L2 only
+}
+
+template <bool GLOBAL>
+__device__ void select_two(const float* list, int n, int j, bool need_next, Shared& sh, float& a_out, float& b_out) {
     if (threadIdx.x == 0) { sh.sel_prefix = 0; sh.sel_rank = (unsigned)j; }
-    // the usual list (a few thousand survivors) is read from L2 once and kept in registers
-    constexpr int kHeld = 4;
+    constexpr int kHeld = 8;  // the usual list (a few thousand survivors) is read once and kept in registers
     const bool held = n <= kHeld * kThreads;
     unsigned ev[kHeld];
 #pragma unroll
     for (int u = 0; u < kHeld; ++u) {
         const int i = threadIdx.x + u * kThreads;
-        ev[u] = (held && i < n) ? __float_as_uint(__ldcg(list + i)) : 0u;
+        ev[u] = (held && i < n) ? __float_as_uint(list_ld<GLOBAL>(list, i)) : 0u;
     }
     unsigned mask = 0;
     for (int shift = 24; shift >= 0; shift -= 8) {
@@ -128,11 +158,16 @@ __device__ void select_two(const float* __restrict__ list, int n, int j, bool ne
         const unsigned prefix = sh.sel_prefix;
         if (held) {
 #pragma unroll
-            for (int u = 0; u < kHeld; ++u)
-                if (threadIdx.x + u * kThreads < n && (ev[u] & mask) == prefix) atomicAdd(&sh.hist[(ev[u] >> shift) & 255u], 1u);
+            for (int u = 0; u < kHeld; ++u) {
+                const bool in = threadIdx.x + u * kThreads < n && (ev[u] & mask) == prefix;
+                // warp-aggregate equal digits (score values share their exponent byte): one atomic per distinct digit
+                const unsigned digit = (ev[u] >> shift) & 255u;
+                const unsigned peers = __match_any_sync(0xffffffffu, in ? digit : 0x100u);
+                if (in && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sh.hist[digit], (unsigned)__popc(peers));
+            }
         } else {
             for (int i = threadIdx.x; i < n; i += kThreads) {
-                const unsigned e = __float_as_uint(__ldcg(list + i));
+                const unsigned e = __float_as_uint(list_ld<GLOBAL>(list, i));
                 if ((e & mask) == prefix) atomicAdd(&sh.hist[(e >> shift) & 255u], 1u);
             }
         }
@@ -146,8 +181,8 @@ __device__ void select_two(const float* __restrict__ list, int n, int j, bool ne
             unsigned inc = mine;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const unsigned n = __shfl_up_sync(0xffffffffu, inc, o);
-                if ((int)threadIdx.x >= o) inc += n;
+                const unsigned nn = __shfl_up_sync(0xffffffffu, inc, o);
+                if ((int)threadIdx.x >= o) inc += nn;
             }
             const unsigned before = inc - mine;
             const bool here = (before <= r) && (r < inc);  // exactly one lane (r < total count)
@@ -181,7 +216,7 @@ __device__ void select_two(const float* __restrict__ list, int n, int j, bool ne
                 }
         } else {
             for (int i = threadIdx.x; i < n; i += kThreads) {
-                const unsigned e = __float_as_uint(__ldcg(list + i));
+                const unsigned e = __float_as_uint(list_ld<GLOBAL>(list, i));
                 if (e <= abits) cnt++;
                 else mn = min(mn, e);
             }
@@ -202,15 +237,16 @@ __device__ void select_two(const float* __restrict__ list, int n, int j, bool ne
 }
 
 // PAD columns of zeros on both sides of a band row; a multiple of 4 so that pixel 0 of every row is
-// 16-byte aligned and the passes below can move float4.
+// 16-byte aligned and the sweep can move float4.
 template <int R>
 struct Geo {
     static constexpr int PAD = (R + 3) / 4 * 4;
+    static constexpr int P2 = 2 * R + 1;
 };
 
 // Horizontal window maxima of 4 neighbouring pixels.  a[] holds the 4 + 2*PAD values starting PAD
 // to the left of the first pixel; o[i] = max a[PAD+i-R .. PAD+i+R].  The values shared by all four
-// windows are reduced once, then extended left / right: 2R+7 max operations for 4 outputs.
+// windows are reduced once, then extended left / right.
 template <int R>
 __device__ __forceinline__ void hmax4(const float* a, float (&o)[4]) {
     constexpr int PAD = Geo<R>::PAD;
@@ -221,446 +257,537 @@ __device__ __forceinline__ void hmax4(const float* a, float (&o)[4]) {
         const float l1 = a[PAD + 2 - R], l2 = fmaxf(a[PAD + 1 - R], l1), l3 = fmaxf(a[PAD - R], l2);
         const float r1 = a[PAD + R + 1], r2 = fmaxf(r1, a[PAD + R + 2]), r3 = fmaxf(r2, a[PAD + R + 3]);
         o[0] = fmaxf(common, l3);
-        o[1] = fmaxf(fmaxf(common, l2), r1);
-        o[2] = fmaxf(fmaxf(common, l1), r2);
+        o[1] = fmax3(common, l2, r1);
+        o[2] = fmax3(common, l1, r2);
         o[3] = fmaxf(common, r3);
     } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             float m = a[PAD + i];
 #pragma unroll
-            for (int d = 1; d <= R; ++d) m = fmaxf(m, fmaxf(a[PAD + i - d], a[PAD + i + d]));
+            for (int d = 1; d <= R; ++d) m = fmax3(m, a[PAD + i - d], a[PAD + i + d]);
             o[i] = m;
         }
     }
 }
 
-// Vertical window maxima of 8 consecutive rows from the 8 + 2R row maxima a[] above/below them:
-// o[i] = max a[i .. i+2R].  For 2R >= 8 every window straddles the 7|8 boundary, so a suffix scan of
-// a[0..7] and a prefix scan of a[8..] give all eight with 2R+14 operations.
-template <int R>
-__device__ __forceinline__ void vmax8(const float* a, float (&o)[8]) {
-    if constexpr (R >= 4) {
-        float suf[8];
-        suf[7] = a[7];
-#pragma unroll
-        for (int i = 6; i >= 0; --i) suf[i] = fmaxf(a[i], suf[i + 1]);
-        float pre = a[8];
-#pragma unroll
-        for (int k = 9; k <= 2 * R; ++k) pre = fmaxf(pre, a[k]);
-        o[0] = fmaxf(suf[0], pre);
-#pragma unroll
-        for (int i = 1; i < 8; ++i) {
-            pre = fmaxf(pre, a[i + 2 * R]);
-            o[i] = fmaxf(suf[i], pre);
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float m = a[i];
-#pragma unroll
-            for (int k = 1; k <= 2 * R; ++k) m = fmaxf(m, a[i + k]);
-            o[i] = m;
-        }
-    }
-}
+// The copies of band-local row l (image row ys - R + l) that live in the neighbouring bands of the cluster.
+struct Copies {
+    int rank, T, nrows, nprev;
+    // local row index of the same image row in the band above / below, or -1 when that band holds no copy
+    __device__ __forceinline__ int up(int l, int R2) const { return (rank > 0 && l < R2) ? l + nprev : -1; }
+    __device__ __forceinline__ int down(int l) const { return (rank < T - 1 && l >= nrows) ? l - nrows : -1; }
+};
 
-template <int R, bool SMEM>
-// 48 registers (no spills) instead of the 64 a 1024-thread launch bound allows: the CTA then leaves a quarter of the
-// register file free, so CTAs of the concurrent voxel kernels can share its SM and use the issue slots the NMS
-// rounds leave idle (the step runs voxelisation and both detect chains on three streams)
-__global__ void __maxnreg__(48) detect_kernel(const DetectParams P) {
+template <int R, bool MULTI>
+__global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
     constexpr int PAD = Geo<R>::PAD;
+    constexpr int P2 = Geo<R>::P2;
+    constexpr unsigned kWinMask = (1u << P2) - 1u;
     cg::cluster_group cluster = cg::this_cluster();
-    const int rank = (int)cluster.block_rank();
-    const int CS = P.CS;
-    const int b = blockIdx.x / CS;
+    const int T = MULTI ? P.T : 1;
+    const int rank = MULTI ? (int)cluster.block_rank() : 0;
+    const int b = blockIdx.x / T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int S = P.S, WS = P.WS, HS = 32 * P.S, Hp = P.Hp, Wp = P.Wp;
+    const int WS = P.WS, SB = P.SB, Hp = P.Hp, Wp = P.Wp, W4 = P.W4, NCW = P.NCW;
 
     // balanced row bands
-    const int base_rows = Hp / CS, rem = Hp % CS;
+    const int base_rows = Hp / T, rem = Hp % T;
     const int nrows = base_rows + (rank < rem ? 1 : 0);
     const int ys = rank * base_rows + min(rank, rem);
-    const int nprev = base_rows + ((rank - 1) < rem ? 1 : 0);  // rows of the band above
+    Copies cp;
+    cp.rank = rank; cp.T = T; cp.nrows = nrows;
+    cp.nprev = base_rows + ((rank - 1) < rem ? 1 : 0);  // rows of the band above
+    const int L = nrows + 2 * R;                        // local rows: R halo + own + R halo
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
-    // Local row lr of every array is image row ys - R + lr: own rows are lr in [R, R + nrows), the R
-    // rows on either side are the halo (copies of the neighbouring bands in the shared-memory
-    // variant; simply the neighbours' rows of the same padded image in the global variant).
-    float *V, *Hm;
-    uint32_t *LM, *RD, *PS;
-    const int lrows = P.RBmax + 2 * R;
-    if (SMEM) {
-        size_t o = align_up(sizeof(Shared), 16);
-        V = reinterpret_cast<float*>(smem_raw + o);
-        o += sizeof(float) * (size_t)lrows * WS;
-        Hm = reinterpret_cast<float*>(smem_raw + o);
-        o += sizeof(float) * (size_t)lrows * HS;
-        LM = reinterpret_cast<uint32_t*>(smem_raw + o);
-        o += sizeof(uint32_t) * (size_t)lrows * S;
-        RD = reinterpret_cast<uint32_t*>(smem_raw + o);
-        o += sizeof(uint32_t) * (size_t)lrows * S;
-        PS = reinterpret_cast<uint32_t*>(smem_raw + o);
-    } else {
-        const size_t img_rows = (size_t)Hp + 2 * R;
-        V = P.gV + ((size_t)b * img_rows + ys) * WS;
-        Hm = P.gH + ((size_t)b * img_rows + ys) * HS;
-        LM = P.gLM + ((size_t)b * img_rows + ys) * S;
-        RD = P.gRD + ((size_t)b * img_rows + ys) * S;
-        PS = P.gPS + ((size_t)b * img_rows + ys) * S;
+    // Local row l of every array is image row ys - R + l: own rows are l in [R, R + nrows).
+    const int lrows = P.RB + 2 * R;
+    size_t so = align_up(sizeof(Shared), 16);
+    float* const V = reinterpret_cast<float*>(smem_raw + so);
+    so += sizeof(float) * (size_t)lrows * WS;
+    uint32_t* const LM = reinterpret_cast<uint32_t*>(smem_raw + so);
+    so += sizeof(uint32_t) * (size_t)lrows * SB;
+    uint32_t* const UB = reinterpret_cast<uint32_t*>(smem_raw + so);
+    so += sizeof(uint32_t) * (size_t)lrows * SB;
+    unsigned int* const list = reinterpret_cast<unsigned int*>(smem_raw + so);
+    const uint32_t V_s = (uint32_t)__cvta_generic_to_shared(V);
+    // neighbours' arrays (same offsets in their shared memory)
+    float *Vup = nullptr, *Vdn = nullptr;
+    uint32_t *UBup = nullptr, *UBdn = nullptr;
+    int *und_up = nullptr, *und_dn = nullptr;
+    if (MULTI) {
+        if (rank > 0) {
+            Vup = cluster.map_shared_rank(V, rank - 1);
+            UBup = cluster.map_shared_rank(UB, rank - 1);
+            und_up = cluster.map_shared_rank(&sh.und, rank - 1);
+        }
+        if (rank < T - 1) {
+            Vdn = cluster.map_shared_rank(V, rank + 1);
+            UBdn = cluster.map_shared_rank(UB, rank + 1);
+            und_dn = cluster.map_shared_rank(&sh.und, rank + 1);
+        }
     }
-    // ---- load the band: border + mask zeroing (in place on `score`), zero padding ---------- //
-    if (SMEM) {
-        float4* v4 = reinterpret_cast<float4*>(V);
-        for (int i = tid; i < lrows * WS / 4; i += kThreads) v4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int i = tid; i < lrows * S; i += kThreads) { LM[i] = 0u; RD[i] = 0u; PS[i] = 0u; }
+
+    // ---- load the band: border + mask zeroing (in place on `score`), zero padding, UB bits -------- //
+    for (int i = tid; i < lrows * SB; i += kThreads) { LM[i] = 0u; UB[i] = 0u; }
+    if (tid == 0) { sh.und = 0; sh.n_new[0] = sh.n_new[1] = 0; sh.wl_n[0] = sh.wl_n[1] = 0; sh.xcnt[0] = sh.xcnt[1] = 0; }
+    // zero pads of every row: PAD floats on the left, PAD on the right
+    if constexpr (PAD > 0) {
+        constexpr int PF = PAD / 2;  // float4 per row
+        for (int i = tid; i < L * PF; i += kThreads) {
+            const int l = i / PF, k = i - l * PF;
+            float* rowp = V + (size_t)l * WS;
+            const int off = k < PAD / 4 ? 4 * k : 4 * W4 + PAD + 4 * (k - PAD / 4);
+            *reinterpret_cast<float4*>(rowp + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
-    if (tid == 0) { sh.flags[0] = sh.flags[1] = 0; sh.xcnt[0] = sh.xcnt[1] = 0; sh.wl_n[0] = sh.wl_n[1] = 0; }
     __syncthreads();
     {
         float* simg = P.score + (size_t)b * Hp * Wp;
         const uint8_t* mimg = P.mask ? P.mask + (size_t)b * Hp * Wp : nullptr;
         const int bd = P.border;
-        for (int lr = warp; lr < nrows; lr += kWarps) {
-            const int y = ys + lr;
+        const int vec = P.vec;                       // pixels per lane and access
+        const int gl = 32 / vec;                     // lanes per bitmap word
+        const int tasks_per_row = (4 * W4 + 32 * vec - 1) / (32 * vec);
+        int cnt = 0;
+        for (int t = warp; t < L * tasks_per_row; t += kWarps) {
+            const int l = t / tasks_per_row, cw = t - l * tasks_per_row;
+            const int y = ys - R + l;
+            const bool own = l >= R && l < R + nrows;
+            const bool rowin = y >= 0 && y < Hp;
             const bool rowkill = (y < bd) | (y >= Hp - bd);
-            float* srow = simg + (size_t)y * Wp;
-            const uint8_t* mrow = mimg ? mimg + (size_t)y * Wp : nullptr;
-            float* vrow = V + (size_t)(lr + R) * WS + PAD;
-            if (P.vec4) {
-                for (int c = lane; c < (Wp >> 2); c += 32) {
-                    float4 v = *reinterpret_cast<const float4*>(srow + 4 * c);
-                    float e[4] = {v.x, v.y, v.z, v.w};
-                    uchar4 m4 = make_uchar4(1, 1, 1, 1);
-                    if (mrow) m4 = *reinterpret_cast<const uchar4*>(mrow + 4 * c);
-                    const unsigned char mm[4] = {m4.x, m4.y, m4.z, m4.w};
-                    bool changed = false;
+            const int x = (cw * 32 + lane) * vec;
+            float* srow = simg + (size_t)(rowin ? y : 0) * Wp;
+            const uint8_t* mrow = mimg ? mimg + (size_t)(rowin ? y : 0) * Wp : nullptr;
+            float e[4] = {0.f, 0.f, 0.f, 0.f};
+            const bool in = rowin && x < Wp;
+            if (in) {
+                if (vec == 4) {
+                    const float4 q = *reinterpret_cast<const float4*>(srow + x);
+                    e[0] = q.x; e[1] = q.y; e[2] = q.z; e[3] = q.w;
+                } else if (vec == 2) {
+                    const float2 q = *reinterpret_cast<const float2*>(srow + x);
+                    e[0] = q.x; e[1] = q.y;
+                } else {
+                    e[0] = srow[x];
+                }
+                bool changed = false;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int x = 4 * c + j;
-                        const bool kill = rowkill | (x < bd) | (x >= Wp - bd) | (mm[j] == 0);
+                for (int j = 0; j < 4; ++j) {
+                    if (j < vec) {
+                        const int xx = x + j;
+                        bool kill = rowkill | (xx < bd) | (xx >= Wp - bd);
+                        if (mrow) kill |= (mrow[xx] == 0);
                         if (kill) {
                             changed |= (e[j] != 0.0f);
                             e[j] = 0.0f;
                         }
                     }
-                    v = make_float4(e[0], e[1], e[2], e[3]);
-                    if (changed) *reinterpret_cast<float4*>(srow + 4 * c) = v;
-                    *reinterpret_cast<float4*>(vrow + 4 * c) = v;
                 }
-            } else {
-                for (int x = lane; x < Wp; x += 32) {
-                    float v = srow[x];
-                    bool kill = rowkill | (x < bd) | (x >= Wp - bd);
-                    if (mrow) kill |= (mrow[x] == 0);
-                    if (kill) {
-                        if (v != 0.0f) srow[x] = 0.0f;
-                        v = 0.0f;
-                    }
-                    vrow[x] = v;
+                if (changed && own) {  // the band that owns the row writes the zeroed frame / mask back
+                    if (vec == 4) *reinterpret_cast<float4*>(srow + x) = make_float4(e[0], e[1], e[2], e[3]);
+                    else if (vec == 2) *reinterpret_cast<float2*>(srow + x) = make_float2(e[0], e[1]);
+                    else srow[x] = e[0];
                 }
             }
+            unsigned bits = 0;
+            if (x < 4 * W4) {
+                float* vrow = V + (size_t)l * WS + PAD + x;
+                if (vec == 4) *reinterpret_cast<float4*>(vrow) = make_float4(e[0], e[1], e[2], e[3]);
+                else if (vec == 2) *reinterpret_cast<float2*>(vrow) = make_float2(e[0], e[1]);
+                else vrow[0] = e[0];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j < vec && e[j] > 0.0f) bits |= 1u << j;
+            }
+            if (own) cnt += __popc(bits);
+            unsigned word = bits << (vec * (lane & (gl - 1)));
+            for (int o = 1; o < gl; o <<= 1) word |= __shfl_xor_sync(0xffffffffu, word, o);
+            if ((lane & (gl - 1)) == 0 && x < 4 * W4) UB[(size_t)l * SB + 1 + (x >> 5)] = word;
         }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (lane == 0 && cnt) atomicAdd(&sh.und, cnt);
     }
-    if (!SMEM) __threadfence();
     EINX_TRACE(0);
-    int trace_slot = 1;
 
     // ---- NMS rounds ------------------------------------------------------------------------ //
-    if constexpr (R > 0) {
-        constexpr int P2 = 2 * R + 1;
-        unsigned int* const wl0 = (SMEM && P.wl_smem) ? reinterpret_cast<unsigned int*>(Hm) : P.worklists + (size_t)blockIdx.x * 2 * kWorklistCap;
-        int wl_cur = 0;         // list buffer holding the current undecided set
-        bool wl_mode = false;   // CTA-uniform: this round runs on the worklist instead of dense passes
-        const int CH = 8 * S;   // float4 chunks per row
-        for (int round = 0;; ++round) {
-            cluster.sync();  // S1: every band's V (and the previous round's flag) is final
-            trace_slot = 1 + 8 * round;
-            EINX_TRACE(trace_slot); ++trace_slot;
-            if (round > 0) {
-                int any = 0;
-                for (int r = 0; r < CS; ++r) any |= *cluster.map_shared_rank(&sh.flags[(round - 1) & 1], r);
-                if (!any) break;
+    auto sync_all = [&]() {
+        if (MULTI) cluster.sync();
+        else __syncthreads();
+    };
+    // clear the window of a (new) maximum at column x in local row l2 of UB, in every copy of that row;
+    // returns the undecided bits this call cleared in the owner's copy, by owner (self / up / down)
+    auto clear_window = [&](int l2, int x, int& c_self, int& c_up, int& c_dn) {
+        const int xl = x - R + 32;
+        const int wi = xl >> 5, shf = xl & 31;
+        const unsigned long long m64 = (unsigned long long)kWinMask << shf;
+        const uint32_t lo = (uint32_t)m64, hi = (uint32_t)(m64 >> 32);
+        const bool mine = l2 >= R && l2 < R + nrows;
+        uint32_t* u = UB + (size_t)l2 * SB + wi;
+        uint32_t o0 = atomicAnd(u, ~lo), o1 = 0;
+        if (hi) o1 = atomicAnd(u + 1, ~hi);
+        if (mine) c_self += __popc(o0 & lo) + __popc(o1 & hi);
+        if (MULTI) {
+            const int lu = cp.up(l2, 2 * R), ld = cp.down(l2);
+            if (lu >= 0) {
+                uint32_t* ur = UBup + (size_t)lu * SB + wi;
+                o0 = atomicAnd(ur, ~lo);
+                o1 = hi ? atomicAnd(ur + 1, ~hi) : 0u;
+                if (l2 < R) c_up += __popc(o0 & lo) + __popc(o1 & hi);  // rows [0, R) belong to the band above
             }
-            if (SMEM) {
-                if (rank > 0) {
-                    const float4* src = reinterpret_cast<const float4*>(cluster.map_shared_rank(V, rank - 1) + (size_t)nprev * WS);
-                    float4* dst = reinterpret_cast<float4*>(V);
-                    for (int i = tid; i < R * WS / 4; i += kThreads) dst[i] = src[i];
+            if (ld >= 0) {
+                uint32_t* ur = UBdn + (size_t)ld * SB + wi;
+                o0 = atomicAnd(ur, ~lo);
+                o1 = hi ? atomicAnd(ur + 1, ~hi) : 0u;
+                if (l2 >= R + nrows) c_dn += __popc(o0 & lo) + __popc(o1 & hi);
+            }
+        }
+    };
+    auto settle_counts = [&](int c_self, int c_up, int c_dn) {
+        c_self = __reduce_add_sync(0xffffffffu, c_self);
+        if (lane == 0 && c_self) atomicSub(&sh.und, c_self);
+        if (MULTI) {
+            c_up = __reduce_add_sync(0xffffffffu, c_up);
+            c_dn = __reduce_add_sync(0xffffffffu, c_dn);
+            if (lane == 0 && c_up) atomicSub(und_up, c_up);
+            if (lane == 0 && c_dn) atomicSub(und_dn, c_dn);
+        }
+    };
+
+    if constexpr (R > 0) {
+        const int half = P.LC / 2;  // worklist capacity (two halves of the list buffer)
+        bool sparse = false;
+        int wl_cur = 0;
+        int trace_slot = 1;
+        for (int round = 0;; ++round) {
+            sync_all();  // every band's und / V / UB is final for this round
+            trace_slot = round < 19 ? 1 + 6 * round : 126;
+            EINX_TRACE(trace_slot); ++trace_slot;
+            int tot = sh.und, mx = tot;
+            if (MULTI) {
+                tot = 0; mx = 0;
+                for (int r = 0; r < T; ++r) {
+                    const int u = *cluster.map_shared_rank(&sh.und, r);
+                    tot += u;
+                    mx = max(mx, u);
                 }
-                if (rank < CS - 1) {
-                    const float4* src = reinterpret_cast<const float4*>(cluster.map_shared_rank(V, rank + 1) + (size_t)R * WS);
-                    float4* dst = reinterpret_cast<float4*>(V + (size_t)(R + nrows) * WS);
-                    for (int i = tid; i < R * WS / 4; i += kThreads) dst[i] = src[i];
+            }
+            if (tot == 0 || round > Hp + Wp) break;  // (the round bound only guards against a corrupted count: a
+                                                     // round always decides at least one pixel)
+            if (!sparse && mx <= half) {
+                // build the worklist of undecided pixels of the own rows, raster order
+                sparse = true;
+                wl_cur = 0;
+                const int nwords = nrows * (SB - 2);
+                int run = 0;
+                for (int base = 0; base < nwords; base += kThreads) {
+                    const int wi = base + tid;
+                    int lr = 0, s = 0;
+                    uint32_t w = 0;
+                    if (wi < nwords) {
+                        lr = wi / (SB - 2);
+                        s = wi - lr * (SB - 2);
+                        w = UB[(size_t)(lr + R) * SB + 1 + s];
+                    }
+                    int totw;
+                    int pos = run + block_excl_scan(__popc(w), sh.warp_scan, totw);
+                    while (w) {
+                        const int bit = __ffs(w) - 1;
+                        w &= w - 1;
+                        list[pos++] = ((unsigned)(lr + R) << 16) | (unsigned)(32 * s + bit);
+                    }
+                    run += totw;
                 }
+                if (tid == 0) { sh.wl_n[0] = run; sh.wl_n[1] = 0; }
                 __syncthreads();
             }
-            if (!wl_mode) {
-                // pass A: Hm = horizontal window maximum of every local row, halo included (in the
-                // global variant the halo rows are the neighbours' own rows: both CTAs then store
-                // identical values, so no cross-CTA ordering is needed inside a round)
-                {
-                    for (int t = tid; t < (nrows + 2 * R) * CH; t += kThreads) {
-                        const int row = (int)__umulhi((unsigned)t, P.magic_ch);
-                        const int ch = t - row * CH;
-                        const float4* src = reinterpret_cast<const float4*>(V + (size_t)row * WS) + ch;
-                        float a[4 + 2 * PAD];
+            if (!sparse) {
+                // ---- dense pass: sweep, collect the new maxima ---------------------------------- //
+                int* const n_new = &sh.n_new[round & 1];
+                const int nunits = NCW * P.NSEG;
+                for (int u = warp; u < nunits; u += kWarps) {
+                    const int seg = u / NCW, cw = u - seg * NCW;
+                    const int a = R + seg * P.SR;                   // local output rows [a, e)
+                    const int e = min(a + P.SR, R + nrows);
+                    if (a >= e) continue;
+                    const int g = cw * 32 + lane;
+                    const bool active = g < W4;
+                    // shared-window byte address of the leftmost float4 the thread reads in row a - R
+                    uint32_t rp = V_s + 4u * (uint32_t)((a - R) * WS + 4 * (active ? g : W4 - 1));
+                    const uint32_t row_bytes = 4u * (uint32_t)WS;
+                    float h[P2][4], p3[P2][4];
+#pragma unroll
+                    for (int j = 0; j < P2; ++j)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) { h[j][c] = 0.0f; p3[j][c] = 0.0f; }
+                    // ring slot of a row = (row - (a - R)) mod P2.  Ingesting a row: its horizontal window maxima
+                    // (h) and the 3-row partial maximum that ends with it (p3 of the row two above).
+                    auto ingest = [&](auto slot) {
+                        constexpr int j = decltype(slot)::value;
+                        constexpr int j1 = (j + P2 - 1) % P2, j2 = (j + P2 - 2) % P2;
+                        float av[4 + 2 * PAD];
 #pragma unroll
                         for (int k = 0; k < 1 + PAD / 2; ++k) {
-                            const float4 q = src[k];
-                            a[4 * k] = q.x; a[4 * k + 1] = q.y; a[4 * k + 2] = q.z; a[4 * k + 3] = q.w;
+                            const float4 q = lds128(rp + 16u * k);
+                            av[4 * k] = q.x; av[4 * k + 1] = q.y; av[4 * k + 2] = q.z; av[4 * k + 3] = q.w;
                         }
-                        float o[4];
-                        hmax4<R>(a, o);
-                        *(reinterpret_cast<float4*>(Hm + (size_t)row * HS) + ch) = make_float4(o[0], o[1], o[2], o[3]);
-                    }
-                }
-                __syncthreads();
-                EINX_TRACE(trace_slot); ++trace_slot;
-                // pass B: a warp decides 8 rows x 32 columns.  lm = v > 0, v == window max, and no
-                // equal value earlier in raster order (rows above: their row maxima; same row: the R
-                // values to the left) -- the first-occurrence argmax of detector_util.py:298-308.
-                {
-                    const int nblk = (nrows + 7) >> 3;
-                    const int avail_all = nrows + 2 * R;
-                    for (int t = warp; t < nblk * S; t += kWarps) {
-                        const int rb = (int)__umulhi((unsigned)t, P.magic_s);
-                        const int s = t - rb * S;
-                        const int r0 = rb * 8;
-                        const int x = 32 * s + lane;
-                        const int avail = avail_all - r0;
-                        float a[8 + 2 * R];
+                        hmax4<R>(av, h[j]);
 #pragma unroll
-                        for (int k = 0; k < 8 + 2 * R; ++k) a[k] = (k < avail) ? Hm[(size_t)(r0 + k) * HS + x] : 0.0f;
-                        float m[8];
-                        vmax8<R>(a, m);
-                        uint32_t lm_mine = 0, pos_mine = 0;
+                        for (int c = 0; c < 4; ++c) p3[j2][c] = fmax3(h[j2][c], h[j1][c], h[j][c]);
+                    };
+                    // Output row y = (row just ingested in slot j) - R: all of its window rows are in the ring.
+                    auto emit = [&](auto slot, int y) {
+                        constexpr int j = decltype(slot)::value;
+                        constexpr int j2 = (j + P2 - 2) % P2;
+                        float M[4];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int lr = r0 + i;
-                            const float* crow = V + (size_t)(lr + R) * WS + PAD + x;
-                            const float vc = (lr < nrows) ? crow[0] : 0.0f;
-                            const bool pos = vc > 0.0f;
-                            bool lm = pos && (vc == m[i]);
-                            if (lm) {
-                                float early = crow[-1];
+                        for (int c = 0; c < 4; ++c) M[c] = p3[j2][c];  // rows y+R-2 .. y+R
 #pragma unroll
-                                for (int d = 2; d <= R; ++d) early = fmaxf(early, crow[-d]);
+                        for (int i = 0; 3 * i < P2 - 3; ++i) {
+                            const int ji = (j + 3 * i + 1) % P2;       // rows y-R+3i .. y-R+3i+2
 #pragma unroll
-                                for (int k = 0; k < R; ++k) early = fmaxf(early, a[i + k]);
-                                lm = early < vc;
+                            for (int c = 0; c < 4; ++c) M[c] = fmaxf(M[c], p3[ji][c]);
+                        }
+                        const uint32_t cpa = rp - (uint32_t)R * row_bytes + 4u * PAD;  // the thread's 4 pixels of row y
+                        const float4 cv = lds128(cpa);
+                        const float vc[4] = {cv.x, cv.y, cv.z, cv.w};
+                        bool any;
+                        if constexpr (R >= 3) {
+                            // a zero pixel equal to its (all-zero) window implies the thread's other pixels are zero too
+                            any = (vc[0] == M[0]) | (vc[1] == M[1]) | (vc[2] == M[2]) | (vc[3] == M[3]);
+                            any = any && fmaxf(fmaxf(vc[0], vc[1]), fmaxf(vc[2], vc[3])) > 0.0f;
+                        } else {
+                            any = false;
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) any |= (vc[c] > 0.0f && vc[c] == M[c]);
+                        }
+                        if (any && active) {
+                            // slow path (about one pixel in (2R+1)^2): exact first-occurrence test of
+                            // detector_util.py:298-308 -- no equal value earlier in raster order
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const float v = vc[c];
+                                if (!(v > 0.0f && v == M[c])) continue;
+                                const int x = 4 * g + c;
+                                const uint32_t px = cpa + 4u * c;
+                                bool tie = false;
+#pragma unroll
+                                for (int dy = 1; dy <= R; ++dy)
+#pragma unroll
+                                    for (int dx = -R; dx <= R; ++dx) tie |= (lds32(px - dy * row_bytes + 4 * dx) == v);
+#pragma unroll
+                                for (int d = 1; d <= R; ++d) tie |= (lds32(px - 4 * d) == v);
+                                if (!tie) {
+                                    const uint32_t bit = 1u << (x & 31);
+                                    const uint32_t old = atomicOr(&LM[(size_t)y * SB + 1 + (x >> 5)], bit);
+                                    if (!(old & bit)) {
+                                        const int pos = atomicAdd(n_new, 1);
+                                        if (pos < P.LC) list[pos] = ((unsigned)y << 16) | (unsigned)x;
+                                    }
+                                }
                             }
-                            const uint32_t lb = __ballot_sync(0xffffffffu, lm);
-                            const uint32_t pb = __ballot_sync(0xffffffffu, pos);
-                            if (lane == i) { lm_mine = lb; pos_mine = pb; }
                         }
-                        if (lane < 8 && r0 + lane < nrows) {
-                            LM[(size_t)(r0 + lane + R) * S + s] = lm_mine;
-                            PS[(size_t)(r0 + lane + R) * S + s] = pos_mine;
-                        }
+                    };
+                    // prologue: rows a-R .. a+R-1 fill the ring (slots 0 .. 2R-1), nothing to emit yet
+                    static_for<0, P2 - 1>([&](auto slot) {
+                        ingest(slot);
+                        rp += row_bytes;
+                    });
+                    // steady state: ingest row y + R (slot (2R + k) mod P2), emit row y
+                    for (int y0 = a; y0 < e; y0 += P2) {
+                        static_for<0, P2>([&](auto kk) {
+                            constexpr int k = decltype(kk)::value;
+                            if (y0 + k < e) {
+                                using Slot = std::integral_constant<int, (P2 - 1 + k) % P2>;
+                                ingest(Slot{});
+                                emit(Slot{}, y0 + k);
+                                rp += row_bytes;
+                            }
+                        });
                     }
                 }
-            } else {
-                // worklist round, phase 1: each undecided pixel scans its own window
-                const int n = sh.wl_n[wl_cur];
-                for (int e = tid; e < n; e += kThreads) {
-                    const unsigned ent = wl0[wl_cur * kWorklistCap + e];
-                    const int lr = (int)(ent >> 16), x = (int)(ent & 0xffffu);
-                    const float* crow = V + (size_t)(lr + R) * WS + x + PAD;
-                    const float vc = crow[0];
-                    float emax = 0.0f, lmax = 0.0f;  // raster-earlier / raster-later halves of the window
-#pragma unroll
-                    for (int dy = 1; dy <= R; ++dy) {
+                EINX_TRACE(trace_slot); ++trace_slot;
+                sync_all();
+                EINX_TRACE(trace_slot); ++trace_slot;
+                // ---- scatter: every new maximum kills its window (V and UB, all copies) ---------- //
+                {
+                    const int nn = min(*n_new, P.LC);
+                    if (tid == 0) sh.n_new[(round + 1) & 1] = 0;
+                    int c_self = 0, c_up = 0, c_dn = 0;
+                    for (int it = tid; it < nn * P2; it += kThreads) {
+                        const int en = it / P2, dyi = it - en * P2;
+                        const unsigned ent = list[en];
+                        const int l = (int)(ent >> 16), x = (int)(ent & 0xffffu);
+                        const int l2 = l + dyi - R;
+                        float* row = V + (size_t)l2 * WS + PAD + x;
+                        const int lu = MULTI ? cp.up(l2, 2 * R) : -1, ld = MULTI ? cp.down(l2) : -1;
+                        float* rowu = lu >= 0 ? Vup + (size_t)lu * WS + PAD + x : nullptr;
+                        float* rowd = ld >= 0 ? Vdn + (size_t)ld * WS + PAD + x : nullptr;
 #pragma unroll
                         for (int dx = -R; dx <= R; ++dx) {
-                            emax = fmaxf(emax, crow[-dy * WS + dx]);
-                            lmax = fmaxf(lmax, crow[dy * WS + dx]);
+                            if (dx == 0 && dyi == R) continue;
+                            row[dx] = 0.0f;
+                            if (MULTI) {
+                                if (rowu) rowu[dx] = 0.0f;
+                                if (rowd) rowd[dx] = 0.0f;
+                            }
                         }
+                        clear_window(l2, x, c_self, c_up, c_dn);
                     }
-#pragma unroll
-                    for (int d = 1; d <= R; ++d) { emax = fmaxf(emax, crow[-d]); lmax = fmaxf(lmax, crow[d]); }
-                    if (vc > emax && vc >= lmax) {
-                        atomicOr(&LM[(size_t)(lr + R) * S + (x >> 5)], 1u << (x & 31));
-                        wl0[wl_cur * kWorklistCap + e] = ent | 0x80000000u;  // decided: a local maximum (rows < 32768)
-                    }
+                    settle_counts(c_self, c_up, c_dn);
                 }
-            }
-            if (!SMEM) __threadfence();
-            EINX_TRACE(trace_slot); ++trace_slot;
-            cluster.sync();  // S2: own-row maxima bits are ready in every band
-            if (SMEM) {
-                if (rank > 0) {
-                    const uint32_t* src = cluster.map_shared_rank(LM, rank - 1) + (size_t)nprev * S;
-                    for (int i = tid; i < R * S; i += kThreads) LM[i] = src[i];
-                }
-                if (rank < CS - 1) {
-                    const uint32_t* src = cluster.map_shared_rank(LM, rank + 1) + (size_t)R * S;
-                    uint32_t* dst = LM + (size_t)(R + nrows) * S;
-                    for (int i = tid; i < R * S; i += kThreads) dst[i] = src[i];
-                }
-            }
-            const int wl_next = wl_cur ^ 1;
-            if (tid == 0) sh.wl_n[wl_next] = 0;
-            __syncthreads();
-            EINX_TRACE(trace_slot); ++trace_slot;
-            int und = 0;
-            if (!wl_mode) {
-                // horizontal dilation of the maxima bits, on words, for every local row
-                for (int t = tid; t < (nrows + 2 * R) * S; t += kThreads) {
-                    const int rr = (int)__umulhi((unsigned)t, P.magic_s);
-                    const int s = t - rr * S;
-                    const size_t i = (size_t)rr * S + s;
-                    const uint32_t w = LM[i];
-                    const uint32_t wl = s > 0 ? LM[i - 1] : 0u;
-                    const uint32_t wr = s < S - 1 ? LM[i + 1] : 0u;
-                    uint32_t acc = w;
-#pragma unroll
-                    for (int d = 1; d <= R; ++d) acc |= (w >> d) | (wr << (32 - d)) | (w << d) | (wl >> (32 - d));
-                    RD[i] = acc;
-                }
-            }
-            if (!wl_mode) {
-                __syncthreads();
                 EINX_TRACE(trace_slot); ++trace_slot;
-                // suppression set + undecided census per own word; the undecided pixels become the
-                // next round's worklist
-                for (int t = tid; t < nrows * S; t += kThreads) {
-                    const int lr = (int)__umulhi((unsigned)t, P.magic_s);
-                    const int s = t - lr * S;
-                    uint32_t dil = 0;
-#pragma unroll
-                    for (int dy = 0; dy < P2; ++dy) dil |= RD[(size_t)(lr + dy) * S + s];
-                    const size_t i = (size_t)(lr + R) * S + s;
-                    const uint32_t posw = PS[i];
-                    const uint32_t sup = dil & ~LM[i] & posw;  // positive pixels a neighbouring maximum suppresses
-                    uint32_t u = posw & ~dil;                   // positive, not a maximum, not suppressed
-                    PS[i] = sup;
-                    if (u) {
-                        und = 1;
-                        int pos = atomicAdd(&sh.wl_n[wl_next], __popc(u));
-                        while (u) {
-                            const int bit = __ffs(u) - 1;
-                            u &= u - 1;
-                            if (pos < kWorklistCap) wl0[wl_next * kWorklistCap + pos] = ((unsigned)lr << 16) | (unsigned)(32 * s + bit);
-                            ++pos;
-                        }
-                    }
-                }
-                __syncthreads();
-                EINX_TRACE(trace_slot); ++trace_slot;
-                // apply: zero the suppressed pixels, 4 at a time
-                for (int t = tid; t < nrows * CH; t += kThreads) {
-                    const int lr = (int)__umulhi((unsigned)t, P.magic_ch);
-                    const int ch = t - lr * CH;
-                    const uint32_t bits = (PS[(size_t)(lr + R) * S + (ch >> 3)] >> ((ch & 7) * 4)) & 0xfu;
-                    if (bits) {
-                        float4* cell = reinterpret_cast<float4*>(V + (size_t)(lr + R) * WS + PAD) + ch;
-                        float4 v = *cell;
-                        if (bits & 1u) v.x = 0.0f;
-                        if (bits & 2u) v.y = 0.0f;
-                        if (bits & 4u) v.z = 0.0f;
-                        if (bits & 8u) v.w = 0.0f;
-                        *cell = v;
-                    }
-                }
             } else {
-                // worklist round, phase 2: drop pixels that now have a local maximum in their window
+                // ---- sparse round, phase 1: an undecided pixel looks at its undecided neighbours ---- //
+                unsigned int* const wl = list + wl_cur * half;
                 const int n = sh.wl_n[wl_cur];
-                for (int e = tid; e < n; e += kThreads) {
-                    const unsigned ent = wl0[wl_cur * kWorklistCap + e];
-                    if (ent & 0x80000000u) continue;  // became a local maximum in phase 1
-                    const int lr = (int)(ent >> 16), x = (int)(ent & 0xffffu);
-                    const int xl = x - R;
-                    const int wi = xl >> 5;  // arithmetic: -1 for the left border
-                    const int sh_ = xl - 32 * wi;
-                    uint32_t any = 0;
+                for (int en = tid; en < n; en += kThreads) {
+                    const unsigned ent = wl[en];
+                    const int l = (int)(ent >> 16), x = (int)(ent & 0xffffu);
+                    const float* cpx = V + (size_t)l * WS + PAD + x;
+                    const float v = cpx[0];
+                    const int xl = x - R + 32;
+                    const int wi = xl >> 5, shf = xl & 31;
+                    bool beaten = false;
 #pragma unroll
                     for (int dy = -R; dy <= R; ++dy) {
-                        const uint32_t* rowp = LM + (size_t)(lr + R + dy) * S;
-                        const uint32_t w0 = (wi >= 0 && wi < S) ? rowp[wi] : 0u;
-                        const uint32_t w1 = (wi + 1 >= 0 && wi + 1 < S) ? rowp[wi + 1] : 0u;
-                        const unsigned long long both = (unsigned long long)w0 | ((unsigned long long)w1 << 32);
-                        any |= (uint32_t)(both >> sh_) & ((1u << P2) - 1u);
+                        const uint32_t* u = UB + (size_t)(l + dy) * SB + wi;
+                        const unsigned long long both = (unsigned long long)u[0] | ((unsigned long long)u[1] << 32);
+                        uint32_t f = (uint32_t)(both >> shf) & kWinMask;
+                        if (dy == 0) f &= ~(1u << R);
+                        while (f) {
+                            const int bit = __ffs(f) - 1;
+                            f &= f - 1;
+                            const float w = cpx[dy * WS + bit - R];
+                            // raster-earlier neighbours win ties (first-occurrence argmax)
+                            const bool earlier = dy < 0 || (dy == 0 && bit < R);
+                            if (w > v || (earlier && w == v)) { beaten = true; f = 0; }
+                        }
                     }
-                    if (any) {
-                        V[(size_t)(lr + R) * WS + x + PAD] = 0.0f;
-                    } else {
-                        const int pos = atomicAdd(&sh.wl_n[wl_next], 1);
-                        wl0[wl_next * kWorklistCap + pos] = ent;  // pos < n <= kWorklistCap
-                        und = 1;
+                    if (!beaten) {
+                        atomicOr(&LM[(size_t)l * SB + 1 + (x >> 5)], 1u << (x & 31));
+                        wl[en] = ent | 0x80000000u;  // a new maximum (local rows < 32768)
                     }
                 }
+                EINX_TRACE(trace_slot); ++trace_slot;
+                sync_all();
+                EINX_TRACE(trace_slot); ++trace_slot;
+                // ---- phase 2: the new maxima clear their windows in UB (all copies) ---------------- //
+                {
+                    if (tid == 0) sh.wl_n[wl_cur ^ 1] = 0;
+                    int c_self = 0, c_up = 0, c_dn = 0;
+                    for (int en = tid; en < n; en += kThreads) {
+                        const unsigned ent = wl[en];
+                        if (!(ent & 0x80000000u)) continue;
+                        const int l = (int)((ent >> 16) & 0x7fffu), x = (int)(ent & 0xffffu);
+#pragma unroll
+                        for (int dy = -R; dy <= R; ++dy) clear_window(l + dy, x, c_self, c_up, c_dn);
+                    }
+                    settle_counts(c_self, c_up, c_dn);
+                }
+                sync_all();
+                EINX_TRACE(trace_slot); ++trace_slot;
+                // ---- phase 3: keep the still-undecided entries ---------------------------------- //
+                {
+                    unsigned int* const wn = list + (wl_cur ^ 1) * half;
+                    for (int base = 0; base < n; base += kThreads) {
+                        const int en = base + tid;
+                        unsigned ent = 0;
+                        bool keep = false;
+                        if (en < n) {
+                            ent = wl[en];
+                            if (!(ent & 0x80000000u)) {
+                                const int l = (int)(ent >> 16), x = (int)(ent & 0xffffu);
+                                keep = (UB[(size_t)l * SB + 1 + (x >> 5)] >> (x & 31)) & 1u;
+                            }
+                        }
+                        const unsigned kb = __ballot_sync(0xffffffffu, keep);
+                        int pos = 0;
+                        if (lane == 0 && kb) pos = atomicAdd(&sh.wl_n[wl_cur ^ 1], __popc(kb));
+                        pos = __shfl_sync(0xffffffffu, pos, 0);
+                        if (keep) wn[pos + __popc(kb & ((1u << lane) - 1u))] = ent;
+                    }
+                    wl_cur ^= 1;
+                }
             }
-            und = __syncthreads_or(und);
-            EINX_TRACE(trace_slot); ++trace_slot;
-            wl_mode = sh.wl_n[wl_next] <= kWorklistCap;
-            wl_cur = wl_next;
-            if (tid == 0) sh.flags[round & 1] = und;
-            if (!SMEM) __threadfence();
         }
     } else {
-        // no NMS: survivors are simply the positive pixels
+        // no NMS: the survivors are simply the positive pixels
         __syncthreads();
-        for (int wi = warp; wi < nrows * S; wi += kWarps) {
-            const int lr = wi / S, s = wi - lr * S;
-            const float v = V[(size_t)(lr + R) * WS + 32 * s + lane + PAD];
-            const unsigned bits = __ballot_sync(0xffffffffu, v > 0.0f);
-            if (lane == 0) LM[(size_t)(lr + R) * S + s] = bits;
-        }
+        for (int i = tid; i < nrows * SB; i += kThreads) LM[(size_t)R * SB + i] = UB[(size_t)R * SB + i];
         __syncthreads();
     }
 
     EINX_TRACE(120);
-    // ---- survivors -> ordered per-image list (global workspace) ------------------------------ //
-    // At the fixpoint every positive pixel is a local maximum, so the maxima bits of the last
-    // round are exactly the survivors.
-    float* slist = P.surv_val + (size_t)b * P.scap;
-    int32_t* sidx = P.surv_idx + (size_t)b * P.scap;
-    const int nwords = nrows * S;
-    int own = 0;
+    // ---- survivors -> ordered per-image list ------------------------------------------------- //
+    // At the fixpoint the selected pixels (LM bits of the own rows) are exactly the survivors.  The lists
+    // live in the shared-memory scratch (UB + list buffer, both dead now) for single-CTA images, in the
+    // global workspace for clusters.
+    float* slist;
+    int32_t* sidx;
+    const bool smem_lists = !MULTI && P.tail_smem;
+    if (smem_lists) {
+        slist = reinterpret_cast<float*>(UB);
+        sidx = reinterpret_cast<int32_t*>(UB) + P.scap;
+    } else {
+        slist = P.surv_val + (size_t)b * P.scap;
+        sidx = P.surv_idx + (size_t)b * P.scap;
+    }
+    const int SW = SB - 2;
+    const int nwords = nrows * SW;
+    int own = 0, offset = 0, total = 0;
     {
         int c = 0;
-        for (int wi = tid; wi < nwords; wi += kThreads) c += __popc(LM[(size_t)R * S + wi]);
+        for (int wi = tid; wi < nwords; wi += kThreads) {
+            const int lr = wi / SW, s = wi - lr * SW;
+            c += __popc(LM[(size_t)(lr + R) * SB + 1 + s]);
+        }
         c = __reduce_add_sync(0xffffffffu, c);
         if (lane == 0 && c) atomicAdd(&sh.xcnt[0], c);
     }
-    cluster.sync();
-    int offset = 0, total = 0;
-    for (int r = 0; r < CS; ++r) {
-        const int c = *cluster.map_shared_rank(&sh.xcnt[0], r);
-        if (r < rank) offset += c;
-        total += c;
+    sync_all();
+    if (MULTI) {
+        for (int r = 0; r < T; ++r) {
+            const int c = *cluster.map_shared_rank(&sh.xcnt[0], r);
+            if (r < rank) offset += c;
+            total += c;
+        }
+    } else {
+        total = sh.xcnt[0];
     }
     own = sh.xcnt[0];
     {
+        // the bitmap words are read before the lists (which may alias UB, never LM) are written
         int run = offset;
         for (int base = 0; base < nwords; base += kThreads) {
             const int wi = base + tid;
-            const uint32_t w = wi < nwords ? LM[(size_t)R * S + wi] : 0u;
+            int lr = 0, s = 0;
+            uint32_t w = 0;
+            if (wi < nwords) {
+                lr = wi / SW;
+                s = wi - lr * SW;
+                w = LM[(size_t)(lr + R) * SB + 1 + s];
+            }
             int tot;
             int pos = run + block_excl_scan(__popc(w), sh.warp_scan, tot);
-            if (w) {
-                const int lr = wi / S, s = wi - lr * S;
-                uint32_t bits = w;
-                while (bits) {
-                    const int bit = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    const int x = 32 * s + bit;
-                    if (pos < P.scap) {
-                        slist[pos] = V[(size_t)(lr + R) * WS + x + PAD];
-                        sidx[pos] = (ys + lr) * Wp + x;
-                    }
-                    ++pos;
+            while (w) {
+                const int bit = __ffs(w) - 1;
+                w &= w - 1;
+                const int x = 32 * s + bit;
+                if (pos < P.scap) {
+                    slist[pos] = V[(size_t)(lr + R) * WS + PAD + x];
+                    sidx[pos] = (ys + lr) * Wp + x;
                 }
+                ++pos;
             }
             run += tot;
         }
     }
-    __threadfence();
+    if (MULTI) __threadfence();
     EINX_TRACE(121);
-    cluster.sync();  // the whole image's list is visible
+    sync_all();  // the whole image's list is visible
     EINX_TRACE(122);
 
     // ---- threshold (detector_util.py:108-133), computed redundantly by every CTA ------------ //
@@ -673,10 +800,12 @@ __global__ void __maxnreg__(48) detect_kernel(const DetectParams P) {
         float a = 0.0f, bq = 0.0f;
         if (P.rank_hi >= zeros) {
             if (P.rank_lo >= zeros) {
-                select_two(slist, total, P.rank_lo - zeros, P.rank_hi != P.rank_lo, sh, a, bq);
+                if (smem_lists) select_two<false>(slist, total, P.rank_lo - zeros, P.rank_hi != P.rank_lo, sh, a, bq);
+                else select_two<true>(slist, total, P.rank_lo - zeros, P.rank_hi != P.rank_lo, sh, a, bq);
             } else {  // lo falls on a zero, hi on the smallest survivor
                 float dummy;
-                select_two(slist, total, 0, false, sh, bq, dummy);
+                if (smem_lists) select_two<false>(slist, total, 0, false, sh, bq, dummy);
+                else select_two<true>(slist, total, 0, false, sh, bq, dummy);
             }
         }
         // torch.lerp(a, b, 0.5) takes the `b - (b - a) * (1 - w)` branch
@@ -688,16 +817,20 @@ __global__ void __maxnreg__(48) detect_kernel(const DetectParams P) {
     // ---- keypoint rows in raster order + optional dense map ---------------------------------- //
     {
         int c = 0;
-        for (int i = tid; i < own; i += kThreads) c += (__ldcg(slist + offset + i) > thr) ? 1 : 0;
+        for (int i = tid; i < own; i += kThreads) c += ((smem_lists ? slist[offset + i] : __ldcg(slist + offset + i)) > thr) ? 1 : 0;
         c = __reduce_add_sync(0xffffffffu, c);
         if (lane == 0 && c) atomicAdd(&sh.xcnt[1], c);
     }
-    cluster.sync();
+    sync_all();
     int koff = 0, ktotal = 0;
-    for (int r = 0; r < CS; ++r) {
-        const int c = *cluster.map_shared_rank(&sh.xcnt[1], r);
-        if (r < rank) koff += c;
-        ktotal += c;
+    if (MULTI) {
+        for (int r = 0; r < T; ++r) {
+            const int c = *cluster.map_shared_rank(&sh.xcnt[1], r);
+            if (r < rank) koff += c;
+            ktotal += c;
+        }
+    } else {
+        ktotal = sh.xcnt[1];
     }
     if (rank == 0 && tid == 0) P.counts[b] = ktotal;
     {
@@ -709,8 +842,8 @@ __global__ void __maxnreg__(48) detect_kernel(const DetectParams P) {
             int idx = 0;
             bool keep = false;
             if (i < own) {
-                v = __ldcg(slist + offset + i);
-                idx = __ldcg(sidx + offset + i);
+                v = smem_lists ? slist[offset + i] : __ldcg(slist + offset + i);
+                idx = smem_lists ? sidx[offset + i] : __ldcg(sidx + offset + i);
                 keep = v > thr;
             }
             int tot;
@@ -725,30 +858,46 @@ __global__ void __maxnreg__(48) detect_kernel(const DetectParams P) {
         }
     }
     if (P.nms_map) {
+        // selected AND above the threshold; V still holds dead values from the sparse rounds, LM decides
         float* out = P.nms_map + (size_t)b * Hp * Wp;
-        for (int e = tid; e < nrows * Wp; e += kThreads) {
-            const int lr = e / Wp, x = e - lr * Wp;
-            const float v = V[(size_t)(lr + R) * WS + x + PAD];
-            out[(size_t)(ys + lr) * Wp + x] = v > thr ? v : 0.0f;
+        if (P.vec == 4) {
+            for (int e = tid; e < nrows * W4; e += kThreads) {
+                const int lr = e / W4, g = e - lr * W4;
+                const int x = 4 * g;
+                const uint32_t nib = (LM[(size_t)(lr + R) * SB + 1 + (x >> 5)] >> (x & 31)) & 0xfu;
+                float4 v = *reinterpret_cast<const float4*>(V + (size_t)(lr + R) * WS + PAD + x);
+                v.x = ((nib & 1u) && v.x > thr) ? v.x : 0.0f;
+                v.y = ((nib & 2u) && v.y > thr) ? v.y : 0.0f;
+                v.z = ((nib & 4u) && v.z > thr) ? v.z : 0.0f;
+                v.w = ((nib & 8u) && v.w > thr) ? v.w : 0.0f;
+                *reinterpret_cast<float4*>(out + (size_t)(ys + lr) * Wp + x) = v;
+            }
+        } else {
+            for (int e = tid; e < nrows * Wp; e += kThreads) {
+                const int lr = e / Wp, x = e - lr * Wp;
+                const bool sel = (LM[(size_t)(lr + R) * SB + 1 + (x >> 5)] >> (x & 31)) & 1u;
+                const float v = V[(size_t)(lr + R) * WS + PAD + x];
+                out[(size_t)(ys + lr) * Wp + x] = (sel && v > thr) ? v : 0.0f;
+            }
         }
     }
     EINX_TRACE(124);
-    cluster.sync();  // nobody leaves while a neighbour may still read its shared memory
+    if (MULTI) cluster.sync();  // nobody leaves while a neighbour may still read its shared memory
     EINX_TRACE(125);
 }
 
-template <int R, bool SMEM>
-int launch_detect(einx_ctx* ctx, const DetectParams& P, size_t smem, cudaStream_t stream) {
-    auto kern = detect_kernel<R, SMEM>;
+template <int R, bool MULTI>
+int launch_nms(einx_ctx* ctx, const NmsParams& P, size_t smem, cudaStream_t stream) {
+    auto kern = nms_kernel<R, MULTI>;
     EINX_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(P.B * P.CS);
+    cfg.gridDim = dim3(P.B * P.T);
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = P.CS;
+    attr[0].val.clusterDim.x = P.T;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -762,7 +911,7 @@ int launch_detect(einx_ctx* ctx, const DetectParams& P, size_t smem, cudaStream_
         long long h[128];
         cudaStreamSynchronize(stream);
         cudaMemcpy(h, P.trace, sizeof(h), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[einx_detect trace] CS=%d smem=%zu:", P.CS, smem);
+        fprintf(stderr, "[einx_detect trace] T=%d smem=%zu:", P.T, smem);
         long long prev = h[0];
         for (int i = 0; i < 128; ++i)
             if (h[i]) { fprintf(stderr, " %d:+%lld", i, h[i] - prev); prev = h[i]; }
@@ -772,32 +921,32 @@ int launch_detect(einx_ctx* ctx, const DetectParams& P, size_t smem, cudaStream_
     return EINX_OK;
 }
 
-template <bool SMEM>
-int dispatch_radius(einx_ctx* ctx, int R, const DetectParams& P, size_t smem, cudaStream_t stream) {
+template <bool MULTI>
+int dispatch_radius(einx_ctx* ctx, int R, const NmsParams& P, size_t smem, cudaStream_t stream) {
     switch (R) {
-        case 0: return launch_detect<0, SMEM>(ctx, P, smem, stream);
-        case 1: return launch_detect<1, SMEM>(ctx, P, smem, stream);
-        case 2: return launch_detect<2, SMEM>(ctx, P, smem, stream);
-        case 3: return launch_detect<3, SMEM>(ctx, P, smem, stream);
-        case 4: return launch_detect<4, SMEM>(ctx, P, smem, stream);
-        case 5: return launch_detect<5, SMEM>(ctx, P, smem, stream);
-        case 6: return launch_detect<6, SMEM>(ctx, P, smem, stream);
-        case 7: return launch_detect<7, SMEM>(ctx, P, smem, stream);
-        case 8: return launch_detect<8, SMEM>(ctx, P, smem, stream);
+        case 0: return launch_nms<0, MULTI>(ctx, P, smem, stream);
+        case 1: return launch_nms<1, MULTI>(ctx, P, smem, stream);
+        case 2: return launch_nms<2, MULTI>(ctx, P, smem, stream);
+        case 3: return launch_nms<3, MULTI>(ctx, P, smem, stream);
+        case 4: return launch_nms<4, MULTI>(ctx, P, smem, stream);
+        case 5: return launch_nms<5, MULTI>(ctx, P, smem, stream);
+        case 6: return launch_nms<6, MULTI>(ctx, P, smem, stream);
+        case 7: return launch_nms<7, MULTI>(ctx, P, smem, stream);
+        case 8: return launch_nms<8, MULTI>(ctx, P, smem, stream);
     }
     return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_detect: nms_radius %d not in [0, 8]", R);
 }
 
+}  // namespace
+
 // fp32 emulation of q = (n-k)/n, rank = q*(n-1) (detector_util.py:113-124; torch divides an
 // int64 tensor by a Python int in fp32 and quantile scales q in the input dtype)
-void topk_ranks(int n, int k, int* lo, int* hi) {
+void einx_topk_ranks(int n, int k, int* lo, int* hi) {
     volatile float q = (float)(n - k) / (float)n;
     volatile float rank = q * (float)(n - 1);
     *lo = (int)floorf(rank);
     *hi = (int)ceilf(rank);
 }
-
-}  // namespace
 
 extern "C" int einx_detect(einx_ctx* ctx, float* score, const uint8_t* mask, int B, int Hp, int Wp, int nms_radius,
                            int border, float prob_thresh, int top_k, float* nms_map, float* kpts, int kcap,
@@ -809,81 +958,90 @@ extern "C" int einx_detect(einx_ctx* ctx, float* score, const uint8_t* mask, int
     if (B == 0) return EINX_OK;
     if (!score || !kpts || !counts) return einx_fail(ctx, EINX_ERR_INVALID, "einx_detect: NULL pointer argument");
     if ((long long)Hp * Wp > (1ll << 30)) return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_detect: map too large");
+    if (nms_radius > 8) return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_detect: nms_radius %d not in [0, 8]", nms_radius);
     DeviceGuard guard(ctx->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int R = nms_radius;
 
-    DetectParams P = {};
+    NmsParams P = {};
     P.score = score; P.mask = mask; P.nms_map = nms_map; P.kpts = kpts; P.counts = counts;
     P.B = B; P.Hp = Hp; P.Wp = Wp; P.border = border; P.kcap = kcap;
-    P.S = (Wp + 31) / 32;
     const int PAD = (R + 3) / 4 * 4;
-    P.WS = 32 * P.S + 2 * PAD;
-    P.magic_s = (unsigned)((0x100000000ull + P.S - 1) / P.S);
-    P.magic_ch = (unsigned)((0x100000000ull + 8 * P.S - 1) / (8 * P.S));
-    P.vec4 = (Wp % 4 == 0) && ((uintptr_t)score % 16 == 0) && (!mask || (uintptr_t)mask % 4 == 0);
+    P.W4 = (Wp + 3) / 4;
+    P.NCW = (P.W4 + 31) / 32;
+    P.WS = 4 * P.W4 + 2 * PAD;
+    P.SB = 4 * P.NCW + 2;
+    P.vec = (Wp % 4 == 0 && (uintptr_t)score % 16 == 0 && (!nms_map || (uintptr_t)nms_map % 16 == 0)) ? 4
+            : (Wp % 2 == 0 && (uintptr_t)score % 8 == 0) ? 2 : 1;
     P.prob_thresh = prob_thresh;
     const int n = Hp * Wp;
     if (top_k > 0) {
         if (top_k >= n) P.use_topk = 2;
-        else { P.use_topk = 1; topk_ranks(n, top_k, &P.rank_lo, &P.rank_hi); }
+        else { P.use_topk = 1; einx_topk_ranks(n, top_k, &P.rank_lo, &P.rank_hi); }
     }
     P.scap = R == 0 ? n : ((Hp + R) / (R + 1)) * ((Wp + R) / (R + 1));
 
-    // pick the cluster size: smallest that fits the band (values, row maxima, three bitmaps) in
-    // shared memory, then widen while the machine would otherwise sit idle
+    // Bands per image: the smallest cluster whose band (values, two bitmaps, list buffer) fits one CTA's shared
+    // memory; then wider while even two such launches side by side (the two sides of a pair run on concurrent
+    // streams) leave SMs idle.  Bands of a cluster are at least 2R rows, so a row has at most two copies.
     const size_t fixed = align_up(sizeof(Shared), 16);
-    const size_t row_bytes = (size_t)P.WS * 4 + (size_t)P.S * 32 * 4 + (size_t)P.S * 12;
-    auto smem_for = [&](int rb) { return fixed + row_bytes * (size_t)(rb + 2 * R); };
     const size_t budget = (size_t)ctx->max_smem_optin;
-    int CS = 0;
-    for (int c = 1; c <= kMaxCluster; ++c) {
-        const int rb = (Hp + c - 1) / c;
-        if (c > 1 && Hp / c < (R > 0 ? R : 1)) break;
-        if ((long long)(rb + 2 * R) * 8 * P.S >= (1 << 20)) continue;  // magic-number division range
-        if (smem_for(rb) <= budget) { CS = c; break; }
+    auto band_cap = [&](int rb) {  // maxima a band can hold (the new-maxima list of a dense round) -- R > 0
+        return R == 0 ? 0 : ((rb + R) / (R + 1) + 1) * ((Wp + R) / (R + 1));
+    };
+    // list buffer: at least the new maxima a dense round can produce; beyond that, a larger buffer means an
+    // earlier switch to sparse rounds (half of it is the worklist capacity)
+    auto smem_for = [&](int rb, int lc) {
+        return fixed + (size_t)(rb + 2 * R) * ((size_t)P.WS * 4 + (size_t)P.SB * 8) + (size_t)lc * 4;
+    };
+    auto list_entries = [&](int rb) {  // 0: the band does not fit
+        for (int want = 4096; want >= 1024; want >>= 1) {
+            int lc = band_cap(rb) > want ? band_cap(rb) : want;
+            lc += lc & 1;
+            if (smem_for(rb, lc) <= budget) return lc;
+        }
+        return 0;
+    };
+    const char* force_env = getenv("EINX_DETECT_CLUSTER");  // testing aid: bands per image (read per call)
+    const int force_t = force_env ? atoi(force_env) : 0;
+    int T = 0;
+    for (int t = 1; t <= kMaxCluster; ++t) {
+        if (force_t > 0 && t != force_t) continue;
+        const int rb = (Hp + t - 1) / t;
+        if (t > 1 && Hp / t < 2 * (R > 0 ? R : 1)) break;
+        if (rb + 2 * R >= 32768 || Wp >= 65536) break;  // worklist entries pack (row << 16 | x), bit 31 = flag
+        if (list_entries(rb) > 0) { T = t; break; }
     }
-    bool use_smem = CS > 0;
-    if (use_smem) {
-        while (CS * 2 <= kMaxCluster && (long long)B * CS * 2 <= ctx->num_sms && Hp / (CS * 2) >= 2 * (R > 0 ? R : 1) + 8) CS *= 2;
-    } else {
-        CS = kMaxCluster;
-        while (CS > 1 && Hp / CS < (R > 0 ? R : 1)) CS /= 2;
-    }
-    P.CS = CS;
-    P.RBmax = (Hp + CS - 1) / CS;
-    if ((long long)(P.RBmax + 2 * R) * 8 * P.S >= (1 << 20))
-        return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_detect: %dx%d map too large for one cluster", Hp, Wp);
+    if (T == 0)  // no cluster of bands holds the map in shared memory: L2-resident variant
+        return einx_detect_large(ctx, score, mask, B, Hp, Wp, nms_radius, border, prob_thresh, top_k, nms_map, kpts, kcap,
+                                 counts, stream_);
+    if (force_t <= 0)
+        while (T * 2 <= kMaxCluster && (long long)B * T * 2 * 2 <= ctx->num_sms && Hp / (T * 2) >= 2 * (R > 0 ? R : 1) + 8) T *= 2;
+    P.T = T;
+    P.RB = (Hp + T - 1) / T;
+    P.LC = list_entries(P.RB);
+    if (P.LC == 0) return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_detect: %dx%d band does not fit shared memory", P.RB, Wp);
+    // sweep runs: NSEG x NCW units over the warps of a CTA
+    P.NSEG = kWarps / P.NCW > 0 ? kWarps / P.NCW : 1;
+    if (P.NSEG > P.RB) P.NSEG = P.RB;
+    P.SR = (P.RB + P.NSEG - 1) / P.NSEG;
+    // survivor lists of the tail: shared-memory scratch (UB + list buffer) when a single CTA owns the image
+    const size_t scratch = (size_t)(P.RB + 2 * R) * P.SB * 4 + (size_t)P.LC * 4;
+    P.tail_smem = (T == 1 && (size_t)P.scap * 8 <= scratch) ? 1 : 0;
 
-    // workspace: survivor lists (+ padded global image, row maxima and bitmaps for the large-map variant)
     const size_t list_bytes = align_up((size_t)B * P.scap * 4, 256);
-    P.wl_smem = use_smem && (size_t)(P.RBmax + 2 * R) * P.S * 32 * 4 >= (size_t)2 * kWorklistCap * 4;
-    const size_t wl_bytes = P.wl_smem ? 0 : align_up((size_t)B * CS * 2 * kWorklistCap * 4, 256);
-    size_t ws_bytes = 2 * list_bytes + wl_bytes;
-    const size_t img_rows = (size_t)Hp + 2 * R;
-    const size_t gv_bytes = align_up((size_t)B * img_rows * P.WS * 4, 256);
-    const size_t gh_bytes = align_up((size_t)B * img_rows * P.S * 32 * 4, 256);
-    const size_t gw_bytes = align_up((size_t)B * img_rows * P.S * 4, 256);
-    if (!use_smem) ws_bytes += gv_bytes + gh_bytes + 3 * gw_bytes;
-    int rc = einx_ws_reserve(ctx, ws_bytes);
+    int rc = einx_ws_reserve(ctx, P.tail_smem ? 256 : 2 * list_bytes);
     if (rc) return rc;
     unsigned char* ws = (unsigned char*)ctx->ws;
     P.surv_val = (float*)ws;
     P.surv_idx = (int32_t*)(ws + list_bytes);
-    P.worklists = (unsigned int*)(ws + 2 * list_bytes);
     static const bool want_trace = getenv("EINX_DETECT_TRACE") != nullptr;
     if (want_trace) {
         static long long* trace_buf = nullptr;
         if (!trace_buf && cudaMalloc(&trace_buf, 128 * sizeof(long long)) == cudaSuccess) cudaMemset(trace_buf, 0, 128 * sizeof(long long));
         P.trace = trace_buf;
     }
-    if (use_smem) return dispatch_radius<true>(ctx, R, P, smem_for(P.RBmax), stream);
-    unsigned char* g = ws + 2 * list_bytes + wl_bytes;
-    P.gV = (float*)g;
-    P.gLM = (uint32_t*)(g + gv_bytes);
-    P.gRD = (uint32_t*)(g + gv_bytes + gw_bytes);
-    P.gPS = (uint32_t*)(g + gv_bytes + 2 * gw_bytes);
-    P.gH = (float*)(g + gv_bytes + 3 * gw_bytes);
-    EINX_CUDA(ctx, cudaMemsetAsync(P.gV, 0, gv_bytes + 3 * gw_bytes, stream));  // zero padding, empty bitmaps
-    return dispatch_radius<false>(ctx, R, P, fixed, stream);
+    const size_t smem = smem_for(P.RB, P.LC);
+    if (T == 1) return dispatch_radius<false>(ctx, R, P, smem, stream);
+    return dispatch_radius<true>(ctx, R, P, smem, stream);
 }

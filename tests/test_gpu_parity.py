@@ -191,6 +191,75 @@ def test_detect_vs_oracle_config_sizes(einx, synth, B, Hp, Wp, k, kind):
         assert d.min() > 4
 
 
+def _smooth_map(rng, B, Hp, Wp, sigma):
+    from scipy.ndimage import gaussian_filter
+
+    v = np.stack([gaussian_filter(rng.random((Hp, Wp)), sigma) for _ in range(B)])
+    v = (v - v.min()) / (v.max() - v.min())
+    return v[:, None].astype(np.float32)
+
+
+@pytest.mark.parametrize("bands", [0, 1, 2, 3, 4, 8])
+@pytest.mark.parametrize("B,Hp,Wp,k,kind", [(2, 184, 240, 1024, "uniform"), (2, 184, 240, 1024, "ties"),
+                                            (2, 184, 240, 500, "smooth"), (3, 130, 346, 700, "uniform"),
+                                            (2, 100, 70, 64, "smooth")])
+def test_detect_every_cluster_size(einx, synth, monkeypatch, bands, B, Hp, Wp, k, kind):
+    """The single-CTA kernel and every cluster split (bands exchange their edge rows over DSMEM) give the oracle's
+    bits; smooth maps need 10+ rounds, most of them dense, ties exercise the first-occurrence rule."""
+    rng = np.random.default_rng(bands * 131 + Hp + k)
+    m = _smooth_map(rng, B, Hp, Wp, 5.0) if kind == "smooth" else synth.score_map(rng, B, Hp, Wp, kind)
+    if bands:
+        monkeypatch.setenv("EINX_DETECT_CLUSTER", str(bands))
+    src = cuda(m)
+    nms, kpts, counts = einx.detect(src, 1.0, 4, 4, k, want_map=True)
+    ref_in = m.copy()
+    ref = O.prob_map_to_points_map(ref_in, 1.0, 4, 4, k)
+    assert np.array_equal(src.cpu().numpy(), ref_in)
+    assert np.array_equal(nms.cpu().numpy(), ref)
+    pos = O.prob_map_to_positions_with_prob(ref)
+    counts, kp = counts.cpu().numpy(), kpts.cpu().numpy()
+    for i in range(B):
+        assert counts[i] == len(pos[i])
+        assert np.array_equal(kp[i, : counts[i]], pos[i])
+
+
+@pytest.mark.parametrize("r", [0, 1, 2, 3, 5, 6, 7, 8])
+@pytest.mark.parametrize("bands", [0, 2])
+def test_detect_other_radii(einx, synth, monkeypatch, r, bands):
+    rng = np.random.default_rng(50 + r)
+    B, Hp, Wp = 2, 120, 150  # width not a multiple of 4: two-pixel global accesses
+    m = synth.score_map(rng, B, Hp, Wp, "ties" if r % 2 else "uniform")
+    if bands:
+        monkeypatch.setenv("EINX_DETECT_CLUSTER", str(bands))
+    src = cuda(m)
+    nms, kpts, counts = einx.detect(src, 0.3, r, 3, None, want_map=True)
+    ref_in = m.copy()
+    ref = O.prob_map_to_points_map(ref_in, 0.3, r, 3, None)
+    assert np.array_equal(src.cpu().numpy(), ref_in)
+    assert np.array_equal(nms.cpu().numpy(), ref)
+    pos = O.prob_map_to_positions_with_prob(ref)
+    for i in range(B):
+        assert int(counts[i]) == len(pos[i])
+        assert np.array_equal(kpts[i, : int(counts[i])].cpu().numpy(), pos[i])
+
+
+def test_detect_full_batch_single_cta(einx, synth):
+    """Batch 64 of EC-size maps: one image per CTA (the bench configuration), odd width variant included."""
+    rng = np.random.default_rng(64)
+    for Hp, Wp, k in ((184, 240, 1024), (91, 133, 200)):
+        m = synth.score_map(rng, 64, Hp, Wp)
+        m[5] = 0
+        m[6, :, : Hp // 2] = 0
+        src = cuda(m)
+        _, kpts, counts = einx.detect(src, 1.0, 4, 4, k, want_map=False)
+        ref = O.prob_map_to_points_map(m.copy(), 1.0, 4, 4, k)
+        pos = O.prob_map_to_positions_with_prob(ref)
+        counts, kp = counts.cpu().numpy(), kpts.cpu().numpy()
+        for i in range(64):
+            assert counts[i] == len(pos[i]), (Hp, i)
+            assert np.array_equal(kp[i, : counts[i]], pos[i]), (Hp, i)
+
+
 def test_detect_mask_and_positions_generic(einx, synth):
     rng = np.random.default_rng(3)
     m = synth.score_map(rng, 2, 96, 128)
