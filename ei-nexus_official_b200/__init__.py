@@ -8,7 +8,7 @@ without an sm_100a device.
 from . import _lib
 from ._lib import EinxError, context_for, contexts_of, launch_count
 from .describe import sample, sparsify_full_resolution_descriptors, sparsify_low_resolution_descriptors
-from .detection import (depth_to_space, detect, events_mask, logits_to_prob, logits_to_score, prob_map_to_points_map,
+from .detection import (depth_to_space, detect, detect_pair, events_mask, logits_to_prob, logits_to_score, prob_map_to_points_map,
                         prob_map_to_positions_with_prob)
 from .dist import gather_matches, pack_matches, shard_range
 from .match import NearestNeighborMatcher, filter_matches, mnn, mnn_dense, sigmoid_log_double_softmax
@@ -20,7 +20,7 @@ from .voxel import (draw_events_accumulation_image, event_stack_device, events_i
 
 __all__ = [
     "EinxError", "context_for", "contexts_of", "launch_count", "events_to_voxel_grid", "time_normalization", "pack_events", "voxelize_batch",
-    "voxelize_device", "detect", "prob_map_to_points_map", "prob_map_to_positions_with_prob", "sample",
+    "voxelize_device", "detect", "detect_pair", "prob_map_to_points_map", "prob_map_to_positions_with_prob", "sample",
     "sparsify_full_resolution_descriptors", "sparsify_low_resolution_descriptors", "NearestNeighborMatcher",
     "mnn", "mnn_dense", "ExtractMatchPipeline", "CapturedStep", "HostBatch", "HostStreamer", "PathConfig", "patch_reference", "shard_range", "pack_matches",
     "gather_matches", "logits_to_prob", "depth_to_space", "logits_to_score", "events_mask",

@@ -24,6 +24,8 @@ SIGNATURES = {
     "einx_voxelize": (C.c_int, [c_ctx, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "einx_detect": (C.c_int, [c_ctx, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                               _P, _P, C.c_int, _P, _P]),
+    "einx_detect_pair": (C.c_int, [c_ctx, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                   _P, _P, _P, _P, C.c_int, _P, _P, _P]),
     "einx_sample": (C.c_int, [c_ctx, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P,
                               C.c_int, C.c_float, C.c_int, _P, _P]),
     "einx_mnn": (C.c_int, [c_ctx, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,

@@ -43,13 +43,17 @@ constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxCluster = 8;
 
-struct NmsParams {
+struct NmsSide {   // one batch of maps and its outputs
     float* score;
     const uint8_t* mask;
     float* nms_map;
     float* kpts;
     int32_t* counts;
-    int B, Hp, Wp, border, kcap;
+};
+
+struct NmsParams {
+    NmsSide side[2];  // images [0, Bsplit) belong to side[0], [Bsplit, B) to side[1] (the two sides of a batch of pairs)
+    int B, Bsplit, Hp, Wp, border, kcap;
     int T;        // CTAs (row bands) per image
     int W4;       // float4 column groups per row: ceil(Wp / 4)
     int NCW;      // warps across a row: ceil(W4 / 32)
@@ -76,12 +80,11 @@ struct NmsParams {
 
 struct Shared {
     int und;        // undecided pixels in own rows, exact
-    int n_new[2];   // new maxima appended by the dense pass of round k -> n_new[k & 1]
-    int wl_n[2];    // worklist lengths (two halves of the list buffer)
+    int wl_n[2];    // worklist length after the compaction of a sparse round
     int xcnt[2];
     int warp_scan[kWarps + 1];
-    unsigned int hist[256];
-    unsigned int sel_prefix, sel_rank, sel_min, sel_cnt;
+    unsigned int hist[4][256];  // one per radix pass of the threshold selection
+    unsigned int sel_min, sel_cnt;
 };
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }  // one FMNMX3
@@ -133,8 +136,9 @@ __device__ __forceinline__ int block_excl_scan(int v, int* scratch, int& total) 
     return inc - v + scratch[warp];
 }
 
-// j-th smallest (0-based) of the positive floats in list[0..n) via 4 radix passes on their bit
-// patterns, then the next order statistic; every thread returns the same (a, b).
+// j-th smallest (0-based) of the positive floats in list[0..n) via 4 radix passes on their bit patterns, then the
+// next order statistic; every thread returns the same (a, b).  One histogram per pass (zeroed by the caller long
+// before) and every warp locating the bin for itself: a pass costs one barrier.
 template <bool GLOBAL>
 __device__ __forceinline__ float list_ld(const float* list, int i) {
     return GLOBAL ? __ldcg(list + i) : list[i];  // global lists are written by other CTAs of the cluster: L2 only
@@ -142,7 +146,7 @@ __device__ __forceinline__ float list_ld(const float* list, int i) {
 
 template <bool GLOBAL>
 __device__ void select_two(const float* list, int n, int j, bool need_next, Shared& sh, float& a_out, float& b_out) {
-    if (threadIdx.x == 0) { sh.sel_prefix = 0; sh.sel_rank = (unsigned)j; }
+    const int lane = threadIdx.x & 31;
     constexpr int kHeld = 8;  // the usual list (a few thousand survivors) is read once and kept in registers
     const bool held = n <= kHeld * kThreads;
     unsigned ev[kHeld];
@@ -151,61 +155,54 @@ __device__ void select_two(const float* list, int n, int j, bool need_next, Shar
         const int i = threadIdx.x + u * kThreads;
         ev[u] = (held && i < n) ? __float_as_uint(list_ld<GLOBAL>(list, i)) : 0u;
     }
-    unsigned mask = 0;
-    for (int shift = 24; shift >= 0; shift -= 8) {
-        for (int i = threadIdx.x; i < 256; i += kThreads) sh.hist[i] = 0;
-        __syncthreads();
-        const unsigned prefix = sh.sel_prefix;
+    unsigned mask = 0, prefix = 0, rank = (unsigned)j;
+#pragma unroll 1
+    for (int p = 0; p < 4; ++p) {
+        const int shift = 24 - 8 * p;
+        unsigned int* hist = sh.hist[p];
         if (held) {
 #pragma unroll
             for (int u = 0; u < kHeld; ++u) {
+                if (u * kThreads >= n) break;  // uniform
                 const bool in = threadIdx.x + u * kThreads < n && (ev[u] & mask) == prefix;
                 // warp-aggregate equal digits (score values share their exponent byte): one atomic per distinct digit
                 const unsigned digit = (ev[u] >> shift) & 255u;
                 const unsigned peers = __match_any_sync(0xffffffffu, in ? digit : 0x100u);
-                if (in && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sh.hist[digit], (unsigned)__popc(peers));
+                if (in && (int)(__ffs(peers) - 1) == lane) atomicAdd(&hist[digit], (unsigned)__popc(peers));
             }
         } else {
             for (int i = threadIdx.x; i < n; i += kThreads) {
                 const unsigned e = __float_as_uint(list_ld<GLOBAL>(list, i));
-                if ((e & mask) == prefix) atomicAdd(&sh.hist[(e >> shift) & 255u], 1u);
+                if ((e & mask) == prefix) atomicAdd(&hist[(e >> shift) & 255u], 1u);
             }
         }
         __syncthreads();
-        if (threadIdx.x < 32) {
-            // warp 0 locates the bin holding rank r: 8 bins per lane, warp prefix, then a short scan
-            const unsigned r = sh.sel_rank;
-            unsigned c[8], mine = 0;
+        // the bin holding `rank`: 8 bins per lane, warp prefix, then a short scan (every warp, same result)
+        unsigned c[8], mine = 0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { c[k] = sh.hist[threadIdx.x * 8 + k]; mine += c[k]; }
-            unsigned inc = mine;
+        for (int k = 0; k < 8; ++k) { c[k] = hist[lane * 8 + k]; mine += c[k]; }
+        unsigned inc = mine;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned nn = __shfl_up_sync(0xffffffffu, inc, o);
-                if ((int)threadIdx.x >= o) inc += nn;
-            }
-            const unsigned before = inc - mine;
-            const bool here = (before <= r) && (r < inc);  // exactly one lane (r < total count)
-            if (here) {
-                unsigned cum = before;
-                int bin = 0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    if (cum + c[k] <= r) { cum += c[k]; bin = k + 1; }
-                    else break;
-                }
-                sh.sel_rank = r - cum;
-                sh.sel_prefix = prefix | ((unsigned)(threadIdx.x * 8 + bin) << shift);
-            }
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned nn = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += nn;
         }
+        const unsigned before = inc - mine;
+        const bool here = (before <= rank) && (rank < inc);  // exactly one lane (rank < total count)
+        unsigned cum = before;
+        int bin = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (cum + c[k] <= rank && bin == k) { cum += c[k]; bin = k + 1; }
+        }
+        const unsigned src = __ffs(__ballot_sync(0xffffffffu, here)) - 1;
+        rank = __shfl_sync(0xffffffffu, rank - cum, src);
+        prefix |= __shfl_sync(0xffffffffu, (unsigned)(lane * 8 + bin), src) << shift;
         mask |= 255u << shift;
-        __syncthreads();
     }
-    const unsigned abits = sh.sel_prefix;
+    const unsigned abits = prefix;
     float a = __uint_as_float(abits), b = a;
     if (need_next) {
-        if (threadIdx.x == 0) { sh.sel_min = 0xffffffffu; sh.sel_cnt = 0; }
-        __syncthreads();
         unsigned cnt = 0, mn = 0xffffffffu;
         if (held) {
 #pragma unroll
@@ -223,15 +220,14 @@ __device__ void select_two(const float* list, int n, int j, bool need_next, Shar
         }
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         mn = __reduce_min_sync(0xffffffffu, mn);
-        if ((threadIdx.x & 31) == 0) {
-            atomicAdd(&sh.sel_cnt, cnt);
+        if (lane == 0) {
+            if (cnt) atomicAdd(&sh.sel_cnt, cnt);
             atomicMin(&sh.sel_min, mn);
         }
         __syncthreads();
         // the (j+1)-th smallest equals a when a is duplicated past position j
         b = (sh.sel_cnt > (unsigned)j + 1u) ? a : __uint_as_float(sh.sel_min);
     }
-    __syncthreads();
     a_out = a;
     b_out = b;
 }
@@ -287,9 +283,12 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
     cg::cluster_group cluster = cg::this_cluster();
     const int T = MULTI ? P.T : 1;
     const int rank = MULTI ? (int)cluster.block_rank() : 0;
-    const int b = blockIdx.x / T;
+    const int bg = blockIdx.x / T;                         // image of the launch
+    const NmsSide& S = P.side[bg >= P.Bsplit ? 1 : 0];
+    const int b = bg >= P.Bsplit ? bg - P.Bsplit : bg;    // image of its side
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int WS = P.WS, SB = P.SB, Hp = P.Hp, Wp = P.Wp, W4 = P.W4, NCW = P.NCW;
+    const int WS = P.WS, SB = P.SB, SW = P.SB - 2, Hp = P.Hp, Wp = P.Wp, W4 = P.W4, NCW = P.NCW;
+    EINX_TRACE(0);
 
     // balanced row bands
     const int base_rows = Hp / T, rem = Hp % T;
@@ -302,7 +301,8 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
-    // Local row l of every array is image row ys - R + l: own rows are l in [R, R + nrows).
+    // Local row l of every array is image row ys - R + l: own rows are l in [R, R + nrows).  Bitmap rows have one
+    // zero word on either side (pixel x is bit x & 31 of word 1 + (x >> 5)), so windows never index out of a row.
     const int lrows = P.RB + 2 * R;
     size_t so = align_up(sizeof(Shared), 16);
     float* const V = reinterpret_cast<float*>(smem_raw + so);
@@ -311,28 +311,33 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
     so += sizeof(uint32_t) * (size_t)lrows * SB;
     uint32_t* const UB = reinterpret_cast<uint32_t*>(smem_raw + so);
     so += sizeof(uint32_t) * (size_t)lrows * SB;
+    // dense rounds: one more bitmap plane (candidates of the sweep, then the horizontally dilated maxima);
+    // sparse rounds: the worklist; tail: the survivor lists (together with UB, dead by then)
     unsigned int* const list = reinterpret_cast<unsigned int*>(smem_raw + so);
+    uint32_t* const XB = reinterpret_cast<uint32_t*>(list);   // dilated maxima, [local row][word]
+    uint32_t* const CB = XB;                                   // candidates, [8-row block of own rows][column group]
+    const int CBW = 32 * NCW;
     const uint32_t V_s = (uint32_t)__cvta_generic_to_shared(V);
     // neighbours' arrays (same offsets in their shared memory)
     float *Vup = nullptr, *Vdn = nullptr;
-    uint32_t *UBup = nullptr, *UBdn = nullptr;
-    int *und_up = nullptr, *und_dn = nullptr;
+    uint32_t *UBup = nullptr, *UBdn = nullptr, *LMup = nullptr, *LMdn = nullptr;
     if (MULTI) {
         if (rank > 0) {
             Vup = cluster.map_shared_rank(V, rank - 1);
             UBup = cluster.map_shared_rank(UB, rank - 1);
-            und_up = cluster.map_shared_rank(&sh.und, rank - 1);
+            LMup = cluster.map_shared_rank(LM, rank - 1);
         }
         if (rank < T - 1) {
             Vdn = cluster.map_shared_rank(V, rank + 1);
             UBdn = cluster.map_shared_rank(UB, rank + 1);
-            und_dn = cluster.map_shared_rank(&sh.und, rank + 1);
+            LMdn = cluster.map_shared_rank(LM, rank + 1);
         }
     }
 
     // ---- load the band: border + mask zeroing (in place on `score`), zero padding, UB bits -------- //
-    for (int i = tid; i < lrows * SB; i += kThreads) { LM[i] = 0u; UB[i] = 0u; }
-    if (tid == 0) { sh.und = 0; sh.n_new[0] = sh.n_new[1] = 0; sh.wl_n[0] = sh.wl_n[1] = 0; sh.xcnt[0] = sh.xcnt[1] = 0; }
+    for (int i = tid; i < lrows * SB; i += kThreads) { LM[i] = 0u; UB[i] = 0u; XB[i] = 0u; }  // (XB: its pad words stay zero)
+    if (tid == 0) { sh.und = 0; sh.wl_n[0] = sh.wl_n[1] = 0; sh.xcnt[0] = sh.xcnt[1] = 0; sh.sel_min = 0xffffffffu; sh.sel_cnt = 0; }
+    for (int i = tid; i < 4 * 256; i += kThreads) (&sh.hist[0][0])[i] = 0u;
     // zero pads of every row: PAD floats on the left, PAD on the right
     if constexpr (PAD > 0) {
         constexpr int PF = PAD / 2;  // float4 per row
@@ -343,127 +348,124 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
             *reinterpret_cast<float4*>(rowp + off) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
-    __syncthreads();
     {
-        float* simg = P.score + (size_t)b * Hp * Wp;
-        const uint8_t* mimg = P.mask ? P.mask + (size_t)b * Hp * Wp : nullptr;
+        // Phase 1: the whole band goes from global to shared memory as asynchronous copies (cp.async, 4 * vec bytes
+        // each, no register staging), all in flight at once -- one memory latency for the band instead of one per
+        // batch of rows.  Rows outside the image and the columns beyond Wp are zero-filled by plain stores.
+        const float* simg = S.score + (size_t)b * Hp * Wp;
+        const int vec = P.vec;
+        const int cpr = Wp / vec;                 // copies per row (Wp % vec == 0)
+        const int y_lo = max(0, R - ys), y_hi = min(L, Hp - ys + R);  // local rows inside the image: [y_lo, y_hi)
+        for (int i = tid; i < (y_hi - y_lo) * cpr; i += kThreads) {
+            const int lr = i / cpr, c = i - lr * cpr;
+            const int l = y_lo + lr, x = c * vec;
+            const float* src = simg + (size_t)(ys - R + l) * Wp + x;
+            const uint32_t dst = V_s + 4u * (uint32_t)(l * WS + PAD + x);
+            if (vec == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            else if (vec == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+            else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const int tailc = 4 * W4 - Wp;            // columns between Wp and the float4 boundary (0..3)
+        for (int i = tid; i < L * W4; i += kThreads) {
+            const int l = i / W4, g = i - l * W4;
+            if (l < y_lo || l >= y_hi) *reinterpret_cast<float4*>(V + (size_t)l * WS + PAD + 4 * g) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (tailc > 0)
+            for (int i = tid; i < (y_hi - y_lo) * tailc; i += kThreads) {
+                const int lr = i / tailc, c = i - lr * tailc;
+                V[(size_t)(y_lo + lr) * WS + PAD + Wp + c] = 0.0f;
+            }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    EINX_TRACE(1);
+    {
+        // Phase 2, over shared memory: border frame and mask (written back to `score` where they change a pixel)
+        // and the bitmap of positive pixels.  A warp owns a fixed run of 128 columns, so its border-column test is
+        // loop invariant, and walks the rows of the band.
+        float* simg = S.score + (size_t)b * Hp * Wp;
+        const uint8_t* mimg = S.mask ? S.mask + (size_t)b * Hp * Wp : nullptr;
         const int bd = P.border;
-        const int vec = P.vec;                       // pixels per lane and access
-        const int gl = 32 / vec;                     // lanes per bitmap word
-        const int tasks_per_row = (4 * W4 + 32 * vec - 1) / (32 * vec);
+        const int wpr = min(NCW, kWarps);            // warps side by side on a row
+        const int lstep = kWarps / wpr;              // rows walked in parallel
         int cnt = 0;
-        for (int t = warp; t < L * tasks_per_row; t += kWarps) {
-            const int l = t / tasks_per_row, cw = t - l * tasks_per_row;
-            const int y = ys - R + l;
-            const bool own = l >= R && l < R + nrows;
-            const bool rowin = y >= 0 && y < Hp;
-            const bool rowkill = (y < bd) | (y >= Hp - bd);
-            const int x = (cw * 32 + lane) * vec;
-            float* srow = simg + (size_t)(rowin ? y : 0) * Wp;
-            const uint8_t* mrow = mimg ? mimg + (size_t)(rowin ? y : 0) * Wp : nullptr;
-            float e[4] = {0.f, 0.f, 0.f, 0.f};
-            const bool in = rowin && x < Wp;
-            if (in) {
-                if (vec == 4) {
-                    const float4 q = *reinterpret_cast<const float4*>(srow + x);
-                    e[0] = q.x; e[1] = q.y; e[2] = q.z; e[3] = q.w;
-                } else if (vec == 2) {
-                    const float2 q = *reinterpret_cast<const float2*>(srow + x);
-                    e[0] = q.x; e[1] = q.y;
-                } else {
-                    e[0] = srow[x];
-                }
-                bool changed = false;
+        if (warp < wpr * lstep) {
+            for (int cw = warp % wpr; cw < NCW; cw += wpr) {
+                const int g = cw * 32 + lane, x = 4 * g;
+                const bool in_s = g < W4;
+                unsigned colkill = 0, inimg = 0;  // border columns / columns inside the image among this lane's 4 pixels
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    if (j < vec) {
-                        const int xx = x + j;
-                        bool kill = rowkill | (xx < bd) | (xx >= Wp - bd);
-                        if (mrow) kill |= (mrow[xx] == 0);
-                        if (kill) {
-                            changed |= (e[j] != 0.0f);
-                            e[j] = 0.0f;
+                    if ((x + j) < bd || (x + j) >= Wp - bd) colkill |= 1u << j;
+                    if (x + j < Wp) inimg |= 1u << j;
+                }
+                for (int l = warp / wpr; l < L; l += lstep) {
+                    const int y = ys - R + l;
+                    const bool own = l >= R && l < R + nrows;
+                    const bool rowin = y >= 0 && y < Hp;
+                    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float* vrow = V + (size_t)l * WS + PAD + x;
+                    if (in_s && rowin) q = *reinterpret_cast<const float4*>(vrow);
+                    float e[4] = {q.x, q.y, q.z, q.w};
+                    unsigned kill = ((y < bd) | (y >= Hp - bd)) ? 0xfu : colkill;
+                    if (mimg && rowin && in_s) {
+                        const uint8_t* mrow = mimg + (size_t)y * Wp + x;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if ((inimg & (1u << j)) && mrow[j] == 0) kill |= 1u << j;
+                    }
+                    unsigned nz = 0, bits = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (e[j] != 0.0f) nz |= 1u << j;
+                        if (e[j] > 0.0f) bits |= 1u << j;
+                    }
+                    bits &= ~kill;
+                    if (nz & kill) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (kill & (1u << j)) e[j] = 0.0f;
+                        *reinterpret_cast<float4*>(vrow) = make_float4(e[0], e[1], e[2], e[3]);
+                        if (own) {  // the band that owns the row writes the zeroed frame / mask back
+                            float* srow = simg + (size_t)y * Wp + x;
+                            if (P.vec == 4) {
+                                *reinterpret_cast<float4*>(srow) = make_float4(e[0], e[1], e[2], e[3]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (nz & kill & (1u << j)) srow[j] = 0.0f;
+                            }
                         }
                     }
-                }
-                if (changed && own) {  // the band that owns the row writes the zeroed frame / mask back
-                    if (vec == 4) *reinterpret_cast<float4*>(srow + x) = make_float4(e[0], e[1], e[2], e[3]);
-                    else if (vec == 2) *reinterpret_cast<float2*>(srow + x) = make_float2(e[0], e[1]);
-                    else srow[x] = e[0];
+                    if (own) cnt += __popc(bits);
+                    unsigned word = bits << (4 * (lane & 7));
+                    word |= __shfl_xor_sync(0xffffffffu, word, 1);
+                    word |= __shfl_xor_sync(0xffffffffu, word, 2);
+                    word |= __shfl_xor_sync(0xffffffffu, word, 4);
+                    if ((lane & 7) == 0 && in_s) UB[(size_t)l * SB + 1 + (x >> 5)] = word;
                 }
             }
-            unsigned bits = 0;
-            if (x < 4 * W4) {
-                float* vrow = V + (size_t)l * WS + PAD + x;
-                if (vec == 4) *reinterpret_cast<float4*>(vrow) = make_float4(e[0], e[1], e[2], e[3]);
-                else if (vec == 2) *reinterpret_cast<float2*>(vrow) = make_float2(e[0], e[1]);
-                else vrow[0] = e[0];
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (j < vec && e[j] > 0.0f) bits |= 1u << j;
-            }
-            if (own) cnt += __popc(bits);
-            unsigned word = bits << (vec * (lane & (gl - 1)));
-            for (int o = 1; o < gl; o <<= 1) word |= __shfl_xor_sync(0xffffffffu, word, o);
-            if ((lane & (gl - 1)) == 0 && x < 4 * W4) UB[(size_t)l * SB + 1 + (x >> 5)] = word;
         }
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         if (lane == 0 && cnt) atomicAdd(&sh.und, cnt);
     }
-    EINX_TRACE(0);
+    EINX_TRACE(126);
 
     // ---- NMS rounds ------------------------------------------------------------------------ //
     auto sync_all = [&]() {
         if (MULTI) cluster.sync();
         else __syncthreads();
     };
-    // clear the window of a (new) maximum at column x in local row l2 of UB, in every copy of that row;
-    // returns the undecided bits this call cleared in the owner's copy, by owner (self / up / down)
-    auto clear_window = [&](int l2, int x, int& c_self, int& c_up, int& c_dn) {
-        const int xl = x - R + 32;
-        const int wi = xl >> 5, shf = xl & 31;
-        const unsigned long long m64 = (unsigned long long)kWinMask << shf;
-        const uint32_t lo = (uint32_t)m64, hi = (uint32_t)(m64 >> 32);
-        const bool mine = l2 >= R && l2 < R + nrows;
-        uint32_t* u = UB + (size_t)l2 * SB + wi;
-        uint32_t o0 = atomicAnd(u, ~lo), o1 = 0;
-        if (hi) o1 = atomicAnd(u + 1, ~hi);
-        if (mine) c_self += __popc(o0 & lo) + __popc(o1 & hi);
-        if (MULTI) {
-            const int lu = cp.up(l2, 2 * R), ld = cp.down(l2);
-            if (lu >= 0) {
-                uint32_t* ur = UBup + (size_t)lu * SB + wi;
-                o0 = atomicAnd(ur, ~lo);
-                o1 = hi ? atomicAnd(ur + 1, ~hi) : 0u;
-                if (l2 < R) c_up += __popc(o0 & lo) + __popc(o1 & hi);  // rows [0, R) belong to the band above
-            }
-            if (ld >= 0) {
-                uint32_t* ur = UBdn + (size_t)ld * SB + wi;
-                o0 = atomicAnd(ur, ~lo);
-                o1 = hi ? atomicAnd(ur + 1, ~hi) : 0u;
-                if (l2 >= R + nrows) c_dn += __popc(o0 & lo) + __popc(o1 & hi);
-            }
-        }
-    };
-    auto settle_counts = [&](int c_self, int c_up, int c_dn) {
-        c_self = __reduce_add_sync(0xffffffffu, c_self);
-        if (lane == 0 && c_self) atomicSub(&sh.und, c_self);
-        if (MULTI) {
-            c_up = __reduce_add_sync(0xffffffffu, c_up);
-            c_dn = __reduce_add_sync(0xffffffffu, c_dn);
-            if (lane == 0 && c_up) atomicSub(und_up, c_up);
-            if (lane == 0 && c_dn) atomicSub(und_dn, c_dn);
-        }
-    };
 
     if constexpr (R > 0) {
-        const int half = P.LC / 2;  // worklist capacity (two halves of the list buffer)
+        const int cap = min(P.LC, 8 * kThreads);   // worklist capacity (phase 3 holds 8 entries per thread)
         bool sparse = false;
-        int wl_cur = 0;
-        int trace_slot = 1;
+        int n_wl = 0;           // worklist length (sparse rounds; uniform in the CTA)
+        int trace_slot = 2;
         for (int round = 0;; ++round) {
-            sync_all();  // every band's und / V / UB is final for this round
-            trace_slot = round < 19 ? 1 + 6 * round : 126;
+            sync_all();  // every band's V / UB / LM / count is final for this round
+            trace_slot = round < 16 ? 2 + 7 * round : 126;
             EINX_TRACE(trace_slot); ++trace_slot;
             int tot = sh.und, mx = tot;
             if (MULTI) {
@@ -476,36 +478,34 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
             }
             if (tot == 0 || round > Hp + Wp) break;  // (the round bound only guards against a corrupted count: a
                                                      // round always decides at least one pixel)
-            if (!sparse && mx <= half) {
-                // build the worklist of undecided pixels of the own rows, raster order
+            if (!sparse && mx <= cap) {
+                // build the worklist of undecided pixels of the own rows, raster order; a thread takes a run of
+                // consecutive words so that one block scan places everything
                 sparse = true;
-                wl_cur = 0;
-                const int nwords = nrows * (SB - 2);
-                int run = 0;
-                for (int base = 0; base < nwords; base += kThreads) {
-                    const int wi = base + tid;
-                    int lr = 0, s = 0;
-                    uint32_t w = 0;
-                    if (wi < nwords) {
-                        lr = wi / (SB - 2);
-                        s = wi - lr * (SB - 2);
-                        w = UB[(size_t)(lr + R) * SB + 1 + s];
-                    }
-                    int totw;
-                    int pos = run + block_excl_scan(__popc(w), sh.warp_scan, totw);
+                const int nwords = nrows * SW;
+                const int per = (nwords + kThreads - 1) / kThreads;
+                const int w0 = tid * per, w1 = min(w0 + per, nwords);
+                int mine = 0;
+                for (int wi = w0; wi < w1; ++wi) {
+                    const int lr = wi / SW, s = wi - lr * SW;
+                    mine += __popc(UB[(size_t)(lr + R) * SB + 1 + s]);
+                }
+                int totw;
+                int pos = block_excl_scan(mine, sh.warp_scan, totw);
+                for (int wi = w0; wi < w1; ++wi) {
+                    const int lr = wi / SW, s = wi - lr * SW;
+                    uint32_t w = UB[(size_t)(lr + R) * SB + 1 + s];
                     while (w) {
                         const int bit = __ffs(w) - 1;
                         w &= w - 1;
                         list[pos++] = ((unsigned)(lr + R) << 16) | (unsigned)(32 * s + bit);
                     }
-                    run += totw;
                 }
-                if (tid == 0) { sh.wl_n[0] = run; sh.wl_n[1] = 0; }
+                n_wl = totw;
                 __syncthreads();
             }
             if (!sparse) {
-                // ---- dense pass: sweep, collect the new maxima ---------------------------------- //
-                int* const n_new = &sh.n_new[round & 1];
+                // ---- dense pass 1: sweep; pixels equal to their window maximum are candidates ------- //
                 const int nunits = NCW * P.NSEG;
                 for (int u = warp; u < nunits; u += kWarps) {
                     const int seg = u / NCW, cw = u - seg * NCW;
@@ -517,13 +517,13 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
                     // shared-window byte address of the leftmost float4 the thread reads in row a - R
                     uint32_t rp = V_s + 4u * (uint32_t)((a - R) * WS + 4 * (active ? g : W4 - 1));
                     const uint32_t row_bytes = 4u * (uint32_t)WS;
-                    float h[P2][4], p3[P2][4];
+                    // ring slot of a row = (row - (a - R)) mod P2: horizontal window maxima (h), the 3-row partial
+                    // maximum that ends with the row (p3 of the row two above) and the thread's own 4 pixels (cv)
+                    float h[P2][4], p3[P2][4], cv[P2][4];
 #pragma unroll
                     for (int j = 0; j < P2; ++j)
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) { h[j][c] = 0.0f; p3[j][c] = 0.0f; }
-                    // ring slot of a row = (row - (a - R)) mod P2.  Ingesting a row: its horizontal window maxima
-                    // (h) and the 3-row partial maximum that ends with it (p3 of the row two above).
+                        for (int c = 0; c < 4; ++c) { h[j][c] = 0.0f; p3[j][c] = 0.0f; cv[j][c] = 0.0f; }
                     auto ingest = [&](auto slot) {
                         constexpr int j = decltype(slot)::value;
                         constexpr int j1 = (j + P2 - 1) % P2, j2 = (j + P2 - 2) % P2;
@@ -533,14 +533,20 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
                             const float4 q = lds128(rp + 16u * k);
                             av[4 * k] = q.x; av[4 * k + 1] = q.y; av[4 * k + 2] = q.z; av[4 * k + 3] = q.w;
                         }
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) cv[j][c] = av[PAD + c];
                         hmax4<R>(av, h[j]);
 #pragma unroll
                         for (int c = 0; c < 4; ++c) p3[j2][c] = fmax3(h[j2][c], h[j1][c], h[j][c]);
                     };
-                    // Output row y = (row just ingested in slot j) - R: all of its window rows are in the ring.
+                    // Output row y = (row just ingested in slot j) - R: all of its window rows are in the ring.  A pixel
+                    // equal to its window maximum is a candidate unless the rows above already hold an equal value
+                    // (first-occurrence rule); candidates of 8 rows x 4 columns collect in one register.
+                    unsigned acc = 0;
                     auto emit = [&](auto slot, int y) {
                         constexpr int j = decltype(slot)::value;
                         constexpr int j2 = (j + P2 - 2) % P2;
+                        constexpr int jc = (j + P2 - R) % P2;          // slot of row y itself
                         float M[4];
 #pragma unroll
                         for (int c = 0; c < 4; ++c) M[c] = p3[j2][c];  // rows y+R-2 .. y+R
@@ -550,44 +556,45 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
 #pragma unroll
                             for (int c = 0; c < 4; ++c) M[c] = fmaxf(M[c], p3[ji][c]);
                         }
-                        const uint32_t cpa = rp - (uint32_t)R * row_bytes + 4u * PAD;  // the thread's 4 pixels of row y
-                        const float4 cv = lds128(cpa);
-                        const float vc[4] = {cv.x, cv.y, cv.z, cv.w};
                         bool any;
                         if constexpr (R >= 3) {
                             // a zero pixel equal to its (all-zero) window implies the thread's other pixels are zero too
-                            any = (vc[0] == M[0]) | (vc[1] == M[1]) | (vc[2] == M[2]) | (vc[3] == M[3]);
-                            any = any && fmaxf(fmaxf(vc[0], vc[1]), fmaxf(vc[2], vc[3])) > 0.0f;
+                            any = (cv[jc][0] == M[0]) | (cv[jc][1] == M[1]) | (cv[jc][2] == M[2]) | (cv[jc][3] == M[3]);
+                            any = any && fmaxf(fmaxf(cv[jc][0], cv[jc][1]), fmaxf(cv[jc][2], cv[jc][3])) > 0.0f;
                         } else {
                             any = false;
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) any |= (vc[c] > 0.0f && vc[c] == M[c]);
+                            for (int c = 0; c < 4; ++c) any |= (cv[jc][c] > 0.0f && cv[jc][c] == M[c]);
                         }
                         if (any && active) {
-                            // slow path (about one pixel in (2R+1)^2): exact first-occurrence test of
-                            // detector_util.py:298-308 -- no equal value earlier in raster order
+                            float up[4];  // maximum of the window rows above: rows y-R .. y-1
+                            if constexpr (R >= 3) {
+                                constexpr int jl = (j + P2 - R - 3) % P2;      // p3 of row y-3: rows y-3 .. y-1
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                const float v = vc[c];
-                                if (!(v > 0.0f && v == M[c])) continue;
-                                const int x = 4 * g + c;
-                                const uint32_t px = cpa + 4u * c;
-                                bool tie = false;
+                                for (int c = 0; c < 4; ++c) up[c] = p3[jl][c];
 #pragma unroll
-                                for (int dy = 1; dy <= R; ++dy)
+                                for (int i = 0; 3 * i < R - 3; ++i) {
+                                    const int ji = (j + 3 * i + 1) % P2;       // rows y-R+3i .. y-R+3i+2
 #pragma unroll
-                                    for (int dx = -R; dx <= R; ++dx) tie |= (lds32(px - dy * row_bytes + 4 * dx) == v);
+                                    for (int c = 0; c < 4; ++c) up[c] = fmaxf(up[c], p3[ji][c]);
+                                }
+                            } else {
 #pragma unroll
-                                for (int d = 1; d <= R; ++d) tie |= (lds32(px - 4 * d) == v);
-                                if (!tie) {
-                                    const uint32_t bit = 1u << (x & 31);
-                                    const uint32_t old = atomicOr(&LM[(size_t)y * SB + 1 + (x >> 5)], bit);
-                                    if (!(old & bit)) {
-                                        const int pos = atomicAdd(n_new, 1);
-                                        if (pos < P.LC) list[pos] = ((unsigned)y << 16) | (unsigned)x;
-                                    }
+                                for (int c = 0; c < 4; ++c) {
+                                    up[c] = h[(jc + P2 - 1) % P2][c];
+                                    if (R == 2) up[c] = fmaxf(up[c], h[(jc + P2 - 2) % P2][c]);
                                 }
                             }
+                            unsigned nib = 0;
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)
+                                if (cv[jc][c] > 0.0f && cv[jc][c] == M[c] && up[c] < cv[jc][c]) nib |= 1u << c;
+                            acc |= nib << (4 * ((y - R) & 7));
+                        }
+                        if (((y - R) & 7) == 7 || y == e - 1) {
+                            // runs start on multiples of 8 rows, so this (8 rows x 4 columns) word has one writer
+                            CB[(size_t)((y - R) >> 3) * CBW + g] = acc;
+                            acc = 0;
                         }
                     };
                     // prologue: rows a-R .. a+R-1 fill the ring (slots 0 .. 2R-1), nothing to emit yet
@@ -609,107 +616,217 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
                     }
                 }
                 EINX_TRACE(trace_slot); ++trace_slot;
-                sync_all();
+                __syncthreads();
                 EINX_TRACE(trace_slot); ++trace_slot;
-                // ---- scatter: every new maximum kills its window (V and UB, all copies) ---------- //
-                {
-                    const int nn = min(*n_new, P.LC);
-                    if (tid == 0) sh.n_new[(round + 1) & 1] = 0;
-                    int c_self = 0, c_up = 0, c_dn = 0;
-                    for (int it = tid; it < nn * P2; it += kThreads) {
-                        const int en = it / P2, dyi = it - en * P2;
-                        const unsigned ent = list[en];
-                        const int l = (int)(ent >> 16), x = (int)(ent & 0xffffu);
-                        const int l2 = l + dyi - R;
-                        float* row = V + (size_t)l2 * WS + PAD + x;
-                        const int lu = MULTI ? cp.up(l2, 2 * R) : -1, ld = MULTI ? cp.down(l2) : -1;
-                        float* rowu = lu >= 0 ? Vup + (size_t)lu * WS + PAD + x : nullptr;
-                        float* rowd = ld >= 0 ? Vdn + (size_t)ld * WS + PAD + x : nullptr;
+                // ---- dense pass 2: candidates -> maxima.  What is left of the first-occurrence test of
+                // detector_util.py:298-308: no equal value to the left in the same row.
+                for (int wi = tid; wi < ((nrows + 7) >> 3) * CBW; wi += kThreads) {
+                    uint32_t c = CB[wi];
+                    if (!c) continue;
+                    const int blk = wi / CBW, g = wi - blk * CBW;
+                    while (c) {
+                        const int bit = __ffs(c) - 1;
+                        c &= c - 1;
+                        const int l = R + 8 * blk + (bit >> 2), x = 4 * g + (bit & 3);
+                        const size_t widx = (size_t)l * SB + 1 + (x >> 5);
+                        const uint32_t m = 1u << (x & 31);
+                        if (LM[widx] & m) continue;  // a maximum of an earlier round stays one
+                        const uint32_t px = V_s + 4u * (uint32_t)(l * WS + PAD + x);
+                        const float v = lds32(px);
+                        bool tie = false;
 #pragma unroll
-                        for (int dx = -R; dx <= R; ++dx) {
-                            if (dx == 0 && dyi == R) continue;
-                            row[dx] = 0.0f;
-                            if (MULTI) {
-                                if (rowu) rowu[dx] = 0.0f;
-                                if (rowd) rowd[dx] = 0.0f;
+                        for (int d = 1; d <= R; ++d) tie |= (lds32(px - 4 * d) == v);
+                        if (tie) continue;
+                        atomicOr(&LM[widx], m);
+                        if (MULTI) {  // the neighbours dilate their copies of my edge rows
+                            const int lu = cp.up(l, 2 * R), ld = cp.down(l);
+                            if (lu >= 0) atomicOr(&LMup[(size_t)lu * SB + 1 + (x >> 5)], m);
+                            if (ld >= 0) atomicOr(&LMdn[(size_t)ld * SB + 1 + (x >> 5)], m);
+                        }
+                    }
+                }
+                EINX_TRACE(trace_slot); ++trace_slot;
+                sync_all();
+                // ---- dense pass 3: horizontal dilation of the maxima, all local rows, on words ------ //
+                if (tid == 0) sh.und = 0;
+                for (int wi = tid; wi < L * SW; wi += kThreads) {
+                    const int l = wi / SW, s = wi - l * SW;
+                    const size_t widx = (size_t)l * SB + 1 + s;
+                    const uint32_t w = LM[widx], wl = LM[widx - 1], wr = LM[widx + 1];
+                    uint32_t acc = w;
+#pragma unroll
+                    for (int d = 1; d <= R; ++d) acc |= __funnelshift_l(wl, w, d) | __funnelshift_r(w, wr, d);
+                    XB[widx] = acc;
+                }
+                __syncthreads();
+                EINX_TRACE(trace_slot); ++trace_slot;
+                // ---- dense pass 4: vertical dilation; undecided pixels under it are dead: clear them in UB and
+                // zero them in V (the owner writes every copy of its rows); count what stays undecided
+                {
+                    int left = 0;
+                    const int nwords = nrows * SW;
+                    for (int base = warp * 32; base < nwords; base += kThreads) {
+                        const int wi = base + lane;
+                        uint32_t sup = 0;
+                        int l = 0, s = 0;
+                        if (wi < nwords) {
+                            const int lr = wi / SW;
+                            s = wi - lr * SW;
+                            l = lr + R;
+                            const size_t widx = (size_t)l * SB + 1 + s;
+                            uint32_t d = 0;
+#pragma unroll
+                            for (int dy = -R; dy <= R; ++dy) d |= XB[widx + dy * SB];
+                            const uint32_t ub = UB[widx];
+                            const uint32_t keep = ub & ~d;
+                            sup = ub & d & ~LM[widx];
+                            if (keep != ub) {
+                                UB[widx] = keep;
+                                if (MULTI) {
+                                    const int lu = cp.up(l, 2 * R), ld = cp.down(l);
+                                    if (lu >= 0) UBup[(size_t)lu * SB + 1 + s] = keep;
+                                    if (ld >= 0) UBdn[(size_t)ld * SB + 1 + s] = keep;
+                                }
+                            }
+                            left += __popc(keep);
+                        }
+                        // zero the dead pixels: the warp walks its 32 words as 256 float4 chunks, lanes on consecutive chunks
+                        if (__any_sync(0xffffffffu, sup != 0)) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const int src = 4 * q + (lane >> 3);            // word (lane of the batch) owning this chunk
+                                const uint32_t sw = __shfl_sync(0xffffffffu, sup, src);
+                                const int sls = __shfl_sync(0xffffffffu, (l << 8) | s, src);  // s < 256 words
+                                const uint32_t nib = (sw >> (4 * (lane & 7))) & 0xfu;
+                                if (nib) {
+                                    const int sl = sls >> 8, ss = sls & 255;
+                                    const int x = 32 * ss + 4 * (lane & 7);
+                                    float4* cell = reinterpret_cast<float4*>(V + (size_t)sl * WS + PAD + x);
+                                    float4 v = *cell;
+                                    if (nib & 1u) v.x = 0.0f;
+                                    if (nib & 2u) v.y = 0.0f;
+                                    if (nib & 4u) v.z = 0.0f;
+                                    if (nib & 8u) v.w = 0.0f;
+                                    *cell = v;
+                                    if (MULTI) {
+                                        const int lu = cp.up(sl, 2 * R), ld = cp.down(sl);
+                                        if (lu >= 0) *reinterpret_cast<float4*>(Vup + (size_t)lu * WS + PAD + x) = v;
+                                        if (ld >= 0) *reinterpret_cast<float4*>(Vdn + (size_t)ld * WS + PAD + x) = v;
+                                    }
+                                }
                             }
                         }
-                        clear_window(l2, x, c_self, c_up, c_dn);
                     }
-                    settle_counts(c_self, c_up, c_dn);
+                    left = __reduce_add_sync(0xffffffffu, left);
+                    if (lane == 0 && left) atomicAdd(&sh.und, left);
                 }
                 EINX_TRACE(trace_slot); ++trace_slot;
             } else {
                 // ---- sparse round, phase 1: an undecided pixel looks at its undecided neighbours ---- //
-                unsigned int* const wl = list + wl_cur * half;
-                const int n = sh.wl_n[wl_cur];
+                const int n = n_wl;
                 for (int en = tid; en < n; en += kThreads) {
-                    const unsigned ent = wl[en];
+                    const unsigned ent = list[en];
                     const int l = (int)(ent >> 16), x = (int)(ent & 0xffffu);
                     const float* cpx = V + (size_t)l * WS + PAD + x;
                     const float v = cpx[0];
                     const int xl = x - R + 32;
                     const int wi = xl >> 5, shf = xl & 31;
-                    bool beaten = false;
+                    // Undecided pixels cluster, so a data-dependent loop over the set bits runs as long as the fullest
+                    // window of the warp: every position is visited instead, its load predicated on the bit.
+                    float early = 0.0f, late = 0.0f;  // raster-earlier / raster-later undecided neighbours (values > 0)
 #pragma unroll
                     for (int dy = -R; dy <= R; ++dy) {
                         const uint32_t* u = UB + (size_t)(l + dy) * SB + wi;
                         const unsigned long long both = (unsigned long long)u[0] | ((unsigned long long)u[1] << 32);
                         uint32_t f = (uint32_t)(both >> shf) & kWinMask;
                         if (dy == 0) f &= ~(1u << R);
-                        while (f) {
-                            const int bit = __ffs(f) - 1;
-                            f &= f - 1;
-                            const float w = cpx[dy * WS + bit - R];
-                            // raster-earlier neighbours win ties (first-occurrence argmax)
-                            const bool earlier = dy < 0 || (dy == 0 && bit < R);
-                            if (w > v || (earlier && w == v)) { beaten = true; f = 0; }
-                        }
-                    }
-                    if (!beaten) {
-                        atomicOr(&LM[(size_t)l * SB + 1 + (x >> 5)], 1u << (x & 31));
-                        wl[en] = ent | 0x80000000u;  // a new maximum (local rows < 32768)
-                    }
-                }
-                EINX_TRACE(trace_slot); ++trace_slot;
-                sync_all();
-                EINX_TRACE(trace_slot); ++trace_slot;
-                // ---- phase 2: the new maxima clear their windows in UB (all copies) ---------------- //
-                {
-                    if (tid == 0) sh.wl_n[wl_cur ^ 1] = 0;
-                    int c_self = 0, c_up = 0, c_dn = 0;
-                    for (int en = tid; en < n; en += kThreads) {
-                        const unsigned ent = wl[en];
-                        if (!(ent & 0x80000000u)) continue;
-                        const int l = (int)((ent >> 16) & 0x7fffu), x = (int)(ent & 0xffffu);
+                        if (f) {
 #pragma unroll
-                        for (int dy = -R; dy <= R; ++dy) clear_window(l + dy, x, c_self, c_up, c_dn);
-                    }
-                    settle_counts(c_self, c_up, c_dn);
-                }
-                sync_all();
-                EINX_TRACE(trace_slot); ++trace_slot;
-                // ---- phase 3: keep the still-undecided entries ---------------------------------- //
-                {
-                    unsigned int* const wn = list + (wl_cur ^ 1) * half;
-                    for (int base = 0; base < n; base += kThreads) {
-                        const int en = base + tid;
-                        unsigned ent = 0;
-                        bool keep = false;
-                        if (en < n) {
-                            ent = wl[en];
-                            if (!(ent & 0x80000000u)) {
-                                const int l = (int)(ent >> 16), x = (int)(ent & 0xffffu);
-                                keep = (UB[(size_t)l * SB + 1 + (x >> 5)] >> (x & 31)) & 1u;
+                            for (int k = 0; k < P2; ++k) {
+                                const float w = (f & (1u << k)) ? cpx[dy * WS + k - R] : 0.0f;
+                                if (dy < 0 || (dy == 0 && k < R)) early = fmaxf(early, w);
+                                else late = fmaxf(late, w);
                             }
                         }
-                        const unsigned kb = __ballot_sync(0xffffffffu, keep);
-                        int pos = 0;
-                        if (lane == 0 && kb) pos = atomicAdd(&sh.wl_n[wl_cur ^ 1], __popc(kb));
-                        pos = __shfl_sync(0xffffffffu, pos, 0);
-                        if (keep) wn[pos + __popc(kb & ((1u << lane) - 1u))] = ent;
                     }
-                    wl_cur ^= 1;
+                    // raster-earlier neighbours win ties (first-occurrence argmax)
+                    const bool beaten = !(v > early && v >= late);
+                    if (!beaten) {
+                        atomicOr(&LM[(size_t)l * SB + 1 + (x >> 5)], 1u << (x & 31));
+                        list[en] = ent | 0x80000000u;  // a new maximum (local rows < 32768)
+                    }
+                }
+                EINX_TRACE(trace_slot); ++trace_slot;
+                sync_all();
+                EINX_TRACE(trace_slot); ++trace_slot;
+                // ---- phase 2: the new maxima clear their windows in UB (every copy of a row; the copies are
+                // identical, so the local one tells whether there is anything to clear) --------------------- //
+                if (tid == 0) sh.wl_n[0] = 0;
+                for (int en = tid; en < n; en += kThreads) {
+                    const unsigned ent = list[en];
+                    if (!(ent & 0x80000000u)) continue;
+                    const int l = (int)((ent >> 16) & 0x7fffu), x = (int)(ent & 0xffffu);
+                    const int xl = x - R + 32;
+                    const int wi = xl >> 5, shf = xl & 31;
+                    const unsigned long long m64 = (unsigned long long)kWinMask << shf;
+                    const uint32_t lo = (uint32_t)m64, hi = (uint32_t)(m64 >> 32);
+#pragma unroll
+                    for (int dy = -R; dy <= R; ++dy) {
+                        const int l2 = l + dy;
+                        uint32_t* u = UB + (size_t)l2 * SB + wi;
+                        const bool c0 = (u[0] & lo) != 0, c1 = hi && (u[1] & hi) != 0;
+                        if (!(c0 | c1)) continue;
+                        if (c0) atomicAnd(u, ~lo);
+                        if (c1) atomicAnd(u + 1, ~hi);
+                        if (MULTI) {
+                            const int lu = cp.up(l2, 2 * R), ld = cp.down(l2);
+                            if (lu >= 0) {
+                                uint32_t* ur = UBup + (size_t)lu * SB + wi;
+                                if (c0) atomicAnd(ur, ~lo);
+                                if (c1) atomicAnd(ur + 1, ~hi);
+                            }
+                            if (ld >= 0) {
+                                uint32_t* ur = UBdn + (size_t)ld * SB + wi;
+                                if (c0) atomicAnd(ur, ~lo);
+                                if (c1) atomicAnd(ur + 1, ~hi);
+                            }
+                        }
+                    }
+                }
+                sync_all();
+                EINX_TRACE(trace_slot); ++trace_slot;
+                // ---- phase 3: keep the still-undecided entries (read all, then write in place) ------ //
+                {
+                    constexpr int kPer = 8;  // cap <= kPer * kThreads is enforced by the host
+                    unsigned held[kPer];
+                    bool keep[kPer];
+#pragma unroll
+                    for (int u = 0; u < kPer; ++u) {
+                        const int en = tid + u * kThreads;
+                        held[u] = 0;
+                        keep[u] = false;
+                        if (en < n) {
+                            const unsigned ent = list[en];
+                            held[u] = ent;
+                            if (!(ent & 0x80000000u)) {
+                                const int l = (int)(ent >> 16), x = (int)(ent & 0xffffu);
+                                keep[u] = (UB[(size_t)l * SB + 1 + (x >> 5)] >> (x & 31)) & 1u;
+                            }
+                        }
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int u = 0; u < kPer; ++u) {
+                        if (u * kThreads >= n) break;  // uniform
+                        const unsigned kb = __ballot_sync(0xffffffffu, keep[u]);
+                        int pos = 0;
+                        if (lane == 0 && kb) pos = atomicAdd(&sh.wl_n[0], __popc(kb));
+                        pos = __shfl_sync(0xffffffffu, pos, 0);
+                        if (keep[u]) list[pos + __popc(kb & ((1u << lane) - 1u))] = held[u];
+                    }
+                    __syncthreads();
+                    n_wl = sh.wl_n[0];
+                    if (tid == 0) sh.und = n_wl;
                 }
             }
         }
@@ -724,7 +841,8 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
     // ---- survivors -> ordered per-image list ------------------------------------------------- //
     // At the fixpoint the selected pixels (LM bits of the own rows) are exactly the survivors.  The lists
     // live in the shared-memory scratch (UB + list buffer, both dead now) for single-CTA images, in the
-    // global workspace for clusters.
+    // global workspace for clusters.  A thread takes a run of consecutive bitmap words, so one block scan
+    // orders the whole band.
     float* slist;
     int32_t* sidx;
     const bool smem_lists = !MULTI && P.tail_smem;
@@ -732,20 +850,21 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
         slist = reinterpret_cast<float*>(UB);
         sidx = reinterpret_cast<int32_t*>(UB) + P.scap;
     } else {
-        slist = P.surv_val + (size_t)b * P.scap;
-        sidx = P.surv_idx + (size_t)b * P.scap;
+        slist = P.surv_val + (size_t)bg * P.scap;
+        sidx = P.surv_idx + (size_t)bg * P.scap;
     }
-    const int SW = SB - 2;
     const int nwords = nrows * SW;
-    int own = 0, offset = 0, total = 0;
+    const int per = (nwords + kThreads - 1) / kThreads;
+    const int w0 = min(tid * per, nwords), w1 = min(w0 + per, nwords);
+    int own = 0, offset = 0, total = 0, mypos = 0;
     {
-        int c = 0;
-        for (int wi = tid; wi < nwords; wi += kThreads) {
+        int mine = 0;
+        for (int wi = w0; wi < w1; ++wi) {
             const int lr = wi / SW, s = wi - lr * SW;
-            c += __popc(LM[(size_t)(lr + R) * SB + 1 + s]);
+            mine += __popc(LM[(size_t)(lr + R) * SB + 1 + s]);
         }
-        c = __reduce_add_sync(0xffffffffu, c);
-        if (lane == 0 && c) atomicAdd(&sh.xcnt[0], c);
+        mypos = block_excl_scan(mine, sh.warp_scan, own);
+        if (tid == 0) sh.xcnt[0] = own;
     }
     sync_all();
     if (MULTI) {
@@ -755,23 +874,14 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
             total += c;
         }
     } else {
-        total = sh.xcnt[0];
+        total = own;
     }
-    own = sh.xcnt[0];
     {
-        // the bitmap words are read before the lists (which may alias UB, never LM) are written
-        int run = offset;
-        for (int base = 0; base < nwords; base += kThreads) {
-            const int wi = base + tid;
-            int lr = 0, s = 0;
-            uint32_t w = 0;
-            if (wi < nwords) {
-                lr = wi / SW;
-                s = wi - lr * SW;
-                w = LM[(size_t)(lr + R) * SB + 1 + s];
-            }
-            int tot;
-            int pos = run + block_excl_scan(__popc(w), sh.warp_scan, tot);
+        // (the lists may alias UB, never LM or V)
+        int pos = offset + mypos;
+        for (int wi = w0; wi < w1; ++wi) {
+            const int lr = wi / SW, s = wi - lr * SW;
+            uint32_t w = LM[(size_t)(lr + R) * SB + 1 + s];
             while (w) {
                 const int bit = __ffs(w) - 1;
                 w &= w - 1;
@@ -782,7 +892,6 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
                 }
                 ++pos;
             }
-            run += tot;
         }
     }
     if (MULTI) __threadfence();
@@ -815,12 +924,14 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
 
     EINX_TRACE(123);
     // ---- keypoint rows in raster order + optional dense map ---------------------------------- //
-    {
-        int c = 0;
-        for (int i = tid; i < own; i += kThreads) c += ((smem_lists ? slist[offset + i] : __ldcg(slist + offset + i)) > thr) ? 1 : 0;
-        c = __reduce_add_sync(0xffffffffu, c);
-        if (lane == 0 && c) atomicAdd(&sh.xcnt[1], c);
-    }
+    // a thread takes a run of consecutive survivors of the band: one block scan places the rows
+    const int sper = (own + kThreads - 1) / kThreads;
+    const int s0 = min(tid * sper, own), s1 = min(s0 + sper, own);
+    int kmine = 0;
+    for (int i = s0; i < s1; ++i) kmine += ((smem_lists ? slist[offset + i] : __ldcg(slist + offset + i)) > thr) ? 1 : 0;
+    int kown;
+    int kpos = block_excl_scan(kmine, sh.warp_scan, kown);
+    if (tid == 0) sh.xcnt[1] = kown;
     sync_all();
     int koff = 0, ktotal = 0;
     if (MULTI) {
@@ -830,36 +941,29 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
             ktotal += c;
         }
     } else {
-        ktotal = sh.xcnt[1];
+        ktotal = kown;
     }
-    if (rank == 0 && tid == 0) P.counts[b] = ktotal;
+    if (rank == 0 && tid == 0) S.counts[b] = ktotal;
     {
-        float* krows = P.kpts + (size_t)b * P.kcap * 3;
-        int run = koff;
-        for (int base = 0; base < own; base += kThreads) {
-            const int i = base + tid;
-            float v = 0.0f;
-            int idx = 0;
-            bool keep = false;
-            if (i < own) {
-                v = smem_lists ? slist[offset + i] : __ldcg(slist + offset + i);
-                idx = smem_lists ? sidx[offset + i] : __ldcg(sidx + offset + i);
-                keep = v > thr;
+        float* krows = S.kpts + (size_t)b * P.kcap * 3;
+        int pos = koff + kpos;
+        for (int i = s0; i < s1; ++i) {
+            const float v = smem_lists ? slist[offset + i] : __ldcg(slist + offset + i);
+            if (v > thr) {
+                if (pos < P.kcap) {
+                    const int idx = smem_lists ? sidx[offset + i] : __ldcg(sidx + offset + i);
+                    const int y = idx / Wp, x = idx - y * Wp;
+                    krows[(size_t)pos * 3 + 0] = (float)y + 0.5f;
+                    krows[(size_t)pos * 3 + 1] = (float)x + 0.5f;
+                    krows[(size_t)pos * 3 + 2] = v;
+                }
+                ++pos;
             }
-            int tot;
-            const int pos = run + block_excl_scan(keep ? 1 : 0, sh.warp_scan, tot);
-            if (keep && pos < P.kcap) {
-                const int y = idx / Wp, x = idx - y * Wp;
-                krows[(size_t)pos * 3 + 0] = (float)y + 0.5f;
-                krows[(size_t)pos * 3 + 1] = (float)x + 0.5f;
-                krows[(size_t)pos * 3 + 2] = v;
-            }
-            run += tot;
         }
     }
-    if (P.nms_map) {
+    if (S.nms_map) {
         // selected AND above the threshold; V still holds dead values from the sparse rounds, LM decides
-        float* out = P.nms_map + (size_t)b * Hp * Wp;
+        float* out = S.nms_map + (size_t)b * Hp * Wp;
         if (P.vec == 4) {
             for (int e = tid; e < nrows * W4; e += kThreads) {
                 const int lr = e / W4, g = e - lr * W4;
@@ -948,31 +1052,29 @@ void einx_topk_ranks(int n, int k, int* lo, int* hi) {
     *hi = (int)ceilf(rank);
 }
 
-extern "C" int einx_detect(einx_ctx* ctx, float* score, const uint8_t* mask, int B, int Hp, int Wp, int nms_radius,
-                           int border, float prob_thresh, int top_k, float* nms_map, float* kpts, int kcap,
-                           int32_t* counts, einx_stream stream_) {
-    if (!ctx) return EINX_ERR_INVALID;
-    if (B < 0 || Hp <= 0 || Wp <= 0 || nms_radius < 0 || border < 0 || kcap < 0)
-        return einx_fail(ctx, EINX_ERR_INVALID, "einx_detect: bad argument B=%d Hp=%d Wp=%d r=%d border=%d kcap=%d", B,
-                         Hp, Wp, nms_radius, border, kcap);
-    if (B == 0) return EINX_OK;
-    if (!score || !kpts || !counts) return einx_fail(ctx, EINX_ERR_INVALID, "einx_detect: NULL pointer argument");
-    if ((long long)Hp * Wp > (1ll << 30)) return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_detect: map too large");
-    if (nms_radius > 8) return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_detect: nms_radius %d not in [0, 8]", nms_radius);
+namespace {
+
+int detect_impl(einx_ctx* ctx, const NmsSide* sides, int nsides, int Bside, int Hp, int Wp, int nms_radius, int border,
+                float prob_thresh, int top_k, int kcap, einx_stream stream_) {
+    const int B = Bside * nsides;
     DeviceGuard guard(ctx->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int R = nms_radius;
 
     NmsParams P = {};
-    P.score = score; P.mask = mask; P.nms_map = nms_map; P.kpts = kpts; P.counts = counts;
-    P.B = B; P.Hp = Hp; P.Wp = Wp; P.border = border; P.kcap = kcap;
+    for (int i = 0; i < nsides; ++i) P.side[i] = sides[i];
+    P.B = B; P.Bsplit = Bside; P.Hp = Hp; P.Wp = Wp; P.border = border; P.kcap = kcap;
     const int PAD = (R + 3) / 4 * 4;
     P.W4 = (Wp + 3) / 4;
     P.NCW = (P.W4 + 31) / 32;
     P.WS = 4 * P.W4 + 2 * PAD;
     P.SB = 4 * P.NCW + 2;
-    P.vec = (Wp % 4 == 0 && (uintptr_t)score % 16 == 0 && (!nms_map || (uintptr_t)nms_map % 16 == 0)) ? 4
-            : (Wp % 2 == 0 && (uintptr_t)score % 8 == 0) ? 2 : 1;
+    P.vec = 4;
+    for (int i = 0; i < nsides; ++i) {
+        const uintptr_t a = (uintptr_t)sides[i].score, m = (uintptr_t)sides[i].nms_map;
+        const int v = (Wp % 4 == 0 && a % 16 == 0 && m % 16 == 0) ? 4 : (Wp % 2 == 0 && a % 8 == 0) ? 2 : 1;
+        if (v < P.vec) P.vec = v;
+    }
     P.prob_thresh = prob_thresh;
     const int n = Hp * Wp;
     if (top_k > 0) {
@@ -982,21 +1084,21 @@ extern "C" int einx_detect(einx_ctx* ctx, float* score, const uint8_t* mask, int
     P.scap = R == 0 ? n : ((Hp + R) / (R + 1)) * ((Wp + R) / (R + 1));
 
     // Bands per image: the smallest cluster whose band (values, two bitmaps, list buffer) fits one CTA's shared
-    // memory; then wider while even two such launches side by side (the two sides of a pair run on concurrent
-    // streams) leave SMs idle.  Bands of a cluster are at least 2R rows, so a row has at most two copies.
+    // memory; then wider while the launch leaves more than half of the SMs idle.  Bands of a cluster are at least
+    // 2R rows, so a row has at most two copies.
     const size_t fixed = align_up(sizeof(Shared), 16);
     const size_t budget = (size_t)ctx->max_smem_optin;
-    auto band_cap = [&](int rb) {  // maxima a band can hold (the new-maxima list of a dense round) -- R > 0
-        return R == 0 ? 0 : ((rb + R) / (R + 1) + 1) * ((Wp + R) / (R + 1));
-    };
-    // list buffer: at least the new maxima a dense round can produce; beyond that, a larger buffer means an
-    // earlier switch to sparse rounds (half of it is the worklist capacity)
+    // list buffer: one bitmap plane in dense rounds (candidates / dilated maxima), the worklist of undecided pixels
+    // in sparse rounds -- the larger it is, the earlier the switch to sparse rounds
     auto smem_for = [&](int rb, int lc) {
         return fixed + (size_t)(rb + 2 * R) * ((size_t)P.WS * 4 + (size_t)P.SB * 8) + (size_t)lc * 4;
     };
     auto list_entries = [&](int rb) {  // 0: the band does not fit
+        // the plane holds the dilated maxima ([local row][word]) or the sweep's candidates ([8-row block][column group])
+        const int hd = (rb + 2 * R) * P.SB, cb = ((rb + 7) / 8 + 1) * 32 * P.NCW;
+        const int plane = hd > cb ? hd : cb;
         for (int want = 4096; want >= 1024; want >>= 1) {
-            int lc = band_cap(rb) > want ? band_cap(rb) : want;
+            int lc = plane > want ? plane : want;
             lc += lc & 1;
             if (smem_for(rb, lc) <= budget) return lc;
         }
@@ -1012,11 +1114,16 @@ extern "C" int einx_detect(einx_ctx* ctx, float* score, const uint8_t* mask, int
         if (rb + 2 * R >= 32768 || Wp >= 65536) break;  // worklist entries pack (row << 16 | x), bit 31 = flag
         if (list_entries(rb) > 0) { T = t; break; }
     }
-    if (T == 0)  // no cluster of bands holds the map in shared memory: L2-resident variant
-        return einx_detect_large(ctx, score, mask, B, Hp, Wp, nms_radius, border, prob_thresh, top_k, nms_map, kpts, kcap,
-                                 counts, stream_);
+    if (T == 0) {  // no cluster of bands holds the map in shared memory: L2-resident variant
+        for (int i = 0; i < nsides; ++i) {
+            const int rc = einx_detect_large(ctx, sides[i].score, sides[i].mask, Bside, Hp, Wp, nms_radius, border, prob_thresh,
+                                             top_k, sides[i].nms_map, sides[i].kpts, kcap, sides[i].counts, stream_);
+            if (rc) return rc;
+        }
+        return EINX_OK;
+    }
     if (force_t <= 0)
-        while (T * 2 <= kMaxCluster && (long long)B * T * 2 * 2 <= ctx->num_sms && Hp / (T * 2) >= 2 * (R > 0 ? R : 1) + 8) T *= 2;
+        while (T * 2 <= kMaxCluster && (long long)B * T * 2 <= ctx->num_sms && Hp / (T * 2) >= 2 * (R > 0 ? R : 1) + 8) T *= 2;
     P.T = T;
     P.RB = (Hp + T - 1) / T;
     P.LC = list_entries(P.RB);
@@ -1024,7 +1131,7 @@ extern "C" int einx_detect(einx_ctx* ctx, float* score, const uint8_t* mask, int
     // sweep runs: NSEG x NCW units over the warps of a CTA
     P.NSEG = kWarps / P.NCW > 0 ? kWarps / P.NCW : 1;
     if (P.NSEG > P.RB) P.NSEG = P.RB;
-    P.SR = (P.RB + P.NSEG - 1) / P.NSEG;
+    P.SR = ((P.RB + P.NSEG - 1) / P.NSEG + 7) / 8 * 8;  // runs start on multiples of 8 rows (candidate words have one writer)
     // survivor lists of the tail: shared-memory scratch (UB + list buffer) when a single CTA owns the image
     const size_t scratch = (size_t)(P.RB + 2 * R) * P.SB * 4 + (size_t)P.LC * 4;
     P.tail_smem = (T == 1 && (size_t)P.scap * 8 <= scratch) ? 1 : 0;
@@ -1044,4 +1151,38 @@ extern "C" int einx_detect(einx_ctx* ctx, float* score, const uint8_t* mask, int
     const size_t smem = smem_for(P.RB, P.LC);
     if (T == 1) return dispatch_radius<false>(ctx, R, P, smem, stream);
     return dispatch_radius<true>(ctx, R, P, smem, stream);
+}
+
+}  // namespace
+
+extern "C" int einx_detect(einx_ctx* ctx, float* score, const uint8_t* mask, int B, int Hp, int Wp, int nms_radius,
+                           int border, float prob_thresh, int top_k, float* nms_map, float* kpts, int kcap,
+                           int32_t* counts, einx_stream stream_) {
+    if (!ctx) return EINX_ERR_INVALID;
+    if (B < 0 || Hp <= 0 || Wp <= 0 || nms_radius < 0 || border < 0 || kcap < 0)
+        return einx_fail(ctx, EINX_ERR_INVALID, "einx_detect: bad argument B=%d Hp=%d Wp=%d r=%d border=%d kcap=%d", B,
+                         Hp, Wp, nms_radius, border, kcap);
+    if (B == 0) return EINX_OK;
+    if (!score || !kpts || !counts) return einx_fail(ctx, EINX_ERR_INVALID, "einx_detect: NULL pointer argument");
+    if ((long long)Hp * Wp > (1ll << 30)) return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_detect: map too large");
+    if (nms_radius > 8) return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_detect: nms_radius %d not in [0, 8]", nms_radius);
+    const NmsSide side = {score, mask, nms_map, kpts, counts};
+    return detect_impl(ctx, &side, 1, B, Hp, Wp, nms_radius, border, prob_thresh, top_k, kcap, stream_);
+}
+
+extern "C" int einx_detect_pair(einx_ctx* ctx, float* score0, float* score1, const uint8_t* mask0, const uint8_t* mask1,
+                                int B, int Hp, int Wp, int nms_radius, int border, float prob_thresh, int top_k,
+                                float* nms_map0, float* nms_map1, float* kpts0, float* kpts1, int kcap, int32_t* counts0,
+                                int32_t* counts1, einx_stream stream_) {
+    if (!ctx) return EINX_ERR_INVALID;
+    if (B < 0 || Hp <= 0 || Wp <= 0 || nms_radius < 0 || border < 0 || kcap < 0)
+        return einx_fail(ctx, EINX_ERR_INVALID, "einx_detect_pair: bad argument B=%d Hp=%d Wp=%d r=%d border=%d kcap=%d", B,
+                         Hp, Wp, nms_radius, border, kcap);
+    if (B == 0) return EINX_OK;
+    if (!score0 || !score1 || !kpts0 || !kpts1 || !counts0 || !counts1)
+        return einx_fail(ctx, EINX_ERR_INVALID, "einx_detect_pair: NULL pointer argument");
+    if ((long long)Hp * Wp > (1ll << 30)) return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_detect_pair: map too large");
+    if (nms_radius > 8) return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_detect_pair: nms_radius %d not in [0, 8]", nms_radius);
+    const NmsSide sides[2] = {{score0, mask0, nms_map0, kpts0, counts0}, {score1, mask1, nms_map1, kpts1, counts1}};
+    return detect_impl(ctx, sides, 2, B, Hp, Wp, nms_radius, border, prob_thresh, top_k, kcap, stream_);
 }

@@ -87,6 +87,82 @@ sample_kernel(const float* __restrict__ raw, int C, int Hd, int Wd, float Hp, fl
 }
 
 
+// ---- gather mode on a channels-last map ------------------------------------------------------- //
+// The SiLK-type gather reads raw[b, :, y, x]: in NCHW that is one 32-byte sector per 4-byte channel value
+// (channel stride = Hd*Wd floats).  cuDNN's native layout on Blackwell is channels-last, where the C channels
+// of a pixel are contiguous: a warp reads a keypoint's descriptor as float4 per lane (C = 128: one 512-byte
+// request), normalises and writes it the same way.  Two keypoints per warp and iteration keep two loads and
+// two shuffle reductions in flight.
+template <int NV>  // float4 per lane: C == 128 * NV (NV = 0: any C % 4 == 0 up to 512, guarded)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+sample_gather_nhwc_kernel(const float* __restrict__ raw, int C, int Hd, int Wd, const float* __restrict__ kpts,
+                          const int32_t* __restrict__ counts, int kcap, float scale, int normalize,
+                          float* __restrict__ desc) {
+    constexpr int MV = NV ? NV : 4;
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int k0 = (blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * 2;
+    if (k0 >= kcap) return;
+    int cnt = counts[b];
+    if (cnt > kcap) cnt = kcap;
+    const float* img = raw + (size_t)b * Hd * Wd * C;
+    const int c4 = C >> 2;  // float4 per descriptor
+    float4 v[2][MV];
+    float ss[2] = {0.0f, 0.0f};
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int k = k0 + u;
+        const bool live = k < cnt;
+        int yy = 0, xx = 0;
+        if (live) {
+            const float* kp = kpts + ((size_t)b * kcap + k) * 3;
+            yy = min(max((int)floorf(__ldg(kp)), 0), Hd - 1);      // pos.floor().long()   (:57-60)
+            xx = min(max((int)floorf(__ldg(kp + 1)), 0), Wd - 1);
+        }
+        const float4* src = reinterpret_cast<const float4*>(img + ((size_t)yy * Wd + xx) * C);
+#pragma unroll
+        for (int j = 0; j < MV; ++j) {
+            const int i = lane + 32 * j;
+            v[u][j] = (live && (NV || i < c4)) ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < MV; ++j) {
+            // same accumulation order as the NCHW kernel is not required: the reference's own norm is a
+            // library reduction; the result is checked to 2e-6 absolute
+            ss[u] = fmaf(v[u][j].x, v[u][j].x, ss[u]);
+            ss[u] = fmaf(v[u][j].y, v[u][j].y, ss[u]);
+            ss[u] = fmaf(v[u][j].z, v[u][j].z, ss[u]);
+            ss[u] = fmaf(v[u][j].w, v[u][j].w, ss[u]);
+        }
+    float mul[2] = {scale, scale};
+    if (normalize) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ss[0] += __shfl_xor_sync(0xffffffffu, ss[0], o);
+            ss[1] += __shfl_xor_sync(0xffffffffu, ss[1], o);
+        }
+        mul[0] = __fdiv_rn(scale, fmaxf(sqrtf(ss[0]), 1e-12f));
+        mul[1] = __fdiv_rn(scale, fmaxf(sqrtf(ss[1]), 1e-12f));
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int k = k0 + u;
+        if (k >= kcap) continue;
+        float4* out = reinterpret_cast<float4*>(desc + ((size_t)b * kcap + k) * C);
+#pragma unroll
+        for (int j = 0; j < MV; ++j) {
+            const int i = lane + 32 * j;
+            if (NV || i < c4) {
+                const float4 q = v[u][j];  // padding rows (k >= cnt) were loaded as zeros
+                out[i] = make_float4(q.x * mul[u], q.y * mul[u], q.z * mul[u], q.w * mul[u]);
+            }
+        }
+    }
+}
+
 // ---- bilinear mode, coarse map staged in shared memory --------------------------------------- //
 // The generic kernel above reads one 32-byte sector per 4-byte tap (channel stride = Hd*Wd floats).
 // For SuperPoint-type maps (C=256, 23x30 cells) the two coarse rows a keypoint touches are only
@@ -292,6 +368,14 @@ extern "C" int einx_sample(einx_ctx* ctx, const float* raw, int B, int C, int Hd
     if (mode == EINX_SAMPLE_GATHER) {
         sample_kernel<EINX_SAMPLE_GATHER><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
             raw, C, Hd, Wd, (float)Hp, (float)Wp, kpts, counts, kcap, scale, normalize, desc);
+    } else if (mode == EINX_SAMPLE_GATHER_NHWC) {
+        if (C % 4 != 0 || (uintptr_t)raw % 16 != 0 || (uintptr_t)desc % 16 != 0)
+            return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_sample: channels-last gather needs C %% 4 == 0 and 16-byte aligned buffers (C=%d)", C);
+        dim3 g2((kcap + 2 * kWarpsPerBlock - 1) / (2 * kWarpsPerBlock), B);
+        const int T = kWarpsPerBlock * 32;
+        if (C == 128) sample_gather_nhwc_kernel<1><<<g2, T, 0, stream>>>(raw, C, Hd, Wd, kpts, counts, kcap, scale, normalize, desc);
+        else if (C == 256) sample_gather_nhwc_kernel<2><<<g2, T, 0, stream>>>(raw, C, Hd, Wd, kpts, counts, kcap, scale, normalize, desc);
+        else sample_gather_nhwc_kernel<0><<<g2, T, 0, stream>>>(raw, C, Hd, Wd, kpts, counts, kcap, scale, normalize, desc);
     } else if (mode == EINX_SAMPLE_BILINEAR) {
         if (Hp <= 1 || Wp <= 1) return einx_fail(ctx, EINX_ERR_INVALID, "einx_sample: bilinear needs Hp, Wp > 1");
         // shared-memory slab variant when two coarse rows of every channel fit (odd pitch: lanes are

@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 
-GATHER, BILINEAR = 0, 1
+GATHER, BILINEAR, GATHER_NHWC = 0, 1, 2
 
 
 def pack_rows(rows: Sequence[torch.Tensor], width: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -33,9 +33,15 @@ def sample(raw: torch.Tensor, kpts: torch.Tensor, counts: torch.Tensor, mode: in
     """einx_sample on padded keypoints: (B, C, Hd, Wd) map -> (B, kcap, C) descriptors (rows >= count zero)."""
     if raw.dtype != torch.float32 or not raw.is_cuda:
         raise _lib.EinxError("sample: raw descriptors must be a float32 CUDA tensor (there is no CPU fallback)")
-    raw = raw.contiguous()
-    kpts = kpts.contiguous()
     B, C, Hd, Wd = raw.shape
+    if (mode == GATHER and C % 4 == 0 and C > 1 and not raw.is_contiguous()
+            and raw.is_contiguous(memory_format=torch.channels_last)):
+        # a channels-last map (what cuDNN convolutions produce on Blackwell) is read in place: its memory is
+        # (B, Hd, Wd, C), so a keypoint's descriptor is one contiguous read instead of C strided sectors
+        mode = GATHER_NHWC
+    else:
+        raw = raw.contiguous()
+    kpts = kpts.contiguous()
     kcap = kpts.shape[1]
     dev = raw.device
     ctx = _lib.context_for(dev)

@@ -66,6 +66,39 @@ def detect(score: torch.Tensor, prob_thresh: float, nms_dist: int, border_dist: 
     return nms_map, kpts, counts
 
 
+@torch.no_grad()
+def detect_pair(score0: torch.Tensor, score1: torch.Tensor, prob_thresh: float, nms_dist: int, border_dist: int,
+                top_k: Optional[int], mask0: Optional[torch.Tensor] = None, mask1: Optional[torch.Tensor] = None,
+                kcap: Optional[int] = None):
+    """:func:`detect` for the two sides of a batch of pairs in one launch (einx_detect_pair): two (B, 1, H, W) maps of
+    one shape -> ``((kpts0, counts0), (kpts1, counts1))``.  Both maps are border-zeroed in place."""
+    for s in (score0, score1):
+        if s.dtype != torch.float32 or not s.is_cuda:
+            raise _lib.EinxError("detect_pair: score maps must be float32 CUDA tensors (there is no CPU fallback)")
+        if not s.is_contiguous():
+            raise ValueError("detect_pair: score maps must be contiguous (they are modified in place)")
+    if score0.shape != score1.shape or score0.device != score1.device:
+        raise ValueError("detect_pair: the two sides must have one shape and one device")
+    if score0.dim() == 4 and score0.shape[1] != 1:
+        raise ValueError("detect_pair: expected (B, 1, H, W)")
+    B, Hp, Wp = score0.shape[0], score0.shape[-2], score0.shape[-1]
+    dev = score0.device
+    ctx = _lib.context_for(dev)
+    k = int(top_k) if top_k else 0
+    if kcap is None:
+        bound = max_keypoints(Hp, Wp, nms_dist)
+        kcap = min(k, bound) if (k > 0 and prob_thresh >= 1.0) else bound
+    kcap = max(int(kcap), 1)
+    kp = [torch.empty((B, kcap, 3), dtype=torch.float32, device=dev) for _ in range(2)]
+    cn = [torch.empty((B,), dtype=torch.int32, device=dev) for _ in range(2)]
+    m8 = [None if m is None else m.reshape(B, Hp, Wp).to(torch.uint8).contiguous() for m in (mask0, mask1)]
+    rc = ctx.lib.einx_detect_pair(ctx.handle, _lib.ptr(score0), _lib.ptr(score1), _lib.ptr(m8[0]), _lib.ptr(m8[1]), B, Hp, Wp,
+                                  int(nms_dist), int(border_dist), float(prob_thresh), k, None, None, _lib.ptr(kp[0]),
+                                  _lib.ptr(kp[1]), kcap, _lib.ptr(cn[0]), _lib.ptr(cn[1]), ctx.stream)
+    ctx.check(rc, "einx_detect_pair")
+    return (kp[0], cn[0]), (kp[1], cn[1])
+
+
 class _PointsMap(torch.Tensor):
     """The dense ``nms`` tensor, remembering the keypoint rows found in the same launch."""
 

@@ -75,7 +75,9 @@ class ExtractMatchPipeline:
         einx context (workspace); the side chain joins before the MNN kernel, the voxel stream after it -- so the
         latency-bound NMS rounds of one side overlap the other side's sampling and the event scatter instead of
         queueing behind them."""
-        if not self.cfg.concurrent:
+        c = self.cfg
+        mode = describe.BILINEAR if c.descriptor_mode == "bilinear" else describe.GATHER
+        if not c.concurrent:
             grid = self.voxelize(*events)
             k0, c0, d0 = self.extract(score0, raw0, mask0)
             k1, c1, d1 = self.extract(score1, raw1, mask1)
@@ -84,19 +86,29 @@ class ExtractMatchPipeline:
             main = torch.cuda.current_stream(dev)
             s_vox, s_side = self._streams(dev)
             s_vox.wait_stream(main)
-            s_side.wait_stream(main)
-            with torch.cuda.stream(s_side):
-                k1, c1, d1 = self.extract(score1, raw1, mask1)
             with torch.cuda.stream(s_vox):
                 grid = self.voxelize(*events)
-            k0, c0, d0 = self.extract(score0, raw0, mask0)
+            if score0.shape == score1.shape:
+                # both sides' maps in ONE detect launch (an image is owned by one CTA, so 2B images fill the machine
+                # where two launches of B would run back to back); the two sampling kernels then run side by side
+                (k0, c0), (k1, c1) = _detect.detect_pair(score0, score1, c.detection_threshold, c.nms_radius,
+                                                        c.remove_borders, c.top_k, mask0, mask1)
+                s_side.wait_stream(main)
+                with torch.cuda.stream(s_side):
+                    d1 = describe.sample(raw1, k1, c1, mode, score1.shape[-2:], c.descriptor_scale, True)
+                d0 = describe.sample(raw0, k0, c0, mode, score0.shape[-2:], c.descriptor_scale, True)
+            else:
+                s_side.wait_stream(main)
+                with torch.cuda.stream(s_side):
+                    k1, c1, d1 = self.extract(score1, raw1, mask1)
+                k0, c0, d0 = self.extract(score0, raw0, mask0)
             main.wait_stream(s_side)
             if not torch.cuda.is_current_stream_capturing():
                 # caching-allocator bookkeeping: tensors cross streams in both directions (a captured
                 # step owns its memory pool for the lifetime of the graph instead)
                 for t in (k1, c1, d1, grid):
                     t.record_stream(main)
-                for t in (score1, raw1, mask1):
+                for t in (score1, raw1, mask1, k1, c1):
                     if t is not None:
                         t.record_stream(s_side)
                 for t in events:

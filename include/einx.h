@@ -34,6 +34,9 @@ extern "C" {
 
 #define EINX_SAMPLE_GATHER 0   /* sparsify_full_resolution_descriptors */
 #define EINX_SAMPLE_BILINEAR 1 /* sparsify_low_resolution_descriptors  */
+#define EINX_SAMPLE_GATHER_NHWC 2 /* sparsify_full_resolution_descriptors on a channels-last map: raw is
+                                   * (B, Hd, Wd, C), the memory of a torch.channels_last (B, C, Hd, Wd) tensor --
+                                   * a keypoint's C channels are one contiguous, coalesced read              */
 
 #define EINX_MNN_FP32 0  /* FFMA tiles, fp32 accumulate: index-exact reference path */
 #define EINX_MNN_TF32X3 1 /* tcgen05 kind::tf32, 3-term split (hi*hi + hi*lo + lo*hi) */
@@ -91,11 +94,22 @@ int einx_detect(einx_ctx* ctx, float* score, const uint8_t* mask, int B, int Hp,
                 float* kpts, int kcap, int32_t* counts, einx_stream stream);
 
 /*
+ * The same for the two sides of a batch of pairs in ONE launch (EIM.forward runs the extractor on the event side
+ * and on the image side, core/modules/EIM.py:89-93: two independent batches of B maps of one size).  Every argument
+ * is as in einx_detect, once per side; B is the batch of one side.  Each image is owned by one CTA (or cluster), so
+ * 2B images fill the machine where two launches of B would run back to back.
+ */
+int einx_detect_pair(einx_ctx* ctx, float* score0, float* score1, const uint8_t* mask0,
+                     const uint8_t* mask1, int B, int Hp, int Wp, int nms_radius, int border,
+                     float prob_thresh, int top_k, float* nms_map0, float* nms_map1, float* kpts0,
+                     float* kpts1, int kcap, int32_t* counts0, int32_t* counts1, einx_stream stream);
+
+/*
  * Descriptor sampling + L2 normalisation.  Replaces core/modules/utils/descriptor_util.py:21-28
  * (normalize_descriptors), :50-71 (gather, SiLK type) and :74-128 (bilinear grid_sample with
  * align_corners=False on the padded-image grid, SuperPoint type).
  *   raw   : (B, C, Hd, Wd) fp32 descriptor map (Hd, Wd = padded image for gather; coarse map
- *           for bilinear)
+ *           for bilinear); (B, Hd, Wd, C) for EINX_SAMPLE_GATHER_NHWC
  *   Hp,Wp : padded image size the positions refer to (bilinear mode only)
  *   kpts  : (B, kcap, 3) as written by einx_detect; counts (B) int32 (clamped to kcap)
  *   desc  : (B, kcap, C) fp32; rows >= count are zero-filled

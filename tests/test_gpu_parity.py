@@ -260,6 +260,24 @@ def test_detect_full_batch_single_cta(einx, synth):
             assert np.array_equal(kp[i, : counts[i]], pos[i]), (Hp, i)
 
 
+def test_detect_pair_is_two_detects(einx, synth):
+    """einx_detect_pair: both sides of a batch of pairs in one launch, bit-identical to one launch per side."""
+    rng = np.random.default_rng(77)
+    for B, Hp, Wp, k in ((64, 184, 240, 1024), (3, 260, 346, 2048), (1, 96, 128, 100)):
+        a, b = synth.score_map(rng, B, Hp, Wp), synth.score_map(rng, B, Hp, Wp, "ties")
+        mb = rng.random((B, 1, Hp, Wp)) > 0.3
+        sa, sb = cuda(a), cuda(b)
+        (k0, c0), (k1, c1) = einx.detect_pair(sa, sb, 1.0, 4, 4, k, None, cuda(mb))
+        ra, rb = cuda(a), cuda(b)
+        _, e0, d0 = einx.detect(ra, 1.0, 4, 4, k)
+        _, e1, d1 = einx.detect(rb, 1.0, 4, 4, k, mask=cuda(mb))
+        assert torch.equal(sa, ra) and torch.equal(sb, rb)  # in-place border / mask zeroing
+        assert torch.equal(c0, d0) and torch.equal(c1, d1)
+        for i in range(B):
+            assert torch.equal(k0[i, : int(c0[i])], e0[i, : int(d0[i])])
+            assert torch.equal(k1[i, : int(c1[i])], e1[i, : int(d1[i])])
+
+
 def test_detect_mask_and_positions_generic(einx, synth):
     rng = np.random.default_rng(3)
     m = synth.score_map(rng, 2, 96, 128)
@@ -310,6 +328,39 @@ def test_sample_vs_oracle_config_sizes(einx, synth, mode, C, Hp, Wp, cell, scale
         assert a.shape == b.shape
         assert np.abs(a.cpu().numpy() - b).max() < 2e-6
         assert np.abs(np.linalg.norm(a.cpu().numpy().astype(np.float64), axis=1) - scale).max() < 1e-5
+
+
+@pytest.mark.parametrize("C,Hp,Wp,scale", [(128, 260, 346, 1.41), (256, 64, 80, 1.0), (96, 40, 56, 1.0), (36, 33, 47, 2.0)])
+def test_sample_gather_channels_last(einx, synth, C, Hp, Wp, scale):
+    """A channels-last descriptor map (the layout cuDNN convolutions produce) is gathered in place -- one contiguous
+    read per keypoint -- and gives the same descriptors as the NCHW map (descriptor_util.py:50-71)."""
+    rng = np.random.default_rng(C * 3 + Hp)
+    B = 3
+    raw = synth.descriptor_map(rng, B, C, Hp, Wp)
+    nms = O.prob_map_to_points_map(synth.score_map(rng, B, Hp, Wp), 1.0, 4, 4, 700)
+    pos = list(O.prob_map_to_positions_with_prob(nms))
+    pos[1] = pos[1][:0]  # an image without keypoints
+    ref = O.sparsify_full_resolution_descriptors(raw, pos, scale, True)
+    nchw = cuda(raw)
+    nhwc = nchw.contiguous(memory_format=torch.channels_last)
+    assert not nhwc.is_contiguous() and nhwc.shape == nchw.shape
+    got_a = einx.sparsify_full_resolution_descriptors(nchw, [cuda(p) for p in pos], scale, True)
+    got_b = einx.sparsify_full_resolution_descriptors(nhwc, [cuda(p) for p in pos], scale, True)
+    for a, b, r in zip(got_a, got_b, ref):
+        assert a.shape == r.shape and b.shape == r.shape
+        assert np.abs(b.cpu().numpy() - r).max() < 2e-6 if r.size else True
+        assert np.abs(a.cpu().numpy() - b.cpu().numpy()).max() < 2e-6 if r.size else True
+    # padded form: rows beyond the count are zero
+    kpts, counts = importlib_describe().pack_rows([cuda(p) for p in pos], 3, DEV)
+    desc = einx.sample(nhwc, kpts, counts, 0, (Hp, Wp), scale, True)
+    for i in range(B):
+        assert not desc[i, len(pos[i]):].any()
+
+
+def importlib_describe():
+    import importlib
+
+    return importlib.import_module("ei-nexus_official_b200.describe")
 
 
 # ------------------------------------------------------------------ MNN ------------- #

@@ -28,3 +28,11 @@ for (B, Hp, Wp, K) in [(64, 184, 240, 1024), (32, 260, 346, 2048), (32, 264, 352
         ts.append(ctx.profile_read()[1])
     ctx.profile(False)
     print(f"detect B={B} {Hp}x{Wp} k={K}: kernel {np.median(ts) * 1e3:.1f} us (min {min(ts) * 1e3:.1f})", flush=True)
+    if B > 1:
+        ctx.profile(True)
+        ts = []
+        for i in range(3):
+            det.detect_pair(copies[2 * i].copy_(s), copies[2 * i + 1].copy_(s), 1.0, 4, 4, K, kcap=K)
+            ts.append(ctx.profile_read()[1])
+        ctx.profile(False)
+        print(f"detect_pair 2x{B} {Hp}x{Wp} k={K}: kernel {np.median(ts) * 1e3:.1f} us (min {min(ts) * 1e3:.1f})", flush=True)
