@@ -67,18 +67,22 @@ assignment_filter_kernel(const unsigned long long* __restrict__ rowkey, const un
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long* rk = rowkey + (size_t)b * M;
     const unsigned long long* ck = colkey + (size_t)b * N;
+    // A key of 0 means "no candidate": the carried-keys producer skips rows / columns whose best value is -inf or
+    // NaN (a diverged model), and key_index(0) would be -1.
     if (t < M) {
         const unsigned long long k = rk[t];
-        const int j = key_index(k);
-        const bool mutual = key_index(ck[j]) == t;                      // indices0 == m1.gather(1, m0)
+        const int j = k ? key_index(k) : 0;
+        const unsigned long long kc = k ? ck[j] : 0ull;
+        const bool mutual = k && kc && key_index(kc) == t;              // indices0 == m1.gather(1, m0)
         const float s = mutual ? expf(key_value(k)) : 0.0f;             // where(mutual0, max0.exp(), 0)
         m0[(size_t)b * M + t] = (mutual && s > th) ? j : -1;
         ms0[(size_t)b * M + t] = s;
     }
     if (t < N) {
-        const int i = key_index(ck[t]);
-        const unsigned long long k = rk[i];
-        const bool mutual = key_index(k) == t;                          // indices1 == m0.gather(1, m1)
+        const unsigned long long kc = ck[t];
+        const int i = kc ? key_index(kc) : 0;
+        const unsigned long long k = kc ? rk[i] : 0ull;
+        const bool mutual = kc && k && key_index(k) == t;               // indices1 == m0.gather(1, m1)
         const float s = mutual ? expf(key_value(k)) : 0.0f;             // mscores0.gather(1, m1) under mutual1
         m1[(size_t)b * N + t] = (mutual && s > th) ? i : -1;            // valid0.gather(1, m1)
         ms1[(size_t)b * N + t] = s;

@@ -105,7 +105,7 @@ class _PointsMap(torch.Tensor):
     @staticmethod
     def wrap(t, kpts, counts):
         out = t.as_subclass(_PointsMap)
-        out._einx_kpts = (kpts, counts)
+        out._einx_kpts = (kpts, counts, t._version)  # the rows describe this version of the map only
         return out
 
 
@@ -135,8 +135,8 @@ def unpack_rows(rows: torch.Tensor, counts: torch.Tensor) -> Tuple[torch.Tensor,
 def prob_map_to_positions_with_prob(prob_map: torch.Tensor, threshold: float = 0.0, ordering: str = "yx"):
     """Drop-in for ``detector_util.py:451-484``: tuple of (N_i, 3) rows (y+.5, x+.5, prob)."""
     cached = getattr(prob_map, "_einx_kpts", None)
-    if cached is not None and threshold == 0.0:
-        kpts, counts = cached
+    if cached is not None and threshold == 0.0 and cached[2] == prob_map._version:  # unmodified since the launch
+        kpts, counts = cached[0], cached[1]
     else:
         # stand-alone compaction of `prob_map > threshold` (no NMS, no border): same kernel, r = 0
         pm = prob_map.as_subclass(torch.Tensor).clone().contiguous()

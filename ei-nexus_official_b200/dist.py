@@ -21,8 +21,12 @@ def pack_matches(matches0: torch.Tensor, num_matches: torch.Tensor) -> torch.Ten
     return torch.cat((num_matches.to(torch.int32)[:, None], matches0.to(torch.int32)), dim=1).contiguous()
 
 
-def gather_matches(packed: torch.Tensor, per_rank: int) -> torch.Tensor:
-    """all_gather of equally-shaped packed buffers (ranks with fewer pairs pad with -2 rows)."""
+def gather_matches(packed: torch.Tensor, per_rank: int, total: int = None) -> torch.Tensor:
+    """all_gather of equally-shaped packed buffers (ranks with fewer pairs pad with -2 rows).
+
+    One collective and no host synchronisation: the result is the (world * per_rank, K + 1) buffer itself; when the
+    global number of pairs ``total`` is given (contiguous shards, ``shard_range``), the padding rows are dropped
+    with index arithmetic done on the host instead of a device-side mask."""
     if not (dist.is_available() and dist.is_initialized()):
         return packed
     world = dist.get_world_size()
@@ -31,4 +35,10 @@ def gather_matches(packed: torch.Tensor, per_rank: int) -> torch.Tensor:
         packed = torch.cat((packed, pad), 0)
     out = packed.new_empty((world * per_rank, packed.shape[1]))
     dist.all_gather_into_tensor(out, packed.contiguous())
-    return out[out[:, 0] != -2]
+    if total is None or total == world * per_rank:
+        return out
+    parts = []
+    for r in range(world):
+        lo, hi = shard_range(total, r, world)
+        parts.append(out[r * per_rank: r * per_rank + (hi - lo)])
+    return torch.cat(parts, 0)

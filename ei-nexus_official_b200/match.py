@@ -44,6 +44,8 @@ def mnn(desc0: torch.Tensor, desc1: torch.Tensor, n0: Optional[torch.Tensor] = N
     s1 = torch.empty((B, M), dtype=torch.float32, device=dev)
     mk0 = mk1 = nm = None
     if kpts0 is not None:
+        if kpts0.shape[-1] != 3 or kpts1.shape[-1] != 3:
+            raise ValueError("mnn: keypoint rows must be (y, x, prob) -- three columns")
         kpts0, kpts1 = kpts0.contiguous(), kpts1.contiguous()
         mk0 = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
         mk1 = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
@@ -57,6 +59,15 @@ def mnn(desc0: torch.Tensor, desc1: torch.Tensor, n0: Optional[torch.Tensor] = N
     if kpts0 is not None:
         out.update(matched_kpts0=mk0, matched_kpts1=mk1, num_matches=nm)
     return out
+
+
+def _rows3(kpts: torch.Tensor) -> torch.Tensor:
+    """(B, N, 2 | 3 | more) keypoints -> (B, N, 3) fp32: the kernels read rows of three floats (y, x, prob);
+    two-column positions get a zero third column, extra columns are dropped."""
+    k = kpts[..., :3].float()
+    if k.shape[-1] < 3:
+        k = torch.cat((k, k.new_zeros(k.shape[:-1] + (3 - k.shape[-1],))), dim=-1)
+    return k
 
 
 @torch.no_grad()
@@ -104,7 +115,7 @@ class NearestNeighborMatcher(nn.Module):
                 "similarity": desc0.new_zeros((b, n, m)) if dense else None,
                 "log_assignment": desc0.new_zeros((b, n + 1, m + 1)) if dense else None,
             }
-        out = mnn(desc0, desc1, None, None, kpts0[..., :3].float(), kpts1[..., :3].float(), self.ratio_thresh,
+        out = mnn(desc0, desc1, None, None, _rows3(kpts0), _rows3(kpts1), self.ratio_thresh,
                   self.distance_thresh, self.mutual_check, self.precision)
         if self.mutual_check:
             assert (out["matches0"] > -1).sum() == (out["matches1"] > -1).sum()  # MNN.py:95

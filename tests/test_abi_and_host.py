@@ -139,20 +139,84 @@ def test_fp16x3_needs_bounded_descriptors(einx):
 def test_patch_reference_swaps_adjacent_rows(einx):
     import types
 
+    import torch
+
+    calls = []
+
+    def ref_fn(name):
+        def f(*a, **k):
+            calls.append(name)
+            return "reference"
+        f.__module__ = "fake_ref"
+        return f
+
     fake = types.ModuleType("fake_ref.detector_util")
     for name in ("logits_to_prob", "depth_to_space", "prob_map_to_points_map"):
-        setattr(fake, name, lambda *a, **k: None)
+        setattr(fake, name, ref_fn(name))
     lg = types.ModuleType("fake_ref.lightglue")
-    lg.filter_matches = lambda *a, **k: None
-    lg.sigmoid_log_double_softmax = lambda *a, **k: None
+    lg.filter_matches = ref_fn("filter_matches")
+    lg.sigmoid_log_double_softmax = ref_fn("sigmoid_log_double_softmax")
     vis = types.ModuleType("fake_ref.visualize")
-    vis.draw_events_accumulation_image = lambda *a, **k: None
+    vis.draw_events_accumulation_image = ref_fn("draw_events_accumulation_image")
     done = einx.patch_reference([fake, lg, vis])
-    assert fake.logits_to_prob is einx.logits_to_prob and fake.depth_to_space is einx.depth_to_space
+    # inference-side functions are replaced outright
+    assert fake.prob_map_to_points_map is einx.prob_map_to_points_map
     assert lg.filter_matches is einx.filter_matches
-    assert lg.sigmoid_log_double_softmax is einx.sigmoid_log_double_softmax
-    assert vis.draw_events_accumulation_image is einx.draw_events_accumulation_image
-    assert set(done) == {"fake_ref.detector_util", "fake_ref.lightglue", "fake_ref.visualize"}
+    # dataset-side functions run in DataLoader workers: only on request
+    assert "fake_ref.visualize" not in done and not hasattr(vis.draw_events_accumulation_image, "_einx_guard")
+    assert set(done) == {"fake_ref.detector_util", "fake_ref.lightglue"}
+    # differentiable outputs: the kernels are forward only, so a tensor that requires grad goes to the reference
+    x = torch.zeros(1, 65, 2, 2, requires_grad=True)
+    assert fake.logits_to_prob(x) == "reference" and fake.depth_to_space(x, 8) == "reference"
+    assert lg.sigmoid_log_double_softmax(x, x, x) == "reference"
+    assert calls == ["logits_to_prob", "depth_to_space", "sigmoid_log_double_softmax"]
+    with torch.no_grad(), pytest.raises(einx.EinxError):  # inference: ours (which refuses CPU tensors -- no fallback)
+        fake.logits_to_prob(x)
+    with pytest.raises(einx.EinxError):
+        fake.logits_to_prob(x.detach())
+    # patching twice does not wrap a wrapper
+    assert einx.patch_reference([fake, lg, vis]) == {}
+    done = einx.patch_reference([vis], datasets=True)
+    assert done == {"fake_ref.visualize": ["draw_events_accumulation_image"]}
+    assert vis.draw_events_accumulation_image._einx_original.__module__ == "fake_ref"
+
+
+def test_dataset_functions_defer_to_reference_in_loader_workers(einx):
+    """A patched events_to_voxel_grid inside a (forked) DataLoader worker must not touch CUDA."""
+    import types
+
+    import torch
+
+    ds_mod = types.ModuleType("fake_ref.representations")
+
+    def ref_voxel(events, input_size, normalize=True):
+        return torch.full(tuple(input_size), 7.0)
+
+    ref_voxel.__module__ = "fake_ref"
+    ds_mod.events_to_voxel_grid = ref_voxel
+    einx.patch_reference([ds_mod], datasets=True)
+
+    class DS(torch.utils.data.Dataset):
+        def __len__(self):
+            return 2
+
+        def __getitem__(self, i):
+            ev = {k: np.zeros(4) for k in "xytp"}
+            return ds_mod.events_to_voxel_grid(ev, (2, 3, 4))
+
+    out = next(iter(torch.utils.data.DataLoader(DS(), batch_size=2, num_workers=1)))
+    assert out.shape == (2, 2, 3, 4) and bool((out == 7.0).all())
+
+
+def test_points_map_cache_is_versioned(einx):
+    import torch
+
+    det = importlib.import_module("ei-nexus_official_b200.detection")
+    t = torch.zeros(1, 4, 4)
+    wrapped = det._PointsMap.wrap(t, "kpts", "counts")
+    assert wrapped._einx_kpts[2] == t._version
+    wrapped.mul_(2.0)  # an in-place edit invalidates the carried keypoints
+    assert wrapped._einx_kpts[2] != wrapped._version
 
 
 def test_log_double_softmax_host_checks(einx):

@@ -24,7 +24,9 @@ def _worker(rank, world, port, total, K, ret):
         all_n = (all_m > -1).sum(1).to(torch.int32)
         packed = einx.pack_matches(all_m[lo:hi], all_n[lo:hi])
         per_rank = (total + world - 1) // world
-        full = einx.gather_matches(packed, per_rank)
+        full = einx.gather_matches(packed, per_rank, total)
+        raw = einx.gather_matches(packed, per_rank)  # no trimming: one collective, padding rows (-2) kept
+        assert raw.shape == (world * per_rank, K + 1)
         ok = full.shape == (total, K + 1) and torch.equal(full[:, 1:].long(), all_m) and torch.equal(full[:, 0], all_n)
         ret[rank] = bool(ok)
     finally:
