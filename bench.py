@@ -12,9 +12,9 @@ Prints ONE JSON line on stdout (rank 0); everything else goes to stderr.
                its events and maps host->device and reads the matches back device->host
   roofline     dominant kernel of the step: algorithmic bytes (or flops) / its CUDA-event time,
                against MEASURED_PEAKS.json
-  cpu_baseline the oracle port of the reference algorithm on this box's host cores (bounded sample)
-  --impl reference   times only that CPU port (the reference is Python and cannot travel to the
-               GPU box; oracle/einx_oracle.py restates it and is pinned to reference-made goldens)
+  cpu_baseline the reference's own functions (oracle/_ref/, made by oracle/make_ref.py) on this box's host cores,
+               bounded sample; the numpy port's figure beside it (`port_value`)
+  --impl reference   times only that CPU arm (oracle/_ref/ when it travelled with the tree, else the port)
 """
 from __future__ import annotations
 
@@ -68,35 +68,55 @@ def make_batch(synth, cfg_name, batch, first_sample, n_events=None):
 # CPU arm: the oracle port over all host cores
 # --------------------------------------------------------------------------------------------- #
 def _cpu_pair(args):
-    from oracle import einx_oracle as O
-
-    cfg, ev, s0, r0, s1, r1 = args
+    """One pair through the CPU arm: `impl` = "reference" (the reference's own functions, oracle/ref_arm.py over
+    oracle/_ref/) or "port" (the numpy restatement, oracle/einx_oracle.py).  One process per core, one thread each."""
+    impl, cfg, ev, s0, r0, s1, r1 = args
     try:
         from threadpoolctl import threadpool_limits
         ctxm = threadpool_limits(limits=1)
     except Exception:  # pragma: no cover
         import contextlib
         ctxm = contextlib.nullcontext()
+    kind = "full" if cfg["kind"] == "gather" else "low"
     with ctxm:
-        _, p0, p1, m = O.pair_pipeline(ev, cfg["bins"], cfg["H"], cfg["W"], s0.copy(), r0, s1.copy(), r1,
-                                       "full" if cfg["kind"] == "gather" else "low", cfg["top_k"], cfg["scale"])
+        if impl == "reference":
+            import torch
+
+            from oracle import ref_arm
+            torch.set_num_threads(1)
+            _, p0, p1, m = ref_arm.pair_pipeline(ev, cfg["bins"], cfg["H"], cfg["W"], s0.copy(), r0, s1.copy(), r1, kind,
+                                                 cfg["top_k"], cfg["scale"])
+        else:
+            from oracle import einx_oracle as O
+            _, p0, p1, m = O.pair_pipeline(ev, cfg["bins"], cfg["H"], cfg["W"], s0.copy(), r0, s1.copy(), r1, kind,
+                                           cfg["top_k"], cfg["scale"])
     return int((m["matches0"] > -1).sum())
 
 
-def cpu_pairs_per_sec(synth, cfg_name, pairs, budget_s=12.0, workers=None):
-    """Run the oracle pipeline over all host cores for about `budget_s` seconds of wall time (a bounded
-    sample: the same `pairs` inputs are re-run); returns (pairs/s, cores, secs, pairs_done)."""
+def cpu_arm_kind():
+    """"reference" when the reference's own leaf modules travelled with the tree (oracle/_ref/), else "port"."""
+    from oracle import ref_arm
+    return "reference" if ref_arm.available() else "port"
+
+
+def cpu_jobs(synth, cfg_name, pairs, impl):
+    cfg = synth.CONFIGS[cfg_name]
+    evs, s0, r0, s1, r1 = make_batch(synth, cfg_name, pairs, 0)
+    return [(impl, cfg, evs[i], s0[i:i + 1], r0[i:i + 1], s1[i:i + 1], r1[i:i + 1]) for i in range(pairs)]
+
+
+def cpu_pairs_per_sec(synth, cfg_name, pairs, impl, budget_s=12.0, workers=None):
+    """Run the CPU arm over all host cores for about `budget_s` seconds of wall time (a bounded sample: the same
+    `pairs` inputs are re-run, at least once); returns (pairs/s, cores, secs, pairs_done)."""
     import multiprocessing as mp
 
-    cfg = synth.CONFIGS[cfg_name]
     cores = workers or os.cpu_count() or 1
     cores = max(1, min(cores, pairs))
-    evs, s0, r0, s1, r1 = make_batch(synth, cfg_name, pairs, 0)
-    jobs = [(cfg, evs[i], s0[i:i + 1], r0[i:i + 1], s1[i:i + 1], r1[i:i + 1]) for i in range(pairs)]
+    jobs = cpu_jobs(synth, cfg_name, pairs, impl)
     ctx = mp.get_context("fork")
     done, total = 0, 0.0
     with ctx.Pool(cores) as pool:
-        pool.map(_cpu_pair, jobs[:cores])  # warm the workers (imports, page faults)
+        pool.map(_cpu_pair, [("port",) + j[1:] for j in jobs[:cores]])  # warm the workers (imports, page faults)
         while total < budget_s:
             t0 = time.perf_counter()
             pool.map(_cpu_pair, jobs, chunksize=1)
@@ -106,18 +126,20 @@ def cpu_pairs_per_sec(synth, cfg_name, pairs, budget_s=12.0, workers=None):
 
 
 def run_reference(args, synth):
-    """--impl reference: the CPU port of the reference path, all host cores, same metric / config."""
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref/: its functions in its
+    call order, per-sample matcher loop and per-keypoint Python loop included) on all host cores, same metric and
+    config; the numpy port stands in only where oracle/_ref/ did not travel.  A step is a bounded sample of the
+    batch: one pair per host core, run side by side (a pair takes seconds on a core)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cfg_name = args.config
     cores = os.cpu_count() or 1
-    pairs = max(cores, min(args.batch, 2 * cores))  # a bounded sample of the batch per step
-    cfg = synth.CONFIGS[cfg_name]
+    kind = cpu_arm_kind()
+    pairs = cores if kind == "reference" else max(cores, min(args.batch, 2 * cores))
     import multiprocessing as mp
 
-    evs, s0, r0, s1, r1 = make_batch(synth, cfg_name, pairs, 0)
-    jobs = [(cfg, evs[i], s0[i:i + 1], r0[i:i + 1], s1[i:i + 1], r1[i:i + 1]) for i in range(pairs)]
+    jobs = cpu_jobs(synth, cfg_name, pairs, kind)
     times = []
     with mp.get_context("fork").Pool(min(cores, pairs)) as pool:
         for step in range(args.warmup + args.steps):
@@ -128,13 +150,15 @@ def run_reference(args, synth):
                 times.append(dt)
     total = sum(times)
     value = pairs * len(times) / total
+    what = ("the reference's own functions (oracle/_ref/), one process per core, one thread each" if kind == "reference"
+            else "numpy port of the reference (oracle/einx_oracle.py), one process per core")
     line = {
         "impl": "reference", "metric": "pairs/sec (voxel+detect+MNN)", "value": value, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, synth),
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": min(cores, pairs), "kind": "port",
-                         "sample": f"{pairs} pairs of the workload per step, one oracle process per core"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": min(cores, pairs), "kind": kind,
+                         "sample": f"{pairs} pairs of the workload per step: {what}"},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -469,11 +493,23 @@ def run_einx(args, synth):
             roof["note"] = ("largest share only as the sum of its two launches (one per side); iterative NMS in shared memory is "
                             "bound by instruction issue (48 % of issue slots under ncu), not by HBM: the map is read once, "
                             "12 MB per launch.  Per launch the MNN kernel is the longest: see kernels.mnn_similarity")
-        log("timing the CPU baseline (oracle port) ...")
         cores = os.cpu_count() or 1
-        cpu_pairs = max(cores, min(2 * cores, 64))
-        cpu_val, cpu_cores, cpu_secs, cpu_done = (cpu_pairs_per_sec(synth, args.config, cpu_pairs) if world == 1 and not args.skip_cpu
-                                                  else (None, None, None, None))
+        cpu = None
+        if world == 1 and not args.skip_cpu:
+            kind = cpu_arm_kind()
+            log(f"timing the CPU baseline ({kind}) ...")
+            if kind == "reference":
+                v, cc, secs, done = cpu_pairs_per_sec(synth, args.config, cores, "reference", budget_s=10.0)
+                pv, _, psecs, pdone = cpu_pairs_per_sec(synth, args.config, max(cores, min(2 * cores, 64)), "port", budget_s=4.0)
+                cpu = {"value": v, "unit": "pairs/s", "cores": cc, "kind": "reference",
+                       "sample": f"{done} pairs of the workload in {secs:.1f}s through the reference's own functions "
+                                 f"(oracle/_ref/), one process per core, one thread each",
+                       "port_value": pv, "port_sample": f"{pdone} pairs in {psecs:.1f}s through the numpy port (oracle/einx_oracle.py)"}
+            else:
+                cpu_pairs = max(cores, min(2 * cores, 64))
+                v, cc, secs, done = cpu_pairs_per_sec(synth, args.config, cpu_pairs, "port")
+                cpu = {"value": v, "unit": "pairs/s", "cores": cc, "kind": "port",
+                       "sample": f"{done} pairs ({cpu_pairs} distinct) of the workload in {secs:.1f}s, one oracle process per core"}
         line = {
             "metric": "pairs/sec (voxel+detect+MNN)", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -483,9 +519,7 @@ def run_einx(args, synth):
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "kernels": kernels,
             "stages": stages,
-            "cpu_baseline": ({"value": cpu_val, "unit": "pairs/s", "cores": cpu_cores, "kind": "port",
-                              "sample": f"{cpu_done} pairs ({cpu_pairs} distinct) of the workload in {cpu_secs:.1f}s, one oracle process per core"}
-                             if cpu_val is not None else None),
+            "cpu_baseline": cpu,
             "gather_ms": gather_ms,
         }
         print(json.dumps(line), flush=True)
