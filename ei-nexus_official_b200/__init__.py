@@ -12,9 +12,11 @@ from .detection import (depth_to_space, detect, detect_pair, events_mask, logits
                         prob_map_to_positions_with_prob)
 from .dist import gather_matches, pack_matches, shard_range
 from .match import NearestNeighborMatcher, filter_matches, mnn, mnn_dense, sigmoid_log_double_softmax
+from .metrics import Repeatability, gt_assign, pairwise_min_dist
 from .patch import patch_reference
 from .pipeline import CapturedStep, ExtractMatchPipeline, HostBatch, HostStreamer, PathConfig
-from .voxel import (draw_events_accumulation_image, event_stack_device, events_image_device, events_to_event_stack,
+from .voxel import (distance_map_device, draw_events_accumulation_image, event_stack_device, events_image_signed_device,
+                    events_to_distance_map, events_image_device, events_to_event_stack,
                     events_to_time_surface, events_to_voxel_grid, pack_events, time_normalization, time_surface_device,
                     voxelize_batch, voxelize_device)
 
@@ -26,4 +28,5 @@ __all__ = [
     "gather_matches", "logits_to_prob", "depth_to_space", "logits_to_score", "events_mask",
     "draw_events_accumulation_image", "events_image_device", "filter_matches", "events_to_event_stack",
     "events_to_time_surface", "event_stack_device", "time_surface_device", "sigmoid_log_double_softmax",
+    "events_to_distance_map", "distance_map_device", "events_image_signed_device", "Repeatability", "gt_assign", "pairwise_min_dist",
 ]

@@ -32,6 +32,11 @@ SIGNATURES = {
                            C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "einx_mnn_dense": (C.c_int, [c_ctx, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "einx_events_image": (C.c_int, [c_ctx, _P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "einx_events_image_signed": (C.c_int, [c_ctx, _P, _P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "einx_distance_map": (C.c_int, [c_ctx, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "einx_pairwise_min_dist": (C.c_int, [c_ctx, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "einx_gt_assign": (C.c_int, [c_ctx, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                 _P, _P, _P, _P, _P]),
     "einx_event_stack": (C.c_int, [c_ctx, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "einx_time_surface": (C.c_int, [c_ctx, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "einx_unpack_events": (C.c_int, [c_ctx, _P, _P, _P, C.c_int64, _P, _P, _P, _P]),

@@ -11,17 +11,19 @@
 
 namespace {
 
+// pol == nullptr: += 1 per event (dict branch, visualize.py:37-40); else += 2 * p - 1 (array branch, :42-44)
 template <typename T>
 __global__ void __launch_bounds__(256)
-events_count_kernel(const T* __restrict__ x, const T* __restrict__ y, const int64_t* __restrict__ off, int H, int W,
-                    int* __restrict__ cnt) {
+events_count_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ pol,
+                    const int64_t* __restrict__ off, int H, int W, int* __restrict__ cnt) {
     const int b = blockIdx.y;
     const int64_t beg = off[b], end = off[b + 1];
     int* c = cnt + (size_t)b * H * W;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = beg + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) {
         const int ix = (int)__ldg(x + i), iy = (int)__ldg(y + i);  // int() truncates toward zero
-        if ((unsigned)ix < (unsigned)W && (unsigned)iy < (unsigned)H) atomicAdd(c + (size_t)iy * W + ix, 1);
+        const int w = pol ? (int)(2.0 * (double)__ldg(pol + i) - 1.0) : 1;  // integer-valued polarities (host-checked)
+        if ((unsigned)ix < (unsigned)W && (unsigned)iy < (unsigned)H) atomicAdd(c + (size_t)iy * W + ix, w);
     }
 }
 
@@ -94,14 +96,15 @@ unpack_events_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict_
 
 }  // namespace
 
-extern "C" int einx_events_image(einx_ctx* ctx, const void* x, const void* y, int coord_f64, const int64_t* ev_offsets,
-                                 int B, int H, int W, uint8_t* image, einx_stream stream_) {
-    if (!ctx) return EINX_ERR_INVALID;
-    if (B < 0 || H <= 0 || W <= 0) return einx_fail(ctx, EINX_ERR_INVALID, "einx_events_image: bad shape B=%d H=%d W=%d", B, H, W);
+namespace {
+
+int events_image_impl(einx_ctx* ctx, const char* who, const void* x, const void* y, const void* pol, int coord_f64,
+                      const int64_t* ev_offsets, int B, int H, int W, uint8_t* image, einx_stream stream_) {
+    if (B < 0 || H <= 0 || W <= 0) return einx_fail(ctx, EINX_ERR_INVALID, "%s: bad shape B=%d H=%d W=%d", who, B, H, W);
     if (B == 0) return EINX_OK;
-    if (!x || !y || !ev_offsets || !image) return einx_fail(ctx, EINX_ERR_INVALID, "einx_events_image: NULL pointer argument");
-    if (B > 65535) return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_events_image: B=%d > 65535", B);
-    if ((size_t)H * W > (size_t)INT_MAX) return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_events_image: image too large");
+    if (!x || !y || !ev_offsets || !image) return einx_fail(ctx, EINX_ERR_INVALID, "%s: NULL pointer argument", who);
+    if (B > 65535) return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "%s: B=%d > 65535", who, B);
+    if ((size_t)H * W > (size_t)INT_MAX) return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "%s: image too large", who);
     DeviceGuard guard(ctx->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const size_t npix = (size_t)H * W;
@@ -113,13 +116,28 @@ extern "C" int einx_events_image(einx_ctx* ctx, const void* x, const void* y, in
     if (per_window < 1) per_window = 1;
     if (per_window > 1024) per_window = 1024;
     if (coord_f64)
-        events_count_kernel<double><<<dim3(per_window, B), 256, 0, stream>>>((const double*)x, (const double*)y, ev_offsets, H, W, cnt);
+        events_count_kernel<double><<<dim3(per_window, B), 256, 0, stream>>>((const double*)x, (const double*)y, (const double*)pol, ev_offsets, H, W, cnt);
     else
-        events_count_kernel<float><<<dim3(per_window, B), 256, 0, stream>>>((const float*)x, (const float*)y, ev_offsets, H, W, cnt);
+        events_count_kernel<float><<<dim3(per_window, B), 256, 0, stream>>>((const float*)x, (const float*)y, (const float*)pol, ev_offsets, H, W, cnt);
     EINX_CHECK_LAUNCH(ctx);
     events_normalize_kernel<<<B, kNormThreads, 0, stream>>>(cnt, (int)npix, image);
     EINX_CHECK_LAUNCH(ctx);
     return EINX_OK;
+}
+
+}  // namespace
+
+extern "C" int einx_events_image(einx_ctx* ctx, const void* x, const void* y, int coord_f64, const int64_t* ev_offsets,
+                                 int B, int H, int W, uint8_t* image, einx_stream stream_) {
+    if (!ctx) return EINX_ERR_INVALID;
+    return events_image_impl(ctx, "einx_events_image", x, y, nullptr, coord_f64, ev_offsets, B, H, W, image, stream_);
+}
+
+extern "C" int einx_events_image_signed(einx_ctx* ctx, const void* x, const void* y, const void* p, int coord_f64,
+                                        const int64_t* ev_offsets, int B, int H, int W, uint8_t* image, einx_stream stream_) {
+    if (!ctx) return EINX_ERR_INVALID;
+    if (B > 0 && !p) return einx_fail(ctx, EINX_ERR_INVALID, "einx_events_image_signed: NULL pointer argument");
+    return events_image_impl(ctx, "einx_events_image_signed", x, y, p, coord_f64, ev_offsets, B, H, W, image, stream_);
 }
 
 extern "C" int einx_mask_dilate(einx_ctx* ctx, const uint8_t* image, int B, int H, int W, int pad_top, int pad_left, int Hp,

@@ -26,7 +26,7 @@ import sys
 
 import torch
 
-from . import describe, detection as detect, match, voxel
+from . import describe, detection as detect, match, metrics, voxel
 
 _FUNCS = {
     "prob_map_to_points_map": detect.prob_map_to_points_map,
@@ -39,6 +39,7 @@ _FUNCS = {
     "depth_to_space": detect.depth_to_space,
     "filter_matches": match.filter_matches,
     "sigmoid_log_double_softmax": match.sigmoid_log_double_softmax,
+    "Repeatability": metrics.Repeatability,   # core/metrics/keypoints_metrics.py:52 (train_extractor.py:189, val_extractor.py:75)
 }
 # called from Dataset.__getitem__ (datasets/MVSEC.py:850-860, datasets/EC.py:300-306)
 _DATASET_FUNCS = {
@@ -46,13 +47,15 @@ _DATASET_FUNCS = {
     "draw_events_accumulation_image": voxel.draw_events_accumulation_image,
     "events_to_event_stack": voxel.events_to_event_stack,
     "events_to_time_surface": voxel.events_to_time_surface,
+    "events_to_distance_map": voxel.events_to_distance_map,
 }
 # outputs the reference differentiates through when it trains the extractor / matcher
 _GRAD_SENSITIVE = ("logits_to_prob", "depth_to_space", "sparsify_full_resolution_descriptors",
                    "sparsify_low_resolution_descriptors", "sigmoid_log_double_softmax")
 
 _MODULE_HINTS = ("representations", "detector_util", "descriptor_util", "MNN", "EventExtractors",
-                 "superpoint_extractor", "silk_extractor", "Matchers", "MVSEC", "EC", "visualize", "lightglue")
+                 "superpoint_extractor", "silk_extractor", "Matchers", "MVSEC", "EC", "visualize", "lightglue",
+                 "keypoints_metrics", "train_extractor", "val_extractor")
 
 
 def _needs_grad(args, kwargs) -> bool:

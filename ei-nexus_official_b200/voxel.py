@@ -120,18 +120,50 @@ def events_image_device(x: torch.Tensor, y: torch.Tensor, offsets: torch.Tensor,
     return out
 
 
+@torch.no_grad()
+def events_image_signed_device(x: torch.Tensor, y: torch.Tensor, p: torch.Tensor, offsets: torch.Tensor, height: int,
+                               width: int) -> torch.Tensor:
+    """einx_events_image_signed (every event adds 2 * p - 1) on device-resident arrays -> (B, H, W) uint8."""
+    dev = x.device
+    if not x.is_cuda:
+        raise _lib.EinxError("events_image: expected CUDA tensors (there is no CPU fallback)")
+    if not (x.dtype == y.dtype == p.dtype) or x.dtype not in (torch.float32, torch.float64):
+        raise ValueError("events_image: x, y and p must all be float32 or all float64")
+    if offsets.dtype != torch.int64:
+        raise ValueError("events_image: offsets must be int64")
+    ctx = _lib.context_for(dev)
+    B = offsets.numel() - 1
+    out = torch.empty((B, int(height), int(width)), dtype=torch.uint8, device=dev)
+    rc = ctx.lib.einx_events_image_signed(ctx.handle, _lib.ptr(x.contiguous()), _lib.ptr(y.contiguous()),
+                                          _lib.ptr(p.contiguous()), int(x.dtype == torch.float64),
+                                          _lib.ptr(offsets.contiguous()), B, int(height), int(width), _lib.ptr(out), ctx.stream)
+    ctx.check(rc, "einx_events_image_signed")
+    return out
+
+
 def draw_events_accumulation_image(events, image_shape, device="cuda") -> np.ndarray:
-    """Drop-in for ``datasets/visualize.py:23-49`` (dict branch): (H, W) uint8 numpy image.
+    """Drop-in for ``datasets/visualize.py:23-49``: (H, W) uint8 numpy image.
 
     ``image_shape`` is (W, H) like the reference's ``RESOLUTION`` tuples.  The coordinates cross to the
-    device as fp64, so ``int()`` truncation matches the reference's per-event Python loop exactly."""
-    if not isinstance(events, dict):
-        raise ValueError("events must be a dictionary (the (N, 4) array branch of the reference is not on the path)")
+    device as fp64, so ``int()`` truncation matches the reference's per-event Python loop exactly.  A dict counts
+    events per pixel (:37-40); an (N, 4) array of (x, y, t, p) rows adds ``2 * p - 1`` per event (:41-44) -- the sums
+    stay exact for integer-valued ``2 * p - 1`` (polarities 0/1 or -1/1), anything else is refused."""
     dev = torch.device(device)
-    x = torch.from_numpy(np.ascontiguousarray(events["x"], dtype=np.float64)).to(dev)
-    y = torch.from_numpy(np.ascontiguousarray(events["y"], dtype=np.float64)).to(dev)
-    off = torch.tensor([0, x.numel()], dtype=torch.int64, device=dev)
-    return events_image_device(x, y, off, image_shape[1], image_shape[0])[0].cpu().numpy()
+    if isinstance(events, dict):
+        x = torch.from_numpy(np.ascontiguousarray(events["x"], dtype=np.float64)).to(dev)
+        y = torch.from_numpy(np.ascontiguousarray(events["y"], dtype=np.float64)).to(dev)
+        off = torch.tensor([0, x.numel()], dtype=torch.int64, device=dev)
+        return events_image_device(x, y, off, image_shape[1], image_shape[0])[0].cpu().numpy()
+    if isinstance(events, np.ndarray):
+        if events.ndim != 2 or events.shape[1] < 4:
+            raise ValueError("events array must have shape [N, 4]")
+        w = 2.0 * events[:, 3].astype(np.float64) - 1.0
+        if not np.all(w == np.round(w)):
+            raise ValueError("draw_events_accumulation_image: 2 * p - 1 must be integer-valued (polarities 0/1 or -1/1)")
+        cols = [torch.from_numpy(np.ascontiguousarray(events[:, k], dtype=np.float64)).to(dev) for k in (0, 1, 3)]
+        off = torch.tensor([0, events.shape[0]], dtype=torch.int64, device=dev)
+        return events_image_signed_device(cols[0], cols[1], cols[2], off, image_shape[1], image_shape[0])[0].cpu().numpy()
+    raise ValueError("events must be a dictionary or numpy array.")
 
 
 # --------------------------------------------------------------------------------------------- #
@@ -183,3 +215,28 @@ def events_to_event_stack(events: Dict, input_size: Tuple, device="cuda") -> tor
 def events_to_time_surface(events: Dict, input_size: Tuple, device="cuda") -> torch.Tensor:
     """Drop-in for ``datasets/representations.py:25-63``: CPU fp32 (bins, H, W); ``events['t']`` is normalised."""
     return _single(events, time_surface_device, input_size, device)
+
+
+@torch.no_grad()
+def distance_map_device(x, y, t, offsets, input_size) -> torch.Tensor:
+    """einx_distance_map on device-resident SoA events -> (B, bins, H, W) fp32 (polarity is not used)."""
+    bins, H, W = (int(v) for v in input_size)
+    dev = x.device
+    if not x.is_cuda:
+        raise _lib.EinxError("einx_distance_map: expected CUDA tensors (there is no CPU fallback)")
+    for name, ten, dt in (("x", x, torch.float32), ("y", y, torch.float32), ("t", t, torch.float64),
+                          ("offsets", offsets, torch.int64)):
+        if ten.dtype != dt or not ten.is_contiguous() or ten.device != dev:
+            raise ValueError(f"{name}: expected contiguous {dt} on {dev}")
+    ctx = _lib.context_for(dev)
+    B = offsets.numel() - 1
+    out = torch.empty((B, bins, H, W), dtype=torch.float32, device=dev)
+    rc = ctx.lib.einx_distance_map(ctx.handle, _lib.ptr(x), _lib.ptr(y), _lib.ptr(t), _lib.ptr(offsets), B, bins, H, W,
+                                   _lib.ptr(out), ctx.stream)
+    ctx.check(rc, "einx_distance_map")
+    return out
+
+
+def events_to_distance_map(events: Dict, input_size: Tuple, device="cuda") -> torch.Tensor:
+    """Drop-in for ``datasets/representations.py:215-248``: CPU fp32 (bins, H, W); ``events['t']`` is normalised."""
+    return _single(events, lambda x, y, t, p, off, size: distance_map_device(x, y, t, off, size), input_size, device)

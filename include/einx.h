@@ -161,6 +161,15 @@ int einx_events_image(einx_ctx* ctx, const void* x, const void* y, int coord_f64
                       einx_stream stream);
 
 /*
+ * The (N, 4) ndarray branch of the same function (datasets/visualize.py:41-44): every event adds 2 * p - 1 to its
+ * pixel (a signed histogram), then the same min-max normalisation.  p has the dtype of x / y; 2 * p - 1 must be
+ * integer-valued (polarities 0/1 or -1/1; the host layer checks), which keeps the fp64 sums of the reference exact.
+ */
+int einx_events_image_signed(einx_ctx* ctx, const void* x, const void* y, const void* p, int coord_f64,
+                             const int64_t* ev_offsets, int B, int H, int W, uint8_t* image,
+                             einx_stream stream);
+
+/*
  * The reference's other scatter representations, selectable through `representation_type`
  * (datasets/MVSEC.py:706-718).  Same ragged SoA events as einx_voxelize (x, y, p fp32; t fp64, time-sorted);
  * time_normalization (datasets/representations.py:8-22) runs on the device in fp64, and an event belongs to
@@ -178,6 +187,20 @@ int einx_event_stack(einx_ctx* ctx, const float* x, const float* y, const double
                      const int64_t* ev_offsets, int B, int bins, int H, int W, float* out,
                      einx_stream stream);
 int einx_time_surface(einx_ctx* ctx, const float* x, const float* y, const double* t, const float* p,
+                      const int64_t* ev_offsets, int B, int bins, int H, int W, float* out,
+                      einx_stream stream);
+
+/*
+ * Event distance map.  Replaces datasets/representations.py:215-248 (events_to_distance_map): per time bin
+ * (i/bins <= t <= (i+1)/bins after time_normalization, both ends inclusive) the event pixels are marked and
+ * cv.distanceTransform(1 - event_map, cv.DIST_L2, 3) gives every pixel its 3x3 chamfer distance (axial 0.955,
+ * diagonal 1.3693) to the nearest event pixel.  Computed in closed form, fp64 rounded once: within 1e-6 relative
+ * of OpenCV (whose own IPP / fixed-point paths differ from each other by that much), bit-exact against the
+ * oracle.  A bin without events is FLT_MAX everywhere.  Polarity is not used.  Events outside [0,W)x[0,H) are
+ * skipped (the reference wraps negative indices or raises).
+ *   x, y fp32, t fp64 time-sorted, ev_offsets (B + 1) int64; out (B, bins, H, W) fp32; H, W <= 65534.
+ */
+int einx_distance_map(einx_ctx* ctx, const float* x, const float* y, const double* t,
                       const int64_t* ev_offsets, int B, int bins, int H, int W, float* out,
                       einx_stream stream);
 
@@ -248,6 +271,34 @@ int einx_log_double_softmax(einx_ctx* ctx, const float* sim, const float* z0, co
                             einx_stream stream);
 int einx_filter_matches_keys(einx_ctx* ctx, const uint64_t* best_keys, int B, int M, int N, float th,
                              int64_t* m0, int64_t* m1, float* ms0, float* ms1, einx_stream stream);
+
+/*
+ * Metric-side N x M reductions (the distance matrix is reduced along both axes and never stored).
+ *
+ * einx_pairwise_min_dist -- core/metrics/keypoints_metrics.py:110-124 (Repeatability.update_one):
+ *   norm = ||a[:, None, :2] - b[None, :, :2]||_2  (difference in fp32, squares / sum / sqrt in fp64, rounded to
+ *   fp32: what torch.linalg.norm does on the CPU);  rowmin[i] = min_j norm[i, j]  (torch.min(norm, 1), :120),
+ *   colmin[j] = min_i norm[i, j]  (torch.min(norm, 0), :117).  The caller counts `<= distance_thresh`.
+ *   a (B, N, 2), b (B, M, 2) fp32; na, nb (B) int32 valid counts or NULL; rowmin (B, N), colmin (B, M) fp32
+ *   (+inf beyond the counts and for an empty other side).
+ *
+ * einx_gt_assign -- core/geometry/gt_generation.py:96-126 (gt_matches_from_pose_depth, between `project` and the
+ *   epipolar pass):  dist0 = |kp0_1[i] - kp1[j]|^2, dist1 = |kp0[i] - kp1_0[j]|^2 (fp32), dist = max(dist0, dist1)
+ *   where visible0[i] & visible1[j] else +inf; min0 / min1 = first argmin along j / i; positive = mutual argmin
+ *   & dist < pos_th^2; negative0 = min_j dist0 > neg_th^2 & valid0 (negative1 alike with dist1);
+ *   m0 = -1 where negative0, else min0 where positive, else -2 (IGNORE_FEATURE); m1 alike.
+ *   kp* (B, N|M, 2) fp32 in the order the reference indexes them (after its `ordering` flip); visible*, valid*
+ *   (B, N|M) uint8; m0 (B, N), m1 (B, M) int64; min0, min1 optional int32 argmins (NULL to skip) from which the
+ *   caller scatters the dense `assignment`.  N, M >= 1 (an empty side is the reference's early return, :63-71).
+ */
+int einx_pairwise_min_dist(einx_ctx* ctx, const float* a, const float* b, const int32_t* na,
+                           const int32_t* nb, int B, int N, int M, float* rowmin, float* colmin,
+                           einx_stream stream);
+int einx_gt_assign(einx_ctx* ctx, const float* kp0, const float* kp1, const float* kp0_1,
+                   const float* kp1_0, const uint8_t* visible0, const uint8_t* visible1,
+                   const uint8_t* valid0, const uint8_t* valid1, int B, int N, int M, float pos_th,
+                   float neg_th, int64_t* m0, int64_t* m1, int32_t* min0, int32_t* min1,
+                   einx_stream stream);
 
 /* Number of kernel launches issued through `ctx` so far (bench.py's gpu_launches). */
 int64_t einx_launch_count(const einx_ctx* ctx);

@@ -653,3 +653,43 @@ def repeatability(points1, points2, img1_shape, img2_shape, homography, distance
     c2 = int((min2 <= distance_thresh).sum()) if m else 0
     value = (c1 + c2) / (n + m) if n + m > 0 else None
     return value, min1, min2
+
+
+def gt_assign(kp0, kp1, kp0_1, kp1_0, visible0, visible1, valid0, valid1, pos_th=3, neg_th=5):
+    """core/geometry/gt_generation.py:96-126 (gt_matches_from_pose_depth between `project` and the epipolar pass),
+    one batch item at a time.  kp* (B, N|M, 2) fp32 in the order the function indexes them; returns
+    (assignment (B, N, M) bool, m0 (B, N) int64, m1 (B, M) int64) with -1 = unmatched, -2 = ignore."""
+    kp0, kp1, kp0_1, kp1_0 = (np.asarray(a, dtype=F32) for a in (kp0, kp1, kp0_1, kp1_0))
+    B, N, M = kp0.shape[0], kp0.shape[1], kp1.shape[1]
+    assignment = np.zeros((B, N, M), dtype=bool)
+    m0 = np.full((B, N), -1, dtype=np.int64)
+    m1 = np.full((B, M), -1, dtype=np.int64)
+    if N == 0 or M == 0:  # :63-71
+        return assignment, m0, m1
+    pos2, neg2 = pos_th ** 2, neg_th ** 2
+    with np.errstate(invalid="ignore"):
+        for b in range(B):
+            def sq(p, q):  # torch.sum((p[:, None] - q[None]) ** 2, -1): fp32 differences, squares, one fp32 add
+                d = (p[:, None, :] - q[None, :, :]).astype(F32)
+                return (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]).astype(F32)
+            dist0 = sq(kp0_1[b], kp1[b])                      # :100
+            dist1 = sq(kp0[b], kp1_0[b])                      # :101
+            dist = np.maximum(dist0, dist1)                   # :102 (NaN propagates like torch.max)
+            vis = np.asarray(visible0[b], bool)[:, None] & np.asarray(visible1[b], bool)[None, :]
+            dist = np.where(vis, dist, np.float32(np.inf))    # :103-104
+            min0 = dist.argmin(-1)                            # :106 first index on ties
+            min1 = dist.argmin(-2)                            # :107
+            ismin0 = np.zeros_like(vis)
+            ismin1 = np.zeros_like(vis)
+            ismin0[np.arange(N), min0] = True
+            ismin1[min1, np.arange(M)] = True
+            positive = ismin0 & ismin1 & (dist < pos2)        # :113
+            # torch.min propagates NaN (np.min too); NaN > x is False
+            neg0 = (dist0.min(-1) > neg2) & np.asarray(valid0[b], bool)   # :115
+            neg1 = (dist1.min(-2) > neg2) & np.asarray(valid1[b], bool)   # :116
+            a0 = np.where(positive.any(-1), min0, -2)         # :123
+            a1 = np.where(positive.any(-2), min1, -2)
+            m0[b] = np.where(neg0, -1, a0)                    # :125
+            m1[b] = np.where(neg1, -1, a1)
+            assignment[b] = positive
+    return assignment, m0, m1

@@ -19,4 +19,4 @@ def golden():
     import numpy as np
 
     return {name: np.load(os.path.join(GOLDEN, f"{name}.npz"), allow_pickle=False)
-            for name in ("voxel", "detect", "sample", "mnn", "next", "repr", "lg", "metrics")}
+            for name in ("voxel", "detect", "sample", "mnn", "next", "repr", "lg", "metrics", "gt_assign")}

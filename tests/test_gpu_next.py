@@ -262,3 +262,133 @@ def test_log_double_softmax_empty_side(einx, M, N):
 def test_log_double_softmax_rejects_cpu(einx):
     with pytest.raises(einx.EinxError):
         einx.sigmoid_log_double_softmax(torch.zeros(1, 2, 2), torch.zeros(1, 2, 1), torch.zeros(1, 2, 1))
+
+
+# --------------------------------------------------- distance map / metric-side reductions ---- #
+def test_distance_map_golden_and_oracle(einx, golden):
+    """einx_distance_map vs the reference's cv.distanceTransform output (1e-6 relative, the bar the oracle is pinned
+    with) and bit-exact against the oracle's closed form."""
+    g = golden["repr"]
+    cases = [f"c{ci}" for ci in range(int(g["ncases"]))] + ["sparse"]
+    for key in cases:
+        bins, H, W = (int(v) for v in g[f"{key}_shape"])
+        ev = {k: np.array(g[f"{key}_{k}"], copy=True) for k in "xytp"}
+        out = einx.events_to_distance_map(ev, (bins, H, W), DEV).numpy()
+        ref = g[f"{key}_distance"]
+        empty = ref > 1e30
+        assert out.shape == ref.shape and np.array_equal(out > 1e30, empty)
+        np.testing.assert_allclose(out[~empty], ref[~empty], rtol=1e-6, atol=0)
+        orc = O.events_to_distance_map(*[g[f"{key}_{k}"] for k in "xytp"], bins, H, W)
+        assert np.array_equal(out, orc), key  # same closed form, fp64 rounded once
+        # the reference normalises events['t'] in place
+        assert ev["t"].min() >= 0.0 and ev["t"].max() <= 1.0
+
+
+def test_distance_map_batch_ragged(einx):
+    import importlib
+
+    synth = importlib.import_module("ei-nexus_official_b200.synth")
+    rng = np.random.default_rng(11)
+    H, W, bins = 65, 97, 4
+    evs = [synth.events(rng, n, H, W, style) for n, style in ((5000, "mvsec"), (3, "ec"), (800, "ec"))]
+    x, y, t, p, off = (a.to(DEV) for a in einx.pack_events(evs))
+    out = einx.distance_map_device(x, y, t, off, (bins, H, W)).cpu().numpy()
+    for i, ev in enumerate(evs):
+        ref = O.events_to_distance_map(ev["x"].astype(np.float32), ev["y"].astype(np.float32), ev["t"], ev["p"], bins, H, W)
+        assert np.array_equal(out[i], ref), i
+
+
+def test_accumulation_image_array_branch(einx):
+    """(N, 4) ndarray branch of draw_events_accumulation_image (visualize.py:41-44): += 2p - 1, signed histogram."""
+    rng = np.random.default_rng(3)
+    H, W, n = 48, 64, 5000
+    ev = np.stack([rng.uniform(0, W, n), rng.uniform(0, H, n), np.sort(rng.random(n)), rng.integers(0, 2, n)], 1)
+    img = einx.draw_events_accumulation_image(ev, (W, H), DEV)
+    acc = np.zeros((H, W))
+    for i in range(n):  # the reference's loop, verbatim semantics
+        acc[int(ev[i, 1]), int(ev[i, 0])] += 2 * ev[i, 3] - 1
+    ref = (acc - acc.min()) / (acc.max() - acc.min()) * 255
+    ref[ref > 255] = 255
+    assert img.dtype == np.uint8 and np.array_equal(img, ref.astype(np.uint8))
+    with pytest.raises(ValueError):
+        einx.draw_events_accumulation_image(np.array([[1.0, 1.0, 0.0, 0.3]]), (W, H), DEV)
+
+
+def test_repeatability_golden(einx, golden):
+    g = golden["metrics"]
+    for ci in range(int(g["ncases"])):
+        H, W, thr, xy = (int(v) for v in g[f"c{ci}_cfg"])
+        metric = einx.Repeatability("repeatability", distance_thresh=thr, ordering="xy" if xy else "yx", device=DEV)
+        out = metric.update_one(torch.from_numpy(g[f"c{ci}_p1"]), torch.from_numpy(g[f"c{ci}_p2"]), (H, W), (H, W),
+                                torch.from_numpy(g[f"c{ci}_hom"]))
+        ref = float(g[f"c{ci}_value"])
+        if np.isnan(ref):
+            assert out == {}
+        else:
+            assert np.float32(out["repeatability"]) == np.float32(ref), ci
+        # the reductions themselves on the oracle's warped points (so the comparison is of the kernel alone): bit-exact
+        sel = [0, 1] if xy else [1, 0]
+        q1 = O._keep_true_points(g[f"c{ci}_p1"].T[sel], g[f"c{ci}_hom"], (H, W))
+        q2 = O._keep_true_points(g[f"c{ci}_p2"].T[sel], np.linalg.inv(g[f"c{ci}_hom"]).astype(np.float32), (H, W))
+        wp = O._warp_points(q1, g[f"c{ci}_hom"]).T
+        if wp.shape[0] and q2.shape[1]:
+            min1, min2 = metric.min_distances(cuda(wp), cuda(q2.T))
+            d = wp[:, None, :].astype(np.float32) - q2.T[None, :, :].astype(np.float32)
+            norm = np.sqrt((d.astype(np.float64) ** 2).sum(-1)).astype(np.float32)
+            assert np.array_equal(min1.cpu().numpy(), norm.min(0)) and np.array_equal(min2.cpu().numpy(), norm.min(1))
+            np.testing.assert_allclose(min1.cpu().numpy(), g[f"c{ci}_min_over_1"], rtol=1e-5, atol=1e-4)
+            np.testing.assert_allclose(min2.cpu().numpy(), g[f"c{ci}_min_over_2"], rtol=1e-5, atol=1e-4)
+
+
+def test_pairwise_min_dist_ragged_counts(einx):
+    rng = np.random.default_rng(9)
+    B, N, M = 3, 300, 517
+    a = rng.uniform(0, 200, (B, N, 2)).astype(np.float32)
+    b = rng.uniform(0, 200, (B, M, 2)).astype(np.float32)
+    na = np.array([300, 0, 129], dtype=np.int32)
+    nb = np.array([517, 40, 0], dtype=np.int32)
+    rmin, cmin = einx.pairwise_min_dist(cuda(a), cuda(b), cuda(na), cuda(nb))
+    rmin, cmin = rmin.cpu().numpy(), cmin.cpu().numpy()
+    for i in range(B):
+        d = a[i, :na[i], None, :] - b[i, None, :nb[i], :]
+        norm = np.sqrt((d.astype(np.float64) ** 2).sum(-1)).astype(np.float32)
+        if nb[i]:
+            assert np.array_equal(rmin[i, :na[i]], norm.min(1))
+        else:
+            assert np.all(np.isinf(rmin[i, :na[i]]))
+        if na[i]:
+            assert np.array_equal(cmin[i, :nb[i]], norm.min(0))
+        else:
+            assert np.all(np.isinf(cmin[i, :nb[i]]))
+        assert np.all(np.isinf(rmin[i, na[i]:])) and np.all(np.isinf(cmin[i, nb[i]:]))
+
+
+def test_gt_assign_golden_and_oracle(einx, golden):
+    """einx_gt_assign vs the reference's gt_matches_from_pose_depth outputs (bit-exact: integer indices)."""
+    g = golden["gt_assign"]
+    for ci in range(int(g["ncases"])):
+        pos_th, neg_th = (float(v) for v in g[f"c{ci}_th"])
+        args = [cuda(g[f"c{ci}_{k}"]) for k in ("kp0", "kp1", "kp0_1", "kp1_0", "visible0", "visible1", "valid0", "valid1")]
+        a, m0, m1 = einx.gt_assign(*args, pos_th=pos_th, neg_th=neg_th)
+        M = g[f"c{ci}_kp1"].shape[1]
+        want = np.unpackbits(g[f"c{ci}_assignment"], axis=-1)[..., :M].astype(bool)
+        assert np.array_equal(m0.cpu().numpy(), g[f"c{ci}_m0"]) and np.array_equal(m1.cpu().numpy(), g[f"c{ci}_m1"]), ci
+        assert np.array_equal(a.cpu().numpy(), want), ci
+    # ties and fully invisible rows: integer grid points, duplicated columns
+    rng = np.random.default_rng(2)
+    B, N, M = 2, 70, 90
+    kp0 = rng.integers(0, 12, (B, N, 2)).astype(np.float32)
+    kp1 = rng.integers(0, 12, (B, M, 2)).astype(np.float32)
+    kp0_1 = kp0 + rng.integers(-1, 2, (B, N, 2)).astype(np.float32)
+    kp1_0 = kp1 + rng.integers(-1, 2, (B, M, 2)).astype(np.float32)
+    vis0, vis1 = rng.random((B, N)) < 0.8, rng.random((B, M)) < 0.8
+    vis0[0, :5] = False
+    val0, val1 = vis0 | (rng.random((B, N)) < 0.5), vis1 | (rng.random((B, M)) < 0.5)
+    ao, m0o, m1o = O.gt_assign(kp0, kp1, kp0_1, kp1_0, vis0, vis1, val0, val1, 2, 3)
+    a, m0, m1 = einx.gt_assign(*[cuda(v) for v in (kp0, kp1, kp0_1, kp1_0, vis0, vis1, val0, val1)], pos_th=2, neg_th=3)
+    assert np.array_equal(m0.cpu().numpy(), m0o) and np.array_equal(m1.cpu().numpy(), m1o)
+    assert np.array_equal(a.cpu().numpy(), ao)
+    # empty side: the reference's early return
+    a, m0, m1 = einx.gt_assign(cuda(kp0), cuda(kp1[:, :0]), cuda(kp0_1), cuda(kp1_0[:, :0]), cuda(vis0), cuda(vis1[:, :0]),
+                               cuda(val0), cuda(val1[:, :0]))
+    assert a.shape == (B, N, 0) and bool((m0 == -1).all()) and m1.shape == (B, 0)

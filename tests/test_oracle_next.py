@@ -88,3 +88,17 @@ def test_repeatability_matches_reference(golden):
         assert min1.shape == g[f"c{ci}_min_over_1"].shape and min2.shape == g[f"c{ci}_min_over_2"].shape
         np.testing.assert_allclose(min1, g[f"c{ci}_min_over_1"], rtol=1e-5, atol=1e-4)
         np.testing.assert_allclose(min2, g[f"c{ci}_min_over_2"], rtol=1e-5, atol=1e-4)
+
+
+def test_gt_assign_matches_reference(golden):
+    """gt_matches_from_pose_depth (gt_generation.py:96-126) run whole in the reference; the oracle restates the
+    N x M block on the inputs the function itself computed (projections, visibility, validity)."""
+    g = golden["gt_assign"]
+    for ci in range(int(g["ncases"])):
+        pos_th, neg_th = (float(v) for v in g[f"c{ci}_th"])
+        a, m0, m1 = O.gt_assign(g[f"c{ci}_kp0"], g[f"c{ci}_kp1"], g[f"c{ci}_kp0_1"], g[f"c{ci}_kp1_0"], g[f"c{ci}_visible0"],
+                                g[f"c{ci}_visible1"], g[f"c{ci}_valid0"], g[f"c{ci}_valid1"], pos_th, neg_th)
+        M = g[f"c{ci}_kp1"].shape[1]
+        want = np.unpackbits(g[f"c{ci}_assignment"], axis=-1)[..., :M].astype(bool)
+        assert np.array_equal(m0, g[f"c{ci}_m0"]) and np.array_equal(m1, g[f"c{ci}_m1"])
+        assert np.array_equal(a, want)
