@@ -8,6 +8,7 @@ import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libeinx.so")
+TORCH_LIB_PATH = os.path.join(_PKG, "libeinx_torch.so")  # TORCH_LIBRARY(einx, ...) over the C ABI (csrc/torch/einx_torch.cpp)
 
 c_ctx = C.c_void_p
 _P = C.c_void_p
@@ -48,6 +49,7 @@ SIGNATURES = {
 }
 
 _lib = None
+_torch_lib = None
 _lock = threading.Lock()
 
 
@@ -74,19 +76,42 @@ def load():
         return lib
 
 
+def load_torch_ops():
+    """Load the PyTorch operator library (``torch.ops.einx.*``): the hot path's entry points as registered ops with
+    CUDA and Meta kernels.  Returns its ctypes handle (for ``einx_torch_context``)."""
+    global _torch_lib
+    load()
+    with _lock:
+        if _torch_lib is not None:
+            return _torch_lib
+        if not os.path.exists(TORCH_LIB_PATH):
+            raise EinxError(
+                f"{TORCH_LIB_PATH} is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "There is no CPU or PyTorch fallback for this path.")
+        import torch
+
+        torch.ops.load_library(TORCH_LIB_PATH)
+        h = C.CDLL(TORCH_LIB_PATH)
+        h.einx_torch_context.restype = c_ctx
+        h.einx_torch_context.argtypes = [C.c_int, C.c_void_p]
+        _torch_lib = h
+        return h
+
+
 class Context:
     """One einx_ctx per CUDA device (workspace owner).  Not thread-safe, like the C object."""
 
-    def __init__(self, device: int):
+    def __init__(self, device: int, stream: int = 0):
         self.lib = load()
         self.device = int(device)
-        h = c_ctx()
-        rc = self.lib.einx_create(self.device, C.byref(h))
-        if rc != 0:
+        # the operator library owns the contexts (one per device and stream), so torch.ops.einx.* and the ctypes
+        # calls of this package share workspaces, launch counters and profiling slots
+        h = load_torch_ops().einx_torch_context(self.device, C.c_void_p(stream))
+        if not h:
             msg = self.lib.einx_last_error(None)
-            raise EinxError(f"einx_create({device}) failed ({rc}): {msg.decode() if msg else ''}")
-        self.handle = h
-        self.stream = C.c_void_p(0)  # set by context_for: the one stream this context serves
+            raise EinxError(f"einx_create({device}) failed: {msg.decode() if msg else ''}")
+        self.handle = C.c_void_p(h)
+        self.stream = C.c_void_p(stream)  # the one stream this context serves
 
     def check(self, rc: int, what: str):
         if rc != 0:
@@ -107,13 +132,6 @@ class Context:
     def launches(self) -> int:
         return int(self.lib.einx_launch_count(self.handle))
 
-    def __del__(self):
-        try:
-            if getattr(self, "handle", None):
-                self.lib.einx_destroy(self.handle)
-                self.handle = None
-        except Exception:
-            pass
 
 
 _contexts = {}
@@ -147,8 +165,7 @@ def context_for(device) -> Context:
     key = (idx, sid)
     ctx = _contexts.get(key)
     if ctx is None:
-        ctx = _contexts[key] = Context(idx)
-        ctx.stream = C.c_void_p(sid)
+        ctx = _contexts[key] = Context(idx, sid)
     return ctx
 
 
@@ -164,6 +181,14 @@ def contexts_of(device):
 def launch_count(device) -> int:
     """Kernel launches issued through libeinx on a device, over all of its streams."""
     return sum(c.launches for c in contexts_of(device))
+
+
+def ops():
+    """``torch.ops.einx`` -- the registered PyTorch operators (loads libeinx_torch.so on first use)."""
+    import torch
+
+    load_torch_ops()
+    return torch.ops.einx
 
 
 def ptr(t):

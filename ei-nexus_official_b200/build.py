@@ -19,6 +19,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libeinx.so")
+TORCH_LIB = os.path.join(PKG, "libeinx_torch.so")
+TORCH_SRC = os.path.join(CSRC, "torch", "einx_torch.cpp")
 OBJ = os.path.join(ROOT, "build", "obj")
 
 NVCC_FLAGS = [
@@ -81,5 +83,42 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_torch_ops(force: bool = False) -> str:
+    """Compile csrc/torch/einx_torch.cpp (TORCH_LIBRARY(einx, ...): the registered PyTorch ops over the C ABI) with
+    the host compiler against this interpreter's torch headers and link it to libeinx.so (rpath $ORIGIN)."""
+    import torch
+    from torch.utils import cpp_extension as ce
+
+    build_library()
+    stamp = os.path.join(OBJ, "torch_digest.txt")
+    h = hashlib.sha256(torch.__version__.encode())
+    for p in (TORCH_SRC, os.path.join(ROOT, "include", "einx.h")):
+        with open(p, "rb") as f:
+            h.update(f.read())
+    digest = h.hexdigest()
+    if not force and os.path.exists(TORCH_LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
+        return TORCH_LIB
+    os.makedirs(OBJ, exist_ok=True)
+    try:
+        inc = ce.include_paths(device_type="cuda")
+    except TypeError:  # older signature
+        inc = ce.include_paths(cuda=True)
+    libdirs = ce.library_paths()
+    # the system compiler torch itself was built against; $CXX in this image is a wrapper that swaps the linker and
+    # start files (-B...), and a library linked that way cannot unwind C++ exceptions (measured: TORCH_CHECK segfaults)
+    cxx = os.environ.get("EINX_CXX") or ("/usr/bin/g++" if os.path.exists("/usr/bin/g++") else (shutil.which("g++") or "g++"))
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
+           *[f"-I{d}" for d in inc], "-I" + os.path.join(ROOT, "include"), TORCH_SRC, "-o", TORCH_LIB,
+           *[f"-L{d}" for d in libdirs], "-ltorch", "-ltorch_cpu", "-lc10", "-lc10_cuda", "-L" + PKG, "-leinx",
+           "-Wl,-rpath,$ORIGIN", *[f"-Wl,-rpath,{d}" for d in libdirs]]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"{cxx} failed on {TORCH_SRC}:\n{r.stdout}\n{r.stderr}")
+    with open(stamp, "w") as f:
+        f.write(digest)
+    return TORCH_LIB
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_torch_ops(force="--force" in sys.argv))

@@ -102,7 +102,7 @@ extern "C" int einx_filter_matches(einx_ctx* ctx, const float* scores, int B, in
     DeviceGuard guard(ctx->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const size_t nkeys = (size_t)B * ((size_t)M + N);
-    int rc = einx_ws_reserve(ctx, sizeof(unsigned long long) * nkeys);
+    int rc = einx_ws_reserve(ctx, sizeof(unsigned long long) * nkeys, stream);
     if (rc) return rc;
     unsigned long long* rowkey = (unsigned long long*)ctx->ws;
     unsigned long long* colkey = rowkey + (size_t)B * M;

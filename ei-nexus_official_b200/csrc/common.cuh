@@ -13,6 +13,7 @@ struct einx_ctx {
     int max_smem_optin;   // bytes of dynamic shared memory a CTA may opt in to
     void* ws;             // grow-only device workspace
     size_t ws_bytes;
+    cudaStream_t ws_stream;  // stream the workspace was allocated on (cudaMallocAsync)
     int64_t launches;
     int profile;                    // einx_profile_enable
     cudaEvent_t prof_ev[4][2];      // [slot][begin/end], created lazily
@@ -25,8 +26,10 @@ struct einx_ctx {
 void einx_prof_begin(einx_ctx* ctx, int slot, cudaStream_t stream);
 void einx_prof_end(einx_ctx* ctx, int slot, cudaStream_t stream);
 
-// Grow the workspace to at least `bytes` (synchronising cudaFree/cudaMalloc only on growth).
-int einx_ws_reserve(einx_ctx* ctx, size_t bytes);
+// Grow the workspace to at least `bytes`.  Growth is stream-ordered (cudaMallocAsync / cudaFreeAsync on the caller's
+// stream): nothing synchronises with the host and other streams keep running; a context serves one stream at a time,
+// so work queued earlier on that stream finishes with the old block before its memory can be reused.
+int einx_ws_reserve(einx_ctx* ctx, size_t bytes, cudaStream_t stream);
 int einx_fail(einx_ctx* ctx, int code, const char* fmt, ...);
 
 #define EINX_CUDA(ctx, call)                                                                   \

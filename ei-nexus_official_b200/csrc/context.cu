@@ -14,21 +14,29 @@ int einx_fail(einx_ctx* ctx, int code, const char* fmt, ...) {
     return code;
 }
 
-int einx_ws_reserve(einx_ctx* ctx, size_t bytes) {
+int einx_ws_reserve(einx_ctx* ctx, size_t bytes, cudaStream_t stream) {
     if (bytes <= ctx->ws_bytes) return EINX_OK;
-    // Growth only: earlier work queued on any stream may still use the old block.
-    cudaError_t e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) return einx_fail(ctx, EINX_ERR_CUDA, "workspace sync: %s", cudaGetErrorString(e));
-    if (ctx->ws) cudaFree(ctx->ws);
-    ctx->ws = nullptr;
-    ctx->ws_bytes = 0;
+    // Growth only, ordered on the caller's stream: the new block is usable by everything queued after this point,
+    // the old one returns to the pool once the kernels queued before it have run.  No host synchronisation.
     size_t want = align_up(bytes + bytes / 4, 1 << 20);
-    e = cudaMalloc(&ctx->ws, want);
+    void* fresh = nullptr;
+    cudaError_t e = cudaMallocAsync(&fresh, want, stream);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return einx_fail(ctx, EINX_ERR_NOMEM, "workspace of %zu bytes: %s", want, cudaGetErrorString(e));
     }
+    if (ctx->ws) {
+        // (a caller that moved the context to another stream: the old stream's work must be done first)
+        if (ctx->ws_stream != stream) cudaStreamSynchronize(ctx->ws_stream);
+        e = cudaFreeAsync(ctx->ws, stream);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return einx_fail(ctx, EINX_ERR_CUDA, "workspace release: %s", cudaGetErrorString(e));
+        }
+    }
+    ctx->ws = fresh;
     ctx->ws_bytes = want;
+    ctx->ws_stream = stream;
     return EINX_OK;
 }
 
@@ -100,7 +108,7 @@ void einx_destroy(einx_ctx* ctx) {
     DeviceGuard g(ctx->device);
     if (ctx->ws) {
         cudaDeviceSynchronize();
-        cudaFree(ctx->ws);
+        cudaFree(ctx->ws);  // (valid for stream-ordered allocations too; the stream may be gone by now)
     }
     for (int s = 0; s < EINX_PROFILE_SLOTS; ++s)
         for (int k = 0; k < 2; ++k)

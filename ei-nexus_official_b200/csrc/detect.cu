@@ -1137,7 +1137,7 @@ int detect_impl(einx_ctx* ctx, const NmsSide* sides, int nsides, int Bside, int 
     P.tail_smem = (T == 1 && (size_t)P.scap * 8 <= scratch) ? 1 : 0;
 
     const size_t list_bytes = align_up((size_t)B * P.scap * 4, 256);
-    int rc = einx_ws_reserve(ctx, P.tail_smem ? 256 : 2 * list_bytes);
+    int rc = einx_ws_reserve(ctx, P.tail_smem ? 256 : 2 * list_bytes, stream);
     if (rc) return rc;
     unsigned char* ws = (unsigned char*)ctx->ws;
     P.surv_val = (float*)ws;

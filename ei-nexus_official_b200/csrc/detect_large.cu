@@ -843,7 +843,7 @@ int einx_detect_large(einx_ctx* ctx, float* score, const uint8_t* mask, int B, i
     const size_t gh_bytes = align_up((size_t)B * img_rows * P.S * 32 * 4, 256);
     const size_t gw_bytes = align_up((size_t)B * img_rows * P.S * 4, 256);
     if (!use_smem) ws_bytes += gv_bytes + gh_bytes + 3 * gw_bytes;
-    int rc = einx_ws_reserve(ctx, ws_bytes);
+    int rc = einx_ws_reserve(ctx, ws_bytes, stream);
     if (rc) return rc;
     unsigned char* ws = (unsigned char*)ctx->ws;
     P.surv_val = (float*)ws;

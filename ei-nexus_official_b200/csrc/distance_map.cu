@@ -125,7 +125,7 @@ extern "C" int einx_distance_map(einx_ctx* ctx, const float* x, const float* y, 
     const size_t nplanes = (size_t)B * bins, nrows = nplanes * H;
     const size_t bits_bytes = align_up(nrows * WW * sizeof(uint32_t), 256);
     const size_t rd_bytes = nrows * W * sizeof(uint16_t);
-    int rc = einx_ws_reserve(ctx, bits_bytes + rd_bytes);
+    int rc = einx_ws_reserve(ctx, bits_bytes + rd_bytes, stream);
     if (rc) return rc;
     uint32_t* bits = (uint32_t*)ctx->ws;
     uint16_t* rowdist = (uint16_t*)((unsigned char*)ctx->ws + bits_bytes);

@@ -108,7 +108,7 @@ int events_image_impl(einx_ctx* ctx, const char* who, const void* x, const void*
     DeviceGuard guard(ctx->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     const size_t npix = (size_t)H * W;
-    int rc = einx_ws_reserve(ctx, sizeof(int) * npix * B);
+    int rc = einx_ws_reserve(ctx, sizeof(int) * npix * B, stream);
     if (rc) return rc;
     int* cnt = (int*)ctx->ws;
     EINX_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(int) * npix * B, stream));

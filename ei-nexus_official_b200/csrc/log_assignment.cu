@@ -274,7 +274,7 @@ extern "C" int einx_log_double_softmax(einx_ctx* ctx, const float* sim, const fl
     const size_t colpart_b = align_up(sizeof(float2) * (size_t)chunk * nrt * N, 256);
     const size_t rowstat_b = align_up(sizeof(float4) * (size_t)chunk * M, 256);
     const size_t colstat_b = align_up(sizeof(float4) * (size_t)chunk * N, 256);
-    int rc = einx_ws_reserve(ctx, rowpart_b + colpart_b + rowstat_b + colstat_b);
+    int rc = einx_ws_reserve(ctx, rowpart_b + colpart_b + rowstat_b + colstat_b, stream);
     if (rc) return rc;
     char* ws = (char*)ctx->ws;
     float2* rowpart = (float2*)ws;

@@ -171,7 +171,7 @@ extern "C" int einx_gt_assign(einx_ctx* ctx, const float* kp0, const float* kp1,
     const size_t t0 = (size_t)B * N, t1 = (size_t)B * M;
     // scratch: argmins (unless the caller wants them), distances at the argmin, negative flags
     const size_t bytes = align_up((t0 + t1) * 4, 256) * 2 + align_up(t0 + t1, 256);
-    int rc = einx_ws_reserve(ctx, bytes);
+    int rc = einx_ws_reserve(ctx, bytes, stream);
     if (rc) return rc;
     unsigned char* ws = (unsigned char*)ctx->ws;
     GtParams P = {};

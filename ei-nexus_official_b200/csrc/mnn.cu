@@ -397,7 +397,7 @@ extern "C" int einx_mnn(einx_ctx* ctx, const float* d0, const float* d1, const i
     const size_t rk_bytes = align_up((size_t)B * ncap * 8, 256), ck_bytes = align_up((size_t)B * mcap * 8, 256);
     const size_t key_bytes = (rk_bytes + ck_bytes) * (use_ratio ? 2 : 1);
     const size_t tc_bytes = precision == EINX_MNN_FP32 ? 0 : einx_mnn_tc_scratch_bytes(B, ncap, mcap, D, precision);
-    int rc = einx_ws_reserve(ctx, key_bytes + tc_bytes + 256);
+    int rc = einx_ws_reserve(ctx, key_bytes + tc_bytes + 256, stream);
     if (rc) return rc;
     unsigned char* ws = (unsigned char*)ctx->ws;
     unsigned long long* rowkey = (unsigned long long*)ws;
@@ -463,7 +463,7 @@ extern "C" int einx_mnn_dense(einx_ctx* ctx, const float* d0, const float* d1, i
                                                           nullptr, similarity);
     EINX_CHECK_LAUNCH(ctx);
     if (log_assignment) {
-        int rc = einx_ws_reserve(ctx, sizeof(float) * (size_t)B * (N + M));
+        int rc = einx_ws_reserve(ctx, sizeof(float) * (size_t)B * (N + M), stream);
         if (rc) return rc;
         float* lr = (float*)ctx->ws;
         float* lc = lr + (size_t)B * N;

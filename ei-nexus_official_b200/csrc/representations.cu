@@ -70,7 +70,7 @@ int launch_binned(einx_ctx* ctx, int mode, const float* x, const float* y, const
     if (per_window < 1) per_window = 1;
     if (per_window > 1024) per_window = 1024;
     if (mode == 0) {
-        int rc = einx_ws_reserve(ctx, sizeof(int) * n);
+        int rc = einx_ws_reserve(ctx, sizeof(int) * n, stream);
         if (rc) return rc;
         int* acc = (int*)ctx->ws;
         EINX_CUDA(ctx, cudaMemsetAsync(acc, 0, sizeof(int) * n, stream));

@@ -606,7 +606,7 @@ extern "C" int einx_voxelize(einx_ctx* ctx, const float* x, const float* y, cons
         }
     }
     if (normalize) {
-        int rc = einx_ws_reserve(ctx, sizeof(double) * 3 * B);
+        int rc = einx_ws_reserve(ctx, sizeof(double) * 3 * B, stream);
         if (rc) return rc;
         double* stats = (double*)ctx->ws;
         EINX_CUDA(ctx, cudaMemsetAsync(stats, 0, sizeof(double) * 3 * B, stream));

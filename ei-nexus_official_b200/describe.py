@@ -33,23 +33,14 @@ def sample(raw: torch.Tensor, kpts: torch.Tensor, counts: torch.Tensor, mode: in
     """einx_sample on padded keypoints: (B, C, Hd, Wd) map -> (B, kcap, C) descriptors (rows >= count zero)."""
     if raw.dtype != torch.float32 or not raw.is_cuda:
         raise _lib.EinxError("sample: raw descriptors must be a float32 CUDA tensor (there is no CPU fallback)")
-    B, C, Hd, Wd = raw.shape
-    if (mode == GATHER and C % 4 == 0 and C > 1 and not raw.is_contiguous()
+    C = raw.shape[1]
+    if not (mode == GATHER and C % 4 == 0 and C > 1 and not raw.is_contiguous()
             and raw.is_contiguous(memory_format=torch.channels_last)):
-        # a channels-last map (what cuDNN convolutions produce on Blackwell) is read in place: its memory is
-        # (B, Hd, Wd, C), so a keypoint's descriptor is one contiguous read instead of C strided sectors
-        mode = GATHER_NHWC
-    else:
+        # (a channels-last map -- what cuDNN convolutions produce on Blackwell -- is read in place by the op: its
+        # memory is (B, Hd, Wd, C), so a keypoint's descriptor is one contiguous read instead of C strided sectors)
         raw = raw.contiguous()
-    kpts = kpts.contiguous()
-    kcap = kpts.shape[1]
-    dev = raw.device
-    ctx = _lib.context_for(dev)
-    desc = torch.empty((B, kcap, C), dtype=torch.float32, device=dev)
-    rc = ctx.lib.einx_sample(ctx.handle, _lib.ptr(raw), B, C, Hd, Wd, mode, int(image_size[0]), int(image_size[1]),
-                             _lib.ptr(kpts), _lib.ptr(counts), kcap, float(scale_factor), int(bool(normalize)),
-                             _lib.ptr(desc), ctx.stream)
-    ctx.check(rc, "einx_sample")
+    desc = _lib.ops().sample(raw, kpts.contiguous(), counts, int(mode), int(image_size[0]), int(image_size[1]),
+                             float(scale_factor), bool(normalize))
     return desc
 
 

@@ -43,8 +43,6 @@ def detect(score: torch.Tensor, prob_thresh: float, nms_dist: int, border_dist: 
         B, Hp, Wp = score.shape
     else:
         raise ValueError("detect: expected (B, 1, H, W) or (B, H, W)")
-    dev = score.device
-    ctx = _lib.context_for(dev)
     k = int(top_k) if top_k else 0
     if kcap is None:
         # the top-k threshold only bounds the count by k when prob_thresh cannot undercut it
@@ -52,17 +50,12 @@ def detect(score: torch.Tensor, prob_thresh: float, nms_dist: int, border_dist: 
         bound = max_keypoints(Hp, Wp, nms_dist)
         kcap = min(k, bound) if (k > 0 and prob_thresh >= 1.0) else bound
     kcap = max(int(kcap), 1)
-    kpts = torch.empty((B, kcap, 3), dtype=torch.float32, device=dev)
-    counts = torch.empty((B,), dtype=torch.int32, device=dev)
-    nms_map = torch.empty((B, Hp, Wp), dtype=torch.float32, device=dev) if want_map else None
-    mptr = None
-    if mask is not None:
-        m8 = mask.reshape(B, Hp, Wp).to(torch.uint8).contiguous()
-        mptr = _lib.ptr(m8)
-    rc = ctx.lib.einx_detect(ctx.handle, _lib.ptr(score), mptr, B, Hp, Wp, int(nms_dist), int(border_dist),
-                             float(prob_thresh), k, _lib.ptr(nms_map), _lib.ptr(kpts), kcap, _lib.ptr(counts),
-                             ctx.stream)
-    ctx.check(rc, "einx_detect")
+    m8 = None if mask is None else mask.reshape(B, Hp, Wp).to(torch.uint8).contiguous()
+    # registered PyTorch op over einx_detect (csrc/torch/einx_torch.cpp): current stream, caching allocator
+    kpts, counts, nms_map = _lib.ops().detect(score.view(B, Hp, Wp), m8, int(nms_dist), int(border_dist), float(prob_thresh),
+                                              k, kcap, bool(want_map))
+    if not want_map:
+        nms_map = None
     return nms_map, kpts, counts
 
 
@@ -82,20 +75,15 @@ def detect_pair(score0: torch.Tensor, score1: torch.Tensor, prob_thresh: float, 
     if score0.dim() == 4 and score0.shape[1] != 1:
         raise ValueError("detect_pair: expected (B, 1, H, W)")
     B, Hp, Wp = score0.shape[0], score0.shape[-2], score0.shape[-1]
-    dev = score0.device
-    ctx = _lib.context_for(dev)
     k = int(top_k) if top_k else 0
     if kcap is None:
         bound = max_keypoints(Hp, Wp, nms_dist)
         kcap = min(k, bound) if (k > 0 and prob_thresh >= 1.0) else bound
     kcap = max(int(kcap), 1)
-    kp = [torch.empty((B, kcap, 3), dtype=torch.float32, device=dev) for _ in range(2)]
-    cn = [torch.empty((B,), dtype=torch.int32, device=dev) for _ in range(2)]
     m8 = [None if m is None else m.reshape(B, Hp, Wp).to(torch.uint8).contiguous() for m in (mask0, mask1)]
-    rc = ctx.lib.einx_detect_pair(ctx.handle, _lib.ptr(score0), _lib.ptr(score1), _lib.ptr(m8[0]), _lib.ptr(m8[1]), B, Hp, Wp,
-                                  int(nms_dist), int(border_dist), float(prob_thresh), k, None, None, _lib.ptr(kp[0]),
-                                  _lib.ptr(kp[1]), kcap, _lib.ptr(cn[0]), _lib.ptr(cn[1]), ctx.stream)
-    ctx.check(rc, "einx_detect_pair")
+    k0, c0, k1, c1 = _lib.ops().detect_pair(score0, score1, m8[0], m8[1], int(nms_dist), int(border_dist), float(prob_thresh),
+                                            k, kcap)
+    kp, cn = (k0, k1), (c0, c1)
     return (kp[0], cn[0]), (kp[1], cn[1])
 
 

@@ -35,26 +35,16 @@ def mnn(desc0: torch.Tensor, desc1: torch.Tensor, n0: Optional[torch.Tensor] = N
     M = desc1.shape[1]
     if desc1.shape[0] != B or desc1.shape[2] != D:
         raise ValueError("mnn: desc0 / desc1 batch or feature size mismatch")
-    dev = desc0.device
-    ctx = _lib.context_for(dev)
     prec = _PRECISION[precision] if isinstance(precision, str) else int(precision)
-    m0 = torch.empty((B, N), dtype=torch.int64, device=dev)
-    m1 = torch.empty((B, M), dtype=torch.int64, device=dev)
-    s0 = torch.empty((B, N), dtype=torch.float32, device=dev)
-    s1 = torch.empty((B, M), dtype=torch.float32, device=dev)
-    mk0 = mk1 = nm = None
     if kpts0 is not None:
         if kpts0.shape[-1] != 3 or kpts1.shape[-1] != 3:
             raise ValueError("mnn: keypoint rows must be (y, x, prob) -- three columns")
         kpts0, kpts1 = kpts0.contiguous(), kpts1.contiguous()
-        mk0 = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
-        mk1 = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
-        nm = torch.empty((B,), dtype=torch.int32, device=dev)
-    rc = ctx.lib.einx_mnn(ctx.handle, _lib.ptr(desc0), _lib.ptr(desc1), _lib.ptr(n0), _lib.ptr(n1), B, N, M, D,
-                          float(ratio_thresh or 0.0), float(distance_thresh or 0.0), int(bool(mutual)), prec,
-                          _lib.ptr(m0), _lib.ptr(m1), _lib.ptr(s0), _lib.ptr(s1), _lib.ptr(kpts0), _lib.ptr(kpts1),
-                          _lib.ptr(mk0), _lib.ptr(mk1), _lib.ptr(nm), ctx.stream)
-    ctx.check(rc, "einx_mnn")
+    res = _lib.ops().mnn(desc0, desc1, n0, n1, kpts0, kpts1, float(ratio_thresh or 0.0), float(distance_thresh or 0.0),
+                         bool(mutual), prec)
+    m0, m1, s0, s1 = res[:4]
+    if kpts0 is not None:
+        mk0, mk1, nm = res[4:]
     out = {"matches0": m0, "matches1": m1, "matching_scores0": s0, "matching_scores1": s1}
     if kpts0 is not None:
         out.update(matched_kpts0=mk0, matched_kpts1=mk1, num_matches=nm)

@@ -63,8 +63,8 @@ def voxelize_device(x, y, t, p, offsets, input_size: Tuple[int, int, int], norma
         if ten.dtype != dt or not ten.is_contiguous() or ten.device != dev:
             raise ValueError(f"{name}: expected contiguous {dt} on {dev}")
     B = offsets.numel() - 1
-    if out is None:
-        out = torch.empty((B, bins, H, W), dtype=torch.float32, device=dev)
+    if out is None:  # registered PyTorch op over einx_voxelize
+        return _lib.ops().voxelize(x, y, t, p, offsets, bins, H, W, bool(normalize))
     rc = ctx.lib.einx_voxelize(ctx.handle, _lib.ptr(x), _lib.ptr(y), _lib.ptr(t), _lib.ptr(p), _lib.ptr(offsets),
                                B, bins, H, W, int(bool(normalize)), _lib.ptr(out), ctx.stream)
     ctx.check(rc, "einx_voxelize")

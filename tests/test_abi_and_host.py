@@ -233,3 +233,39 @@ def test_log_double_softmax_host_checks(einx):
             einx.sigmoid_log_double_softmax(sim.clone().requires_grad_(), z0, z1)
     with pytest.raises(einx.EinxError):
         einx.filter_matches(torch.zeros(1, 4, 3), 0.1)
+
+
+def test_torch_ops_registered_with_meta_kernels(einx):
+    """The hot path's entry points are registered PyTorch operators (TORCH_LIBRARY(einx) in libeinx_torch.so, built by
+    build()): schemas carry the in-place annotation of the score maps, and the Meta kernels give shapes / dtypes
+    without a GPU -- what FakeTensor tracing (torch.compile) needs."""
+    import torch
+
+    ops = einx._lib.ops()
+    for name in ("voxelize", "detect", "detect_pair", "sample", "mnn"):
+        assert hasattr(ops, name), name
+    assert "Tensor(a!) score" in str(ops.detect.default._schema)
+    assert "Tensor(a!) score0, Tensor(b!) score1" in str(ops.detect_pair.default._schema)
+    m = lambda *shape, dtype=torch.float32: torch.empty(shape, dtype=dtype, device="meta")
+    B, K, D = 3, 128, 64
+    g = ops.voxelize(m(1000), m(1000), m(1000, dtype=torch.float64), m(1000), m(B + 1, dtype=torch.int64), 5, 60, 80, True)
+    assert g.shape == (B, 5, 60, 80) and g.dtype == torch.float32
+    kp, cn, mp = ops.detect(m(B, 1, 64, 96), None, 4, 4, 1.0, K, K, False)
+    assert kp.shape == (B, K, 3) and cn.shape == (B,) and cn.dtype == torch.int32 and mp.numel() == 0
+    k0, c0, k1, c1 = ops.detect_pair(m(B, 1, 64, 96), m(B, 1, 64, 96), None, None, 4, 4, 1.0, K, K)
+    assert k0.shape == k1.shape == (B, K, 3) and c0.dtype == torch.int32
+    d = ops.sample(m(B, D, 8, 12), kp, cn, 1, 64, 96, 1.0, True)
+    assert d.shape == (B, K, D)
+    out = ops.mnn(d, d, cn, cn, kp, kp, 0.0, 0.0, True, 3)
+    assert [tuple(t.shape) for t in out] == [(B, K), (B, K), (B, K), (B, K), (B, K, 3), (B, K, 3), (B,)]
+    assert out[0].dtype == torch.int64 and out[6].dtype == torch.int32
+    assert len(ops.mnn(d, d, None, None, None, None, 0.0, 0.0, True, 0)) == 4
+    # no CPU kernels are registered: a CPU tensor is refused by the dispatcher (no fallback)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        ops.sample(torch.zeros(1, 4, 2, 2), torch.zeros(1, 1, 3), torch.zeros(1, dtype=torch.int32), 0, 2, 2, 1.0, True)
+
+
+def test_torch_ops_error_path_unwinds(einx):
+    """A failing C-ABI call inside a registered op must become a c10::Error (-> RuntimeError in Python), not a crash:
+    the operator library is linked so that exceptions unwind through it (build.py pins the system g++)."""
+    assert einx._lib.load_torch_ops().einx_torch_error_path_selftest() == 1

@@ -128,3 +128,31 @@ def test_captured_step_replays_exactly(einx, batch):
     torch.cuda.synchronize()
     assert torch.equal(out["counts0"].cpu(), ref["counts1"])
     assert valid_rows_equal(out["keypoints0"].cpu(), ref["keypoints1"], ref["counts1"])
+
+
+def test_torch_ops_trace_and_raise(einx):
+    synth = importlib.import_module("ei-nexus_official_b200.synth")
+    """torch.ops.einx.*: the registered operators behind the host layer.  They trace under torch.compile (FakeTensor
+    through the Meta kernels, mutation of the score map declared in the schema) and turn C-ABI error codes into
+    Python exceptions."""
+    ops = einx._lib.ops()
+    rng = np.random.default_rng(4)
+    B, H, W, K, D = 2, 64, 96, 64, 32
+    score = torch.from_numpy(synth.score_map(rng, B, H, W)).to(DEV)
+    raw = torch.from_numpy(synth.descriptor_map(rng, B, D, H, W)).to(DEV)
+
+    def fn(score, raw):
+        kp, cn, _ = torch.ops.einx.detect(score, None, 4, 4, 1.0, K, K, False)
+        d = torch.ops.einx.sample(raw, kp, cn, 0, H, W, 1.41, True)
+        return kp, cn, d * 2.0
+
+    eager = fn(score.clone(), raw)
+    compiled = torch.compile(fn, backend="aot_eager", fullgraph=True)(score.clone(), raw)
+    for a, b in zip(eager, compiled):
+        assert torch.equal(a, b)
+    # the same numbers as the host wrappers (which call these ops)
+    det = importlib.import_module("ei-nexus_official_b200.detection")
+    _, kp, cn = det.detect(score.clone(), 1.0, 4, 4, K, kcap=K)
+    assert torch.equal(kp, eager[0]) and torch.equal(cn, eager[1])
+    with pytest.raises(RuntimeError, match="einx_detect"):
+        ops.detect(score.clone(), None, 99, 4, 1.0, K, K, False)  # nms_radius out of range -> EINX_ERR_UNSUPPORTED
