@@ -29,6 +29,10 @@ SIGNATURES = {
                                    _P, _P, _P, _P, C.c_int, _P, _P, _P]),
     "einx_sample": (C.c_int, [c_ctx, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P,
                               C.c_int, C.c_float, C.c_int, _P, _P]),
+    "einx_sample_split": (C.c_int, [c_ctx, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P,
+                                    C.c_int, C.c_float, C.c_int, _P, _P, _P]),
+    "einx_mnn_split": (C.c_int, [c_ctx, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                 C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "einx_mnn": (C.c_int, [c_ctx, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                            C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "einx_mnn_dense": (C.c_int, [c_ctx, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),

@@ -369,15 +369,29 @@ __global__ void log_assignment_kernel(const float* __restrict__ sim, const float
 
 int einx_mnn_tc(einx_ctx* ctx, const float* d0, const float* d1, const int32_t* n0, const int32_t* n1, int B, int ncap,
                 int mcap, int D, int precision, unsigned long long* rowkey, unsigned long long* colkey,
-                unsigned char* scratch, size_t scratch_bytes, cudaStream_t stream);
-size_t einx_mnn_tc_scratch_bytes(int B, int ncap, int mcap, int D, int precision);
+                unsigned char* scratch, size_t scratch_bytes, const uint16_t* split0, const uint16_t* split1,
+                cudaStream_t stream);
+size_t einx_mnn_tc_scratch_bytes(int B, int ncap, int mcap, int D, int precision, bool have_split);
 bool einx_mnn_tc_supported(const float* d0, const float* d1, int D, int precision);
 
 extern "C" int einx_mnn(einx_ctx* ctx, const float* d0, const float* d1, const int32_t* n0, const int32_t* n1, int B,
                         int ncap, int mcap, int D, float ratio_thresh, float distance_thresh, int mutual,
                         int precision, int64_t* m0, int64_t* m1, float* s0, float* s1, const float* kpts0,
                         const float* kpts1, float* mk0, float* mk1, int32_t* nmatch, einx_stream stream_) {
+    return einx_mnn_split(ctx, d0, d1, nullptr, nullptr, n0, n1, B, ncap, mcap, D, ratio_thresh, distance_thresh, mutual,
+                          precision, m0, m1, s0, s1, kpts0, kpts1, mk0, mk1, nmatch, stream_);
+}
+
+extern "C" int einx_mnn_split(einx_ctx* ctx, const float* d0, const float* d1, const uint16_t* split0,
+                              const uint16_t* split1, const int32_t* n0, const int32_t* n1, int B, int ncap, int mcap,
+                              int D, float ratio_thresh, float distance_thresh, int mutual, int precision, int64_t* m0,
+                              int64_t* m1, float* s0, float* s1, const float* kpts0, const float* kpts1, float* mk0,
+                              float* mk1, int32_t* nmatch, einx_stream stream_) {
     if (!ctx) return EINX_ERR_INVALID;
+    if ((split0 != nullptr) != (split1 != nullptr))
+        return einx_fail(ctx, EINX_ERR_INVALID, "einx_mnn_split: split0 and split1 come together");
+    if (split0 && (((uintptr_t)split0 | (uintptr_t)split1) & 15))
+        return einx_fail(ctx, EINX_ERR_INVALID, "einx_mnn_split: split operands must be 16-byte aligned");
     if (B < 0 || ncap < 0 || mcap < 0 || D <= 0)
         return einx_fail(ctx, EINX_ERR_INVALID, "einx_mnn: bad shape B=%d N=%d M=%d D=%d", B, ncap, mcap, D);
     if (B == 0) return EINX_OK;
@@ -396,7 +410,7 @@ extern "C" int einx_mnn(einx_ctx* ctx, const float* d0, const float* d1, const i
 
     const size_t rk_bytes = align_up((size_t)B * ncap * 8, 256), ck_bytes = align_up((size_t)B * mcap * 8, 256);
     const size_t key_bytes = (rk_bytes + ck_bytes) * (use_ratio ? 2 : 1);
-    const size_t tc_bytes = precision == EINX_MNN_FP32 ? 0 : einx_mnn_tc_scratch_bytes(B, ncap, mcap, D, precision);
+    const size_t tc_bytes = precision == EINX_MNN_FP32 ? 0 : einx_mnn_tc_scratch_bytes(B, ncap, mcap, D, precision, split0 != nullptr);
     int rc = einx_ws_reserve(ctx, key_bytes + tc_bytes + 256, stream);
     if (rc) return rc;
     unsigned char* ws = (unsigned char*)ctx->ws;
@@ -422,7 +436,7 @@ extern "C" int einx_mnn(einx_ctx* ctx, const float* d0, const float* d1, const i
             }
         } else {
             rc = einx_mnn_tc(ctx, d0, d1, n0, n1, B, ncap, mcap, D, precision, rowkey, colkey, ws + key_bytes,
-                             tc_bytes, stream);
+                             tc_bytes, split0, split1, stream);
             if (rc) return rc;
         }
     }

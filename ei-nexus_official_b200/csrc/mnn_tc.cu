@@ -62,20 +62,23 @@ struct Cfg {
     // KIND 0: bf16 operands prepared in HBM.  KIND 1: fp32 operands, tf32 MMAs, lo tiles derived in shared
     // memory.  KIND 2: fp32 operands, fp16 MMAs: converter warps write hi / lo fp16 tiles (half the row
     // width of the raw tile, 64-byte swizzle) and the MMAs read only those.
-    static constexpr int kElt = KIND == 0 ? 2 : 4;       // bytes per element of the TMA'd (raw) tiles
+    // KIND 3: fp16 hi / lo operands already split in HBM (by the sampler that produced the descriptors, or by
+    // split_fp16_kernel): four TMA loads per stage, no converter warps -- the pipeline is pure TMA -> MMA.
+    static constexpr int kElt = (KIND == 0 || KIND == 3) ? 2 : 4;   // bytes per element of the TMA'd (raw) tiles
     static constexpr int kKB = KB;                       // bytes of K per raw stage row (= swizzle span)
     static constexpr int kABytes = TILE_M * KB;
     static constexpr int kBRows = TILE_N / CG;           // rows of d1 this CTA stages per k-block
     static constexpr int kBBytes = kBRows * KB;
-    static constexpr bool kConvert = KIND != 0;
+    static constexpr bool kConvert = KIND == 1 || KIND == 2;
+    static constexpr bool kPresplit = KIND == 3;
     static constexpr int kRawBytes = kABytes + kBBytes;
-    static constexpr int kStageBytes = kRawBytes * (kConvert ? 2 : 1);
+    static constexpr int kStageBytes = kRawBytes * ((kConvert || kPresplit) ? 2 : 1);   // + lo tiles
     // operand tiles the MMAs read: row width in bytes and tile sizes
     static constexpr int kOpKB = KIND == 2 ? KB / 2 : KB;
     static constexpr int kOpABytes = TILE_M * kOpKB;
     static constexpr int kOpBBytes = kBRows * kOpKB;
     // (single-CTA split kernels keep 4 + 8: their stages are 1.5x larger and two must fit beside the scratch)
-    static constexpr int kEpiWarps = KIND == 0 ? EINX_BF16_EPI_WARPS : (CG == 1 ? 4 : (KIND == 1 ? EINX_SPLIT_EPI_WARPS : (EW ? EW : EINX_FP16_EPI_WARPS)));
+    static constexpr int kEpiWarps = (KIND == 0 || KIND == 3) ? EINX_BF16_EPI_WARPS : (CG == 1 ? 4 : (KIND == 1 ? EINX_SPLIT_EPI_WARPS : (EW ? EW : EINX_FP16_EPI_WARPS)));
     static constexpr int kConvWarps = !kConvert ? 0 : (CG == 1 ? 8 : (KIND == 1 ? EINX_SPLIT_CONV_WARPS : 8));
     static constexpr int kConvWarp0 = kEpilogueWarp0 + kEpiWarps;
     static constexpr int kColsPerWarp = TILE_N / (kEpiWarps / 4);
@@ -291,7 +294,9 @@ __device__ __forceinline__ float tf32_lo(float x) {
 
 template <int KIND, int KB, int CG, int EW = 0>
 __global__ void __launch_bounds__(Cfg<KIND, KB, CG, EW>::kThreads, 1)
-mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams P) {
+mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+              const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, const TcParams P) {
+    // (mapA2 / mapB2: the low-order operand matrices of the pre-split form, KIND 3; unused otherwise)
     using C = Cfg<KIND, KB, CG, EW>;
     constexpr int A_BYTES = C::kABytes, B_BYTES = C::kBBytes, RAW_BYTES = C::kRawBytes, STAGES = C::kStages,
                   STAGE_BYTES = C::kStageBytes;
@@ -313,6 +318,10 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+        if (C::kPresplit) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA2) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB2) : "memory");
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -371,15 +380,23 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     if (CG == 1 || C::kConvert) {
                         // (3xTF32 pair form: each CTA's converters wait for their own tiles, so the bytes are
                         // counted locally; the leader's MMA waits for the converters of both CTAs instead)
-                        mbar_expect_tx(&bars->full[stage], RAW_BYTES);
+                        mbar_expect_tx(&bars->full[stage], RAW_BYTES * (C::kPresplit ? 2 : 1));
                         tma_load_2d(sa, &mapA, &bars->full[stage], kcoord, rowA);
                         tma_load_2d(sa + A_BYTES, &mapB, &bars->full[stage], kcoord, rowB);
+                        if (C::kPresplit) {
+                            tma_load_2d(sa + RAW_BYTES, &mapA2, &bars->full[stage], kcoord, rowA);
+                            tma_load_2d(sa + RAW_BYTES + A_BYTES, &mapB2, &bars->full[stage], kcoord, rowB);
+                        }
                     } else {
                         // both CTAs' bytes complete on the leader's barrier; the peer adds its arrival remotely
-                        if (leader) mbar_expect_tx(&bars->full[stage], 2 * RAW_BYTES);
+                        if (leader) mbar_expect_tx(&bars->full[stage], 2 * RAW_BYTES * (C::kPresplit ? 2 : 1));
                         else mbar_arrive_cta(&bars->full[stage], 0);
                         tma_load_2d_pair(sa, &mapA, &bars->full[stage], kcoord, rowA);
                         tma_load_2d_pair(sa + A_BYTES, &mapB, &bars->full[stage], kcoord, rowB);
+                        if (C::kPresplit) {
+                            tma_load_2d_pair(sa + RAW_BYTES, &mapA2, &bars->full[stage], kcoord, rowA);
+                            tma_load_2d_pair(sa + RAW_BYTES + A_BYTES, &mapB2, &bars->full[stage], kcoord, rowB);
+                        }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -427,9 +444,10 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
 #pragma unroll
                         for (int k = 0; k < OKB / 32; ++k)
                             tc_mma<KIND, CG>(tmem_d, a_lo + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), P.idesc, 1u);
-                    } else if (KIND == 1) {
-                        // x.y ~= hi.hi + hi.lo + lo.hi  (the raw tile is its own hi part: the tensor
-                        // core drops the 13 low mantissa bits of a tf32 operand)
+                    } else if (KIND == 1 || KIND == 3) {
+                        // x.y ~= hi.hi + hi.lo + lo.hi  (3xTF32: the raw tile is its own hi part -- the tensor
+                        // core drops the 13 low mantissa bits of a tf32 operand; pre-split fp16: the hi and lo
+                        // tiles arrive by TMA at the same offsets)
                         const uint64_t a_hi = make_smem_desc<KB>(sa), b_hi = make_smem_desc<KB>(sa + A_BYTES);
                         const uint64_t a_lo = make_smem_desc<KB>(sa + RAW_BYTES);
                         const uint64_t b_lo = make_smem_desc<KB>(sa + RAW_BYTES + A_BYTES);
@@ -591,7 +609,7 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     int cr;
                     argmax32(g, cv, cr);
                     const bool col_ok = (jc + lane < M) && (cv > -INFINITY);
-                    ckey[c] = col_ok ? (((unsigned long long)f32_orderable((KIND == 2 ? cv * P.out_scale : cv) + 0.0f) << 32) |
+                    ckey[c] = col_ok ? (((unsigned long long)f32_orderable(((KIND == 2 || KIND == 3) ? cv * P.out_scale : cv) + 0.0f) << 32) |
                                         (0xffffffffu - (uint32_t)(i0 + 32 * q + cr)))
                                      : 0ull;
                     __syncwarp();  // the tile is rewritten by the next chunk
@@ -608,7 +626,7 @@ mnn_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             }
             if (row_ok && best > -INFINITY)
                 atomicMax(P.rowkey + (size_t)b * P.ncap + row,
-                          ((unsigned long long)f32_orderable((KIND == 2 ? best * P.out_scale : best) + 0.0f) << 32) |
+                          ((unsigned long long)f32_orderable(((KIND == 2 || KIND == 3) ? best * P.out_scale : best) + 0.0f) << 32) |
                               (0xffffffffu - (uint32_t)best_j));
             // merge the 4 lane quarters' column keys: every warp parks its keys in its own (now idle) transpose
             // tile, then the threads of the epilogue group take the maximum over the four quarters of a column
@@ -665,6 +683,30 @@ __global__ void to_bf16_kernel(const float* __restrict__ src0, size_t n0, const 
     }
 }
 
+// fp32 descriptors -> the fp16 hi / lo operand matrices of the FP16X3 split: x' = in_scale * x, hi = fp16(x'),
+// lo = fp16(x' - hi).  Used when the caller has no pre-split operands (the sampler writes them itself on the
+// pipeline path, so there this pass does not run).  n0, n1 multiples of 4.
+__global__ void split_fp16_kernel(const float* __restrict__ src0, size_t n0, const float* __restrict__ src1, size_t n1,
+                                  __half* __restrict__ hi0, __half* __restrict__ lo0, __half* __restrict__ hi1,
+                                  __half* __restrict__ lo1, float sc) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+    const size_t n = n0 + n1;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        const bool first = i < n0;
+        const size_t j = first ? i : i - n0;
+        const float4 v = __ldg(reinterpret_cast<const float4*>((first ? src0 : src1) + j));
+        const float x0 = v.x * sc, x1 = v.y * sc, x2 = v.z * sc, x3 = v.w * sc;
+        const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+        uint2 hv, lv;
+        hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+        lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+        *reinterpret_cast<uint2*>((first ? hi0 : hi1) + j) = hv;
+        *reinterpret_cast<uint2*>((first ? lo0 : lo1) + j) = lv;
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -705,7 +747,8 @@ uint32_t make_idesc(int kind, int cg) {
 }
 
 template <int KIND, int KB, int CG, int EW = 0>
-int launch_tc(einx_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, int grid, cudaStream_t stream) {
+int launch_tc(einx_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, int grid, cudaStream_t stream,
+              const CUtensorMap* ma2 = nullptr, const CUtensorMap* mb2 = nullptr) {
     auto kern = mnn_tc_kernel<KIND, KB, CG, EW>;
     using C = Cfg<KIND, KB, CG, EW>;
     const size_t smem = C::kSmem;
@@ -723,7 +766,7 @@ int launch_tc(einx_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     einx_prof_begin(ctx, 3, stream);
-    EINX_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, ma, mb, P));
+    EINX_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, ma, mb, ma2 ? *ma2 : ma, mb2 ? *mb2 : mb, P));
     einx_prof_end(ctx, 3, stream);
     ctx->launches++;
     return EINX_OK;
@@ -731,9 +774,17 @@ int launch_tc(einx_ctx* ctx, const CUtensorMap& ma, const CUtensorMap& mb, const
 
 }  // namespace
 
-size_t einx_mnn_tc_scratch_bytes(int B, int ncap, int mcap, int D, int precision) {
+static bool presplit_wanted() {
+    // EINX_MNN_FP16_INKERNEL=1: the previous FP16X3 form (converter warps split the fp32 tiles in shared memory)
+    static const bool inkernel = getenv("EINX_MNN_FP16_INKERNEL") && atoi(getenv("EINX_MNN_FP16_INKERNEL")) != 0;
+    return !inkernel;
+}
+
+size_t einx_mnn_tc_scratch_bytes(int B, int ncap, int mcap, int D, int precision, bool have_split) {
     const size_t elems = (size_t)B * ((size_t)ncap + mcap) * D;
-    return precision == EINX_MNN_BF16 ? align_up(elems * 2, 1024) + 2048 : 0;  // TF32X3 reads the descriptors in place
+    if (precision == EINX_MNN_BF16) return align_up(elems * 2, 1024) + 2048;
+    if (precision == EINX_MNN_FP16X3 && presplit_wanted() && !have_split && D % 8 == 0) return align_up(elems * 4, 1024) + 2048;
+    return 0;  // TF32X3 reads the descriptors in place
 }
 
 bool einx_mnn_tc_supported(const float* d0, const float* d1, int D, int precision) {
@@ -744,7 +795,8 @@ bool einx_mnn_tc_supported(const float* d0, const float* d1, int D, int precisio
 
 int einx_mnn_tc(einx_ctx* ctx, const float* d0, const float* d1, const int32_t* n0, const int32_t* n1, int B, int ncap,
                 int mcap, int D, int precision, unsigned long long* rowkey, unsigned long long* colkey,
-                unsigned char* scratch, size_t scratch_bytes, cudaStream_t stream) {
+                unsigned char* scratch, size_t scratch_bytes, const uint16_t* split0, const uint16_t* split1,
+                cudaStream_t stream) {
     const size_t e0 = (size_t)B * ncap * D, e1 = (size_t)B * mcap * D;
     CUtensorMap maps[2];
     memset(maps, 0, sizeof(maps));
@@ -780,6 +832,37 @@ int einx_mnn_tc(einx_ctx* ctx, const float* d0, const float* d1, const int32_t* 
         P.idesc = make_idesc(0, CG);
         return CG == 2 ? launch_tc<0, 128, 2>(ctx, maps[0], maps[1], P, grid, stream)
                        : launch_tc<0, 128, 1>(ctx, maps[0], maps[1], P, grid, stream);
+    }
+    if (precision == EINX_MNN_FP16X3 && presplit_wanted() && D % 8 == 0) {
+        // Pre-split fp16 operands: hi = fp16(2^10 d), lo = fp16(2^10 d - hi), each a (rows, D) fp16 matrix -- written
+        // by the sampler next to the fp32 descriptors (split0 / split1 = [hi | lo]) or derived here in one pass.
+        // The tile pipeline is then TMA -> MMA only (no converter warps): 64-element k-blocks, 128-byte swizzle.
+        const __half *hi0, *lo0, *hi1, *lo1;
+        if (split0 && split1) {
+            hi0 = (const __half*)split0; lo0 = hi0 + e0;
+            hi1 = (const __half*)split1; lo1 = hi1 + e1;
+        } else {
+            __half* base = (__half*)(((uintptr_t)scratch + 1023) & ~(uintptr_t)1023);
+            __half *h0 = base, *l0 = h0 + e0, *h1 = l0 + e0, *l1 = h1 + e1;  // e0, e1 multiples of 8: 16-byte aligned
+            const size_t quads = (e0 + e1) / 4;
+            unsigned blocks = (unsigned)((quads + 255) / 256);
+            if (blocks > (unsigned)ctx->num_sms * 16) blocks = (unsigned)ctx->num_sms * 16;
+            split_fp16_kernel<<<blocks ? blocks : 1, 256, 0, stream>>>(d0, e0, d1, e1, h0, l0, h1, l1, 1024.0f);
+            EINX_CHECK_LAUNCH(ctx);
+            hi0 = h0; lo0 = l0; hi1 = h1; lo1 = l1;
+        }
+        CUtensorMap lom[2];
+        memset(lom, 0, sizeof(lom));
+        if ((rc = make_map(ctx, &maps[0], hi0, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (size_t)B * ncap, D, TILE_M, 128))) return rc;
+        if ((rc = make_map(ctx, &maps[1], hi1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (size_t)B * mcap, D, TILE_N / CG, 128))) return rc;
+        if ((rc = make_map(ctx, &lom[0], lo0, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (size_t)B * ncap, D, TILE_M, 128))) return rc;
+        if ((rc = make_map(ctx, &lom[1], lo1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (size_t)B * mcap, D, TILE_N / CG, 128))) return rc;
+        P.nkb = (D * 2 + 127) / 128;
+        P.idesc = make_idesc(2, CG);
+        P.in_scale = 1024.0f;
+        P.out_scale = 1.0f / (1024.0f * 1024.0f);
+        return CG == 2 ? launch_tc<3, 128, 2>(ctx, maps[0], maps[1], P, grid, stream, &lom[0], &lom[1])
+                       : launch_tc<3, 128, 1>(ctx, maps[0], maps[1], P, grid, stream, &lom[0], &lom[1]);
     }
     if (precision == EINX_MNN_FP16X3) {
         // fp32 descriptors in place, 32-element k-blocks (128-byte raw rows); |d| * 2^10 must stay below 65504

@@ -1,9 +1,36 @@
 // Descriptor sampling at the kept keypoints + L2 normalisation (one warp per keypoint).
 // Semantics: reference core/modules/utils/descriptor_util.py:21-28, :50-71 (gather) and :74-128
 // (bilinear grid_sample, align_corners=False, zeros padding) -- see include/einx.h.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
+
+// Optional second output: the fp16 hi / lo operands of the matcher's FP16X3 tensor-core mode (einx_mnn_split),
+// hi = fp16(2^10 d), lo = fp16(2^10 d - hi), written while the descriptor is still in registers -- the matcher's
+// tile pipeline then has nothing to convert.  `hi` == nullptr skips it.
+struct SplitOut {
+    __half* hi;
+    __half* lo;
+};
+__device__ __forceinline__ void split_store(const SplitOut& so, size_t idx, float d) {
+    const float x = d * 1024.0f;
+    const __half h = __float2half_rn(x);
+    so.hi[idx] = h;
+    so.lo[idx] = __float2half_rn(x - __half2float(h));
+}
+__device__ __forceinline__ void split_store4(const SplitOut& so, size_t idx, float4 d) {  // idx % 4 == 0
+    const float x0 = d.x * 1024.0f, x1 = d.y * 1024.0f, x2 = d.z * 1024.0f, x3 = d.w * 1024.0f;
+    const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+    uint2 hv, lv;
+    hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+    lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+    *reinterpret_cast<uint2*>(so.hi + idx) = hv;
+    *reinterpret_cast<uint2*>(so.lo + idx) = lv;
+}
 
 constexpr int kWarpsPerBlock = 8;
 constexpr int kMaxPerLane = 16;  // channels per lane held in registers: C <= 512
@@ -12,7 +39,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 sample_kernel(const float* __restrict__ raw, int C, int Hd, int Wd, float Hp, float Wp,
               const float* __restrict__ kpts, const int32_t* __restrict__ counts, int kcap, float scale,
-              int normalize, float* __restrict__ desc) {
+              int normalize, float* __restrict__ desc, SplitOut so) {
     const int b = blockIdx.y;
     const int k = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -21,7 +48,10 @@ sample_kernel(const float* __restrict__ raw, int C, int Hd, int Wd, float Hp, fl
     int cnt = counts[b];
     if (cnt > kcap) cnt = kcap;
     if (k >= cnt) {  // padding rows are defined (zero) so a batched matcher can ignore them safely
-        for (int c = lane; c < C; c += 32) out[c] = 0.0f;
+        for (int c = lane; c < C; c += 32) {
+            out[c] = 0.0f;
+            if (so.hi) split_store(so, ((size_t)b * kcap + k) * C + c, 0.0f);
+        }
         return;
     }
     const float* kp = kpts + ((size_t)b * kcap + k) * 3;
@@ -82,7 +112,11 @@ sample_kernel(const float* __restrict__ raw, int C, int Hd, int Wd, float Hp, fl
 #pragma unroll
     for (int j = 0; j < kMaxPerLane; ++j) {
         const int c = lane + 32 * j;
-        if (c < C) out[c] = v[j] * mul;
+        if (c < C) {
+            const float d = v[j] * mul;
+            out[c] = d;
+            if (so.hi) split_store(so, ((size_t)b * kcap + k) * C + c, d);
+        }
     }
 }
 
@@ -97,7 +131,7 @@ template <int NV>  // float4 per lane: C == 128 * NV (NV = 0: any C % 4 == 0 up 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 sample_gather_nhwc_kernel(const float* __restrict__ raw, int C, int Hd, int Wd, const float* __restrict__ kpts,
                           const int32_t* __restrict__ counts, int kcap, float scale, int normalize,
-                          float* __restrict__ desc) {
+                          float* __restrict__ desc, SplitOut so) {
     constexpr int MV = NV ? NV : 4;
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31;
@@ -157,7 +191,9 @@ sample_gather_nhwc_kernel(const float* __restrict__ raw, int C, int Hd, int Wd, 
             const int i = lane + 32 * j;
             if (NV || i < c4) {
                 const float4 q = v[u][j];  // padding rows (k >= cnt) were loaded as zeros
-                out[i] = make_float4(q.x * mul[u], q.y * mul[u], q.z * mul[u], q.w * mul[u]);
+                const float4 d = make_float4(q.x * mul[u], q.y * mul[u], q.z * mul[u], q.w * mul[u]);
+                out[i] = d;
+                if (so.hi) split_store4(so, ((size_t)b * kcap + k) * C + 4 * i, d);
             }
         }
     }
@@ -187,7 +223,7 @@ template <int NJ>  // channel groups of 32 held per lane: C == 32 * NJ exactly, 
 __global__ void __launch_bounds__(kSlabThreads, 3)
 sample_bilinear_slab_kernel(const float* __restrict__ raw, int C, int Hd, int Wd, float Hp, float Wp,
                             const float* __restrict__ kpts, const int32_t* __restrict__ counts, int kcap, float scale,
-                            int normalize, float* __restrict__ desc, int SP) {
+                            int normalize, float* __restrict__ desc, int SP, SplitOut so) {
     extern __shared__ __align__(16) float slab[];  // [C][SP]: rows y0, y0+1 of every channel
     __shared__ Tap taps[kSlabThreads];
     __shared__ int s_bound[2];
@@ -231,6 +267,11 @@ sample_bilinear_slab_kernel(const float* __restrict__ raw, int C, int Hd, int Wd
         float4* z = reinterpret_cast<float4*>(desc + ((size_t)b * kcap + cnt) * C);  // C % 4 == 0 on this path
         const size_t nz = (size_t)(kcap - cnt) * C / 4;
         for (size_t i = tid; i < nz; i += kSlabThreads) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (so.hi) {  // (fp16 zeros; C % 8 == 0 whenever the split output is requested)
+            uint2* zh = reinterpret_cast<uint2*>(so.hi + ((size_t)b * kcap + cnt) * C);
+            uint2* zl = reinterpret_cast<uint2*>(so.lo + ((size_t)b * kcap + cnt) * C);
+            for (size_t i = tid; i < nz; i += kSlabThreads) { zh[i] = make_uint2(0u, 0u); zl[i] = make_uint2(0u, 0u); }
+        }
     }
 
     // ---- keypoints are in raster order, so floor(iy) never decreases along the list and this CTA's
@@ -330,7 +371,11 @@ sample_bilinear_slab_kernel(const float* __restrict__ raw, int C, int Hd, int Wd
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     const int c = lane + 32 * j;
-                    if (NJ != kMaxPerLane || c < C) out[c] = v0[j] * mul0;
+                    if (NJ != kMaxPerLane || c < C) {
+                        const float d = v0[j] * mul0;
+                        out[c] = d;
+                        if (so.hi) split_store(so, ((size_t)b * kcap + t0.k) * C + c, d);
+                    }
                 }
             }
             if (live1) {
@@ -338,7 +383,11 @@ sample_bilinear_slab_kernel(const float* __restrict__ raw, int C, int Hd, int Wd
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     const int c = lane + 32 * j;
-                    if (NJ != kMaxPerLane || c < C) out[c] = v1[j] * mul1;
+                    if (NJ != kMaxPerLane || c < C) {
+                        const float d = v1[j] * mul1;
+                        out[c] = d;
+                        if (so.hi) split_store(so, ((size_t)b * kcap + t1.k) * C + c, d);
+                    }
                 }
             }
         }
@@ -350,7 +399,20 @@ sample_bilinear_slab_kernel(const float* __restrict__ raw, int C, int Hd, int Wd
 extern "C" int einx_sample(einx_ctx* ctx, const float* raw, int B, int C, int Hd, int Wd, int mode, int Hp, int Wp,
                            const float* kpts, const int32_t* counts, int kcap, float scale, int normalize,
                            float* desc, einx_stream stream_) {
+    return einx_sample_split(ctx, raw, B, C, Hd, Wd, mode, Hp, Wp, kpts, counts, kcap, scale, normalize, desc, nullptr, stream_);
+}
+
+extern "C" int einx_sample_split(einx_ctx* ctx, const float* raw, int B, int C, int Hd, int Wd, int mode, int Hp, int Wp,
+                                 const float* kpts, const int32_t* counts, int kcap, float scale, int normalize,
+                                 float* desc, uint16_t* split, einx_stream stream_) {
     if (!ctx) return EINX_ERR_INVALID;
+    if (split && (C % 8 != 0 || ((uintptr_t)split & 15)))
+        return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_sample_split: the fp16 operands need C %% 8 == 0 and a 16-byte aligned buffer (C=%d)", C);
+    SplitOut so = {nullptr, nullptr};
+    if (split && B > 0 && kcap > 0) {
+        so.hi = reinterpret_cast<__half*>(split);
+        so.lo = so.hi + (size_t)B * kcap * C;
+    }
     if (B < 0 || C <= 0 || Hd <= 0 || Wd <= 0 || kcap < 0)
         return einx_fail(ctx, EINX_ERR_INVALID, "einx_sample: bad shape B=%d C=%d Hd=%d Wd=%d kcap=%d", B, C, Hd, Wd, kcap);
     if (B == 0 || kcap == 0) return EINX_OK;
@@ -367,15 +429,15 @@ extern "C" int einx_sample(einx_ctx* ctx, const float* raw, int B, int C, int Hd
     } prof_scope(ctx, stream);
     if (mode == EINX_SAMPLE_GATHER) {
         sample_kernel<EINX_SAMPLE_GATHER><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
-            raw, C, Hd, Wd, (float)Hp, (float)Wp, kpts, counts, kcap, scale, normalize, desc);
+            raw, C, Hd, Wd, (float)Hp, (float)Wp, kpts, counts, kcap, scale, normalize, desc, so);
     } else if (mode == EINX_SAMPLE_GATHER_NHWC) {
         if (C % 4 != 0 || (uintptr_t)raw % 16 != 0 || (uintptr_t)desc % 16 != 0)
             return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_sample: channels-last gather needs C %% 4 == 0 and 16-byte aligned buffers (C=%d)", C);
         dim3 g2((kcap + 2 * kWarpsPerBlock - 1) / (2 * kWarpsPerBlock), B);
         const int T = kWarpsPerBlock * 32;
-        if (C == 128) sample_gather_nhwc_kernel<1><<<g2, T, 0, stream>>>(raw, C, Hd, Wd, kpts, counts, kcap, scale, normalize, desc);
-        else if (C == 256) sample_gather_nhwc_kernel<2><<<g2, T, 0, stream>>>(raw, C, Hd, Wd, kpts, counts, kcap, scale, normalize, desc);
-        else sample_gather_nhwc_kernel<0><<<g2, T, 0, stream>>>(raw, C, Hd, Wd, kpts, counts, kcap, scale, normalize, desc);
+        if (C == 128) sample_gather_nhwc_kernel<1><<<g2, T, 0, stream>>>(raw, C, Hd, Wd, kpts, counts, kcap, scale, normalize, desc, so);
+        else if (C == 256) sample_gather_nhwc_kernel<2><<<g2, T, 0, stream>>>(raw, C, Hd, Wd, kpts, counts, kcap, scale, normalize, desc, so);
+        else sample_gather_nhwc_kernel<0><<<g2, T, 0, stream>>>(raw, C, Hd, Wd, kpts, counts, kcap, scale, normalize, desc, so);
     } else if (mode == EINX_SAMPLE_BILINEAR) {
         if (Hp <= 1 || Wp <= 1) return einx_fail(ctx, EINX_ERR_INVALID, "einx_sample: bilinear needs Hp, Wp > 1");
         // shared-memory slab variant when two coarse rows of every channel fit (odd pitch: lanes are
@@ -387,7 +449,7 @@ extern "C" int einx_sample(einx_ctx* ctx, const float* raw, int B, int C, int Hd
                 cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slab_bytes);
                 if (e != cudaSuccess) return e;
                 kern<<<dim3(Hd + 1, B), kSlabThreads, slab_bytes, stream>>>(raw, C, Hd, Wd, (float)Hp, (float)Wp, kpts,
-                                                                          counts, kcap, scale, normalize, desc, SP);
+                                                                          counts, kcap, scale, normalize, desc, SP, so);
                 return cudaSuccess;
             };
             switch (C) {
@@ -401,7 +463,7 @@ extern "C" int einx_sample(einx_ctx* ctx, const float* raw, int B, int C, int Hd
             return EINX_OK;
         }
         sample_kernel<EINX_SAMPLE_BILINEAR><<<grid, kWarpsPerBlock * 32, 0, stream>>>(
-            raw, C, Hd, Wd, (float)Hp, (float)Wp, kpts, counts, kcap, scale, normalize, desc);
+            raw, C, Hd, Wd, (float)Hp, (float)Wp, kpts, counts, kcap, scale, normalize, desc, so);
     } else {
         return einx_fail(ctx, EINX_ERR_INVALID, "einx_sample: unknown mode %d", mode);
     }

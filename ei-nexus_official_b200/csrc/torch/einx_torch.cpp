@@ -147,6 +147,29 @@ at::Tensor sample_cuda(const at::Tensor& raw, const at::Tensor& kpts, const at::
             "einx_sample");
     return desc;
 }
+std::tuple<at::Tensor, at::Tensor> sample_split_cuda(const at::Tensor& raw, const at::Tensor& kpts, const at::Tensor& counts, int64_t mode,
+                                                     int64_t Hp, int64_t Wp, double scale, bool normalize) {
+    Call c(raw);
+    TORCH_CHECK(raw.scalar_type() == at::kFloat && raw.dim() == 4, "raw: expected a 4-d float tensor");
+    want(kpts, at::kFloat, "kpts"); want(counts, at::kInt, "counts");
+    int m = (int)mode;
+    const int64_t B = raw.size(0), C = raw.size(1), Hd = raw.size(2), Wd = raw.size(3);
+    at::Tensor src = raw;
+    if (m == EINX_SAMPLE_GATHER && !raw.is_contiguous() && raw.is_contiguous(at::MemoryFormat::ChannelsLast)) m = EINX_SAMPLE_GATHER_NHWC;
+    else src = raw.contiguous();
+    const int64_t kcap = kpts.size(1);
+    at::Tensor desc = at::empty({B, kcap, C}, kpts.options());
+    at::Tensor split = at::empty({2, B, kcap, C}, kpts.options().dtype(at::kHalf));   // [hi | lo] of the FP16X3 matcher mode
+    c.check(einx_sample_split(c.ctx, src.data_ptr<float>(), (int)B, (int)C, (int)Hd, (int)Wd, m, (int)Hp, (int)Wp, kpts.data_ptr<float>(),
+                              counts.data_ptr<int32_t>(), (int)kcap, (float)scale, normalize ? 1 : 0, desc.data_ptr<float>(),
+                              (uint16_t*)split.data_ptr(), c.stream), "einx_sample_split");
+    return {desc, split};
+}
+std::tuple<at::Tensor, at::Tensor> sample_split_meta(const at::Tensor& raw, const at::Tensor& kpts, const at::Tensor&, int64_t, int64_t,
+                                                     int64_t, double, bool) {
+    return {at::empty({raw.size(0), kpts.size(1), raw.size(1)}, kpts.options()),
+            at::empty({2, raw.size(0), kpts.size(1), raw.size(1)}, kpts.options().dtype(at::kHalf))};
+}
 at::Tensor sample_meta(const at::Tensor& raw, const at::Tensor& kpts, const at::Tensor&, int64_t, int64_t, int64_t, double, bool) {
     return at::empty({raw.size(0), kpts.size(1), raw.size(1)}, kpts.options());
 }
@@ -155,7 +178,7 @@ at::Tensor sample_meta(const at::Tensor& raw, const at::Tensor& kpts, const at::
 std::vector<at::Tensor> mnn_cuda(const at::Tensor& d0, const at::Tensor& d1, const c10::optional<at::Tensor>& n0,
                                  const c10::optional<at::Tensor>& n1, const c10::optional<at::Tensor>& kpts0,
                                  const c10::optional<at::Tensor>& kpts1, double ratio_thresh, double distance_thresh, bool mutual,
-                                 int64_t precision) {
+                                 int64_t precision, const c10::optional<at::Tensor>& split0, const c10::optional<at::Tensor>& split1) {
     Call c(d0);
     want(d0, at::kFloat, "d0"); want(d1, at::kFloat, "d1");
     TORCH_CHECK(d0.dim() == 3 && d1.dim() == 3 && d0.size(0) == d1.size(0) && d0.size(2) == d1.size(2), "mnn: (B, N, D) and (B, M, D)");
@@ -172,7 +195,14 @@ std::vector<at::Tensor> mnn_cuda(const at::Tensor& d0, const at::Tensor& d1, con
         mk0 = at::empty({B, N, 3}, d0.options()); mk1 = at::empty({B, N, 3}, d0.options());
         nm = at::empty({B}, d0.options().dtype(at::kInt));
     }
-    c.check(einx_mnn(c.ctx, d0.data_ptr<float>(), d1.data_ptr<float>(), opt_ptr<int32_t>(n0), opt_ptr<int32_t>(n1), (int)B, (int)N, (int)M,
+    const uint16_t *sp0 = nullptr, *sp1 = nullptr;
+    if (split0.has_value() && split0->defined() && split1.has_value() && split1->defined()) {
+        TORCH_CHECK(split0->scalar_type() == at::kHalf && split1->scalar_type() == at::kHalf && split0->is_contiguous() && split1->is_contiguous() &&
+                        split0->numel() == 2 * d0.numel() && split1->numel() == 2 * d1.numel(),
+                    "mnn: split operands are contiguous (2, B, N|M, D) half tensors (einx::sample_split)");
+        sp0 = (const uint16_t*)split0->data_ptr(); sp1 = (const uint16_t*)split1->data_ptr();
+    }
+    c.check(einx_mnn_split(c.ctx, d0.data_ptr<float>(), d1.data_ptr<float>(), sp0, sp1, opt_ptr<int32_t>(n0), opt_ptr<int32_t>(n1), (int)B, (int)N, (int)M,
                      (int)D, (float)ratio_thresh, (float)distance_thresh, mutual ? 1 : 0, (int)precision, m0.data_ptr<int64_t>(),
                      m1.data_ptr<int64_t>(), s0.data_ptr<float>(), s1.data_ptr<float>(), gather ? kpts0->data_ptr<float>() : nullptr,
                      gather ? kpts1->data_ptr<float>() : nullptr, gather ? mk0.data_ptr<float>() : nullptr,
@@ -181,7 +211,8 @@ std::vector<at::Tensor> mnn_cuda(const at::Tensor& d0, const at::Tensor& d1, con
     return {m0, m1, s0, s1};
 }
 std::vector<at::Tensor> mnn_meta(const at::Tensor& d0, const at::Tensor& d1, const c10::optional<at::Tensor>&, const c10::optional<at::Tensor>&,
-                                 const c10::optional<at::Tensor>& kpts0, const c10::optional<at::Tensor>&, double, double, bool, int64_t) {
+                                 const c10::optional<at::Tensor>& kpts0, const c10::optional<at::Tensor>&, double, double, bool, int64_t,
+                                 const c10::optional<at::Tensor>&, const c10::optional<at::Tensor>&) {
     const int64_t B = d0.size(0), N = d0.size(1), M = d1.size(1);
     auto lo = d0.options().dtype(at::kLong);
     std::vector<at::Tensor> out = {at::empty({B, N}, lo), at::empty({B, M}, lo), at::empty({B, N}, d0.options()), at::empty({B, M}, d0.options())};
@@ -218,13 +249,15 @@ TORCH_LIBRARY(einx, m) {
     m.def("detect(Tensor(a!) score, Tensor? mask, int nms_radius, int border, float prob_thresh, int top_k, int kcap, bool want_map=False) -> (Tensor, Tensor, Tensor)");
     m.def("detect_pair(Tensor(a!) score0, Tensor(b!) score1, Tensor? mask0, Tensor? mask1, int nms_radius, int border, float prob_thresh, int top_k, int kcap) -> (Tensor, Tensor, Tensor, Tensor)");
     m.def("sample(Tensor raw, Tensor kpts, Tensor counts, int mode, int Hp, int Wp, float scale, bool normalize=True) -> Tensor");
-    m.def("mnn(Tensor d0, Tensor d1, Tensor? n0, Tensor? n1, Tensor? kpts0, Tensor? kpts1, float ratio_thresh, float distance_thresh, bool mutual, int precision) -> Tensor[]");
+    m.def("sample_split(Tensor raw, Tensor kpts, Tensor counts, int mode, int Hp, int Wp, float scale, bool normalize=True) -> (Tensor, Tensor)");
+    m.def("mnn(Tensor d0, Tensor d1, Tensor? n0, Tensor? n1, Tensor? kpts0, Tensor? kpts1, float ratio_thresh, float distance_thresh, bool mutual, int precision, Tensor? split0=None, Tensor? split1=None) -> Tensor[]");
 }
 TORCH_LIBRARY_IMPL(einx, CUDA, m) {
     m.impl("voxelize", voxelize_cuda);
     m.impl("detect", detect_cuda);
     m.impl("detect_pair", detect_pair_cuda);
     m.impl("sample", sample_cuda);
+    m.impl("sample_split", sample_split_cuda);
     m.impl("mnn", mnn_cuda);
 }
 TORCH_LIBRARY_IMPL(einx, Meta, m) {
@@ -232,5 +265,6 @@ TORCH_LIBRARY_IMPL(einx, Meta, m) {
     m.impl("detect", detect_meta);
     m.impl("detect_pair", detect_pair_meta);
     m.impl("sample", sample_meta);
+    m.impl("sample_split", sample_split_meta);
     m.impl("mnn", mnn_meta);
 }

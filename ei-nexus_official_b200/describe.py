@@ -29,8 +29,11 @@ def pack_rows(rows: Sequence[torch.Tensor], width: int, device) -> Tuple[torch.T
 
 @torch.no_grad()
 def sample(raw: torch.Tensor, kpts: torch.Tensor, counts: torch.Tensor, mode: int, image_size=(0, 0),
-           scale_factor=1.0, normalize: bool = True) -> torch.Tensor:
-    """einx_sample on padded keypoints: (B, C, Hd, Wd) map -> (B, kcap, C) descriptors (rows >= count zero)."""
+           scale_factor=1.0, normalize: bool = True, split: bool = False):
+    """einx_sample on padded keypoints: (B, C, Hd, Wd) map -> (B, kcap, C) descriptors (rows >= count zero).
+
+    ``split=True`` (einx_sample_split) also returns the (2, B, kcap, C) fp16 [hi | lo] operands of the matcher's
+    ``fp16x3`` mode, written by the same kernel: pass them to :func:`match.mnn` as ``split0`` / ``split1``."""
     if raw.dtype != torch.float32 or not raw.is_cuda:
         raise _lib.EinxError("sample: raw descriptors must be a float32 CUDA tensor (there is no CPU fallback)")
     C = raw.shape[1]
@@ -39,9 +42,9 @@ def sample(raw: torch.Tensor, kpts: torch.Tensor, counts: torch.Tensor, mode: in
         # (a channels-last map -- what cuDNN convolutions produce on Blackwell -- is read in place by the op: its
         # memory is (B, Hd, Wd, C), so a keypoint's descriptor is one contiguous read instead of C strided sectors)
         raw = raw.contiguous()
-    desc = _lib.ops().sample(raw, kpts.contiguous(), counts, int(mode), int(image_size[0]), int(image_size[1]),
-                             float(scale_factor), bool(normalize))
-    return desc
+    op = _lib.ops().sample_split if split else _lib.ops().sample
+    return op(raw, kpts.contiguous(), counts, int(mode), int(image_size[0]), int(image_size[1]), float(scale_factor),
+              bool(normalize))
 
 
 def _sparsify(raw, positions, mode, image_size, scale_factor, normalize):

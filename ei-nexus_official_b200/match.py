@@ -22,11 +22,13 @@ _PRECISION = {"fp32": FP32, "tf32x3": TF32X3, "bf16": BF16, "fp16x3": FP16X3}
 def mnn(desc0: torch.Tensor, desc1: torch.Tensor, n0: Optional[torch.Tensor] = None,
         n1: Optional[torch.Tensor] = None, kpts0: Optional[torch.Tensor] = None,
         kpts1: Optional[torch.Tensor] = None, ratio_thresh=None, distance_thresh=None, mutual: bool = True,
-        precision="fp32") -> Dict[str, torch.Tensor]:
+        precision="fp32", split0: Optional[torch.Tensor] = None, split1: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """einx_mnn on padded batches: desc0 (B, N, D), desc1 (B, M, D) fp32 CUDA; n0/n1 valid-row counts.
 
     Returns matches0/1 (int64, -1 = none), matching_scores0/1 and, when keypoints are given, the
-    compacted ``matched_kpts0/1`` (B, N, 3) with ``num_matches`` (B,) int32.
+    compacted ``matched_kpts0/1`` (B, N, 3) with ``num_matches`` (B,) int32.  ``split0`` / ``split1``: the fp16
+    operand pairs ``describe.sample(..., split=True)`` wrote for these descriptors (``fp16x3`` only; without them the
+    library derives the operands in a pre-pass -- same results).
     """
     if desc0.dtype != torch.float32 or not desc0.is_cuda or desc1.dtype != torch.float32 or not desc1.is_cuda:
         raise _lib.EinxError("mnn: descriptors must be float32 CUDA tensors (there is no CPU fallback)")
@@ -41,7 +43,7 @@ def mnn(desc0: torch.Tensor, desc1: torch.Tensor, n0: Optional[torch.Tensor] = N
             raise ValueError("mnn: keypoint rows must be (y, x, prob) -- three columns")
         kpts0, kpts1 = kpts0.contiguous(), kpts1.contiguous()
     res = _lib.ops().mnn(desc0, desc1, n0, n1, kpts0, kpts1, float(ratio_thresh or 0.0), float(distance_thresh or 0.0),
-                         bool(mutual), prec)
+                         bool(mutual), prec, split0, split1)
     m0, m1, s0, s1 = res[:4]
     if kpts0 is not None:
         mk0, mk1, nm = res[4:]

@@ -77,10 +77,21 @@ class ExtractMatchPipeline:
         queueing behind them."""
         c = self.cfg
         mode = describe.BILINEAR if c.descriptor_mode == "bilinear" else describe.GATHER
+        # fp16x3: the samplers write the matcher's fp16 hi / lo operands next to the fp32 descriptors (one fused
+        # kernel), so the similarity kernel's pipeline is TMA -> tcgen05.mma with nothing to convert
+        want_split = c.precision == "fp16x3" and raw0.shape[1] % 8 == 0 and raw1.shape[1] % 8 == 0
+        sp0 = sp1 = None
+
+        def sample(raw, k, n, size):
+            r = describe.sample(raw, k, n, mode, size, c.descriptor_scale, True, split=want_split)
+            return r if want_split else (r, None)
+
         if not c.concurrent:
             grid = self.voxelize(*events)
-            k0, c0, d0 = self.extract(score0, raw0, mask0)
-            k1, c1, d1 = self.extract(score1, raw1, mask1)
+            _, k0, c0 = _detect.detect(score0, c.detection_threshold, c.nms_radius, c.remove_borders, c.top_k, mask=mask0)
+            d0, sp0 = sample(raw0, k0, c0, score0.shape[-2:])
+            _, k1, c1 = _detect.detect(score1, c.detection_threshold, c.nms_radius, c.remove_borders, c.top_k, mask=mask1)
+            d1, sp1 = sample(raw1, k1, c1, score1.shape[-2:])
         else:
             dev = score0.device
             main = torch.cuda.current_stream(dev)
@@ -95,25 +106,28 @@ class ExtractMatchPipeline:
                                                         c.remove_borders, c.top_k, mask0, mask1)
                 s_side.wait_stream(main)
                 with torch.cuda.stream(s_side):
-                    d1 = describe.sample(raw1, k1, c1, mode, score1.shape[-2:], c.descriptor_scale, True)
-                d0 = describe.sample(raw0, k0, c0, mode, score0.shape[-2:], c.descriptor_scale, True)
+                    d1, sp1 = sample(raw1, k1, c1, score1.shape[-2:])
+                d0, sp0 = sample(raw0, k0, c0, score0.shape[-2:])
             else:
                 s_side.wait_stream(main)
                 with torch.cuda.stream(s_side):
-                    k1, c1, d1 = self.extract(score1, raw1, mask1)
-                k0, c0, d0 = self.extract(score0, raw0, mask0)
+                    _, k1, c1 = _detect.detect(score1, c.detection_threshold, c.nms_radius, c.remove_borders, c.top_k, mask=mask1)
+                    d1, sp1 = sample(raw1, k1, c1, score1.shape[-2:])
+                _, k0, c0 = _detect.detect(score0, c.detection_threshold, c.nms_radius, c.remove_borders, c.top_k, mask=mask0)
+                d0, sp0 = sample(raw0, k0, c0, score0.shape[-2:])
             main.wait_stream(s_side)
             if not torch.cuda.is_current_stream_capturing():
                 # caching-allocator bookkeeping: tensors cross streams in both directions (a captured
                 # step owns its memory pool for the lifetime of the graph instead)
-                for t in (k1, c1, d1, grid):
-                    t.record_stream(main)
+                for t in (k1, c1, d1, grid, sp1):
+                    if t is not None:
+                        t.record_stream(main)
                 for t in (score1, raw1, mask1, k1, c1):
                     if t is not None:
                         t.record_stream(s_side)
                 for t in events:
                     t.record_stream(s_vox)
-        out = match.mnn(d0, d1, c0, c1, k0, k1, None, None, True, self.cfg.precision)
+        out = match.mnn(d0, d1, c0, c1, k0, k1, None, None, True, self.cfg.precision, sp0, sp1)
         if self.cfg.concurrent:
             # the matcher does not read the voxel grid: its stream joins only here, so a late event scatter never
             # holds the MNN kernel back

@@ -119,6 +119,17 @@ int einx_sample(einx_ctx* ctx, const float* raw, int B, int C, int Hd, int Wd, i
                 int normalize, float* desc, einx_stream stream);
 
 /*
+ * einx_sample with a second output for the matcher: `split` (NULL to skip) receives the fp16 operand pair of
+ * the FP16X3 tensor-core mode, [hi (B, kcap, C) | lo (B, kcap, C)] with hi = fp16(2^10 d), lo = fp16(2^10 d - hi),
+ * written while the descriptor is in registers.  einx_mnn_split() consumes it, so the similarity kernel's tile
+ * pipeline is TMA -> MMA with nothing to convert.  Needs C % 8 == 0 and a 16-byte aligned buffer of
+ * 2 * B * kcap * C halves.
+ */
+int einx_sample_split(einx_ctx* ctx, const float* raw, int B, int C, int Hd, int Wd, int mode,
+                      int Hp, int Wp, const float* kpts, const int32_t* counts, int kcap, float scale,
+                      int normalize, float* desc, uint16_t* split, einx_stream stream);
+
+/*
  * Mutual-nearest-neighbour matching.  Replaces core/modules/matchers/MNN.py:11-22 (find_nn),
  * :25-32 (mutual_check) and :88-129 of NearestNeighborMatcher.forward.  The similarity matrix
  * is never written to memory: row/column argmax are fused into the tile epilogue.
@@ -134,6 +145,17 @@ int einx_mnn(einx_ctx* ctx, const float* d0, const float* d1, const int32_t* n0,
              float distance_thresh, int mutual, int precision, int64_t* m0, int64_t* m1,
              float* s0, float* s1, const float* kpts0, const float* kpts1, float* mk0,
              float* mk1, int32_t* nmatch, einx_stream stream);
+
+/*
+ * einx_mnn with the FP16X3 operands already split (einx_sample_split): split0 / split1 are the [hi | lo] fp16
+ * buffers of d0 / d1 (both or neither; NULL = derive them from d0 / d1 in one pre-pass, which is what einx_mnn
+ * does).  Ignored by the other precisions.  Results are identical either way.
+ */
+int einx_mnn_split(einx_ctx* ctx, const float* d0, const float* d1, const uint16_t* split0,
+                   const uint16_t* split1, const int32_t* n0, const int32_t* n1, int B, int ncap,
+                   int mcap, int D, float ratio_thresh, float distance_thresh, int mutual,
+                   int precision, int64_t* m0, int64_t* m1, float* s0, float* s1, const float* kpts0,
+                   const float* kpts1, float* mk0, float* mk1, int32_t* nmatch, einx_stream stream);
 
 /*
  * Opt-in dense by-products of MNN.py:88,96-98 for callers that really want them

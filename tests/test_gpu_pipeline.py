@@ -156,3 +156,44 @@ def test_torch_ops_trace_and_raise(einx):
     assert torch.equal(kp, eager[0]) and torch.equal(cn, eager[1])
     with pytest.raises(RuntimeError, match="einx_detect"):
         ops.detect(score.clone(), None, 99, 4, 1.0, K, K, False)  # nms_radius out of range -> EINX_ERR_UNSUPPORTED
+
+
+def test_sampler_split_operands_feed_the_matcher(einx):
+    """einx_sample_split writes the matcher's FP16X3 operands (hi = fp16(2^10 d), lo = fp16(2^10 d - hi)) next to the
+    fp32 descriptors; einx_mnn_split on them gives exactly what einx_mnn derives itself in its pre-pass."""
+    synth = importlib.import_module("ei-nexus_official_b200.synth")
+    desc = importlib.import_module("ei-nexus_official_b200.describe")
+    det = importlib.import_module("ei-nexus_official_b200.detection")
+    rng = np.random.default_rng(12)
+    for mode, (B, D, H, W, cell, K, scale) in ((desc.BILINEAR, (3, 256, 96, 128, 8, 300, 1.0)), (desc.GATHER, (2, 128, 72, 88, 1, 257, 1.41))):
+        sides = []
+        for s in range(2):
+            score = torch.from_numpy(synth.score_map(rng, B, H, W)).to(DEV)
+            raw = torch.from_numpy(synth.descriptor_map(rng, B, D, H // cell, W // cell)).to(DEV)
+            _, kp, cn = det.detect(score, 1.0, 4, 4, K, kcap=K)
+            d_plain = desc.sample(raw, kp, cn, mode, (H, W), scale, True)
+            d, sp = desc.sample(raw, kp, cn, mode, (H, W), scale, True, split=True)
+            assert torch.equal(d, d_plain) and sp.shape == (2, B, K, D) and sp.dtype == torch.float16
+            x = d * 1024.0
+            hi = x.half()
+            lo = (x - hi.float()).half()
+            assert torch.equal(sp[0], hi) and torch.equal(sp[1], lo)
+            if mode == desc.GATHER:  # channels-last map: same operands
+                d2, sp2 = desc.sample(raw.contiguous(memory_format=torch.channels_last), kp, cn, mode, (H, W), scale, True, split=True)
+                # (the channels-last kernel sums the norm in another order: 2e-6, like its own parity test)
+                assert (d2 - d).abs().max().item() <= 2e-6
+                x2 = d2 * 1024.0
+                assert torch.equal(sp2[0], x2.half()) and torch.equal(sp2[1], (x2 - x2.half().float()).half())
+            sides.append((d, sp, kp, cn))
+        (d0, sp0, k0, c0), (d1, sp1, k1, c1) = sides
+        a = einx.mnn(d0, d1, c0, c1, k0, k1, precision="fp16x3")
+        b = einx.mnn(d0, d1, c0, c1, k0, k1, precision="fp16x3", split0=sp0, split1=sp1)
+        for key in ("matches0", "matches1", "matching_scores0", "matching_scores1", "num_matches"):
+            assert torch.equal(a[key], b[key]), key
+        for i in range(B):  # (rows beyond num_matches are unspecified)
+            n = int(a["num_matches"][i])
+            assert torch.equal(a["matched_kpts0"][i, :n], b["matched_kpts0"][i, :n])
+            assert torch.equal(a["matched_kpts1"][i, :n], b["matched_kpts1"][i, :n])
+        ref = einx.mnn(d0, d1, c0, c1, k0, k1, precision="fp32")
+        agree = (ref["matches0"] == b["matches0"]).float().mean().item()
+        assert agree > 0.999, agree  # (index parity modulo fp32 near-ties is adjudicated in test_gpu_mnn_tc.py)
