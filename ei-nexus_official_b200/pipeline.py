@@ -86,7 +86,13 @@ class ExtractMatchPipeline:
             r = describe.sample(raw, k, n, mode, size, c.descriptor_scale, True, split=want_split)
             return r if want_split else (r, None)
 
-        if not c.concurrent:
+        if not c.concurrent and getattr(self, "pair_detect", False) and score0.shape == score1.shape:
+            grid = self.voxelize(*events)
+            (k0, c0), (k1, c1) = _detect.detect_pair(score0, score1, c.detection_threshold, c.nms_radius, c.remove_borders,
+                                                    c.top_k, mask0, mask1)
+            d0, sp0 = sample(raw0, k0, c0, score0.shape[-2:])
+            d1, sp1 = sample(raw1, k1, c1, score1.shape[-2:])
+        elif not c.concurrent:
             grid = self.voxelize(*events)
             _, k0, c0 = _detect.detect(score0, c.detection_threshold, c.nms_radius, c.remove_borders, c.top_k, mask=mask0)
             d0, sp0 = sample(raw0, k0, c0, score0.shape[-2:])
@@ -183,7 +189,10 @@ class HostBatch:
 
     ALIGN = 256
 
-    def __init__(self, events: Sequence[dict], score0, raw0, score1, raw1, chunks: int = 4, compact_events: bool = True):
+    def __init__(self, events: Sequence[dict], score0=None, raw0=None, score1=None, raw1=None, chunks: int = 4,
+                 compact_events: bool = True):
+        """``score0 .. raw1`` = None: an events-only batch -- the maps are produced on the device (by the conv backbones
+        in the real model, core/modules/EIM.py:89-93) and handed to ``HostStreamer.run(..., resident_maps=...)``."""
         import numpy as np
 
         B = len(events)
@@ -206,7 +215,8 @@ class HostBatch:
                       torch.from_numpy(off))
             else:
                 ev = voxel.pack_events(events[a:b])
-            maps = [torch.from_numpy(m[a:b]) if not torch.is_tensor(m) else m[a:b] for m in (score0, raw0, score1, raw1)]
+            maps = ([] if score0 is None else
+                    [torch.from_numpy(m[a:b]) if not torch.is_tensor(m) else m[a:b] for m in (score0, raw0, score1, raw1)])
             arrays = [t.contiguous() for t in (*ev, *maps)]
             layout, off_b = [], 0
             for t in arrays:
@@ -272,7 +282,9 @@ class HostStreamer:
         return st
 
     @torch.no_grad()
-    def run(self, hb: HostBatch, out_host: Dict[str, torch.Tensor]) -> None:
+    def run(self, hb: HostBatch, out_host: Dict[str, torch.Tensor], resident_maps=None) -> None:
+        """``resident_maps`` = (score0, raw0, score1, raw1) device tensors of the whole batch, for an events-only
+        ``hb``: only the events cross PCIe (the boundary of EIM.forward: maps come from on-device backbones)."""
         main = torch.cuda.current_stream(self.dev)
         # (the copy stream never waits for the compute stream as a whole -- only, through `_free`, for the kernels
         # that last read the staging set it is about to overwrite -- so uploads of the next call start while the
@@ -287,7 +299,11 @@ class HostStreamer:
                 ready = torch.cuda.Event()
                 ready.record(self.copy_stream)
             main.wait_event(ready)
-            x, y, t, p, off, s0, r0, s1, r1 = HostBatch.views(dbuf, layout)
+            if resident_maps is None:
+                x, y, t, p, off, s0, r0, s1, r1 = HostBatch.views(dbuf, layout)
+            else:
+                x, y, t, p, off = HostBatch.views(dbuf, layout)
+                s0, r0, s1, r1 = (m[a:b] for m in resident_maps)
             if hb.compact:  # expand the 13-byte wire format to the fp32 SoA the voxeliser reads
                 n = x.numel()
                 f = self._unpacked.get(k)
