@@ -335,117 +335,115 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
     }
 
     // ---- load the band: border + mask zeroing (in place on `score`), zero padding, UB bits -------- //
-    for (int i = tid; i < lrows * SB; i += kThreads) { LM[i] = 0u; UB[i] = 0u; XB[i] = 0u; }  // (XB: its pad words stay zero)
+    {
+        // bitmaps (LM, UB and the list plane are contiguous): 16-byte stores
+        uint4* z = reinterpret_cast<uint4*>(LM);
+        const int nz4 = (int)((sizeof(uint32_t) * ((size_t)2 * lrows * SB + (size_t)lrows * SB)) / 16);
+        for (int i = tid; i < nz4; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = 4 * nz4 + tid; i < 3 * lrows * SB; i += kThreads) LM[i] = 0u;
+    }
     if (tid == 0) { sh.und = 0; sh.wl_n[0] = sh.wl_n[1] = 0; sh.xcnt[0] = sh.xcnt[1] = 0; sh.sel_min = 0xffffffffu; sh.sel_cnt = 0; }
     for (int i = tid; i < 4 * 256; i += kThreads) (&sh.hist[0][0])[i] = 0u;
-    // zero pads of every row: PAD floats on the left, PAD on the right
-    if constexpr (PAD > 0) {
-        constexpr int PF = PAD / 2;  // float4 per row
-        for (int i = tid; i < L * PF; i += kThreads) {
-            const int l = i / PF, k = i - l * PF;
-            float* rowp = V + (size_t)l * WS;
-            const int off = k < PAD / 4 ? 4 * k : 4 * W4 + PAD + 4 * (k - PAD / 4);
-            *reinterpret_cast<float4*>(rowp + off) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    }
     {
-        // Phase 1: the whole band goes from global to shared memory as asynchronous copies (cp.async, 4 * vec bytes
-        // each, no register staging), all in flight at once -- one memory latency for the band instead of one per
-        // batch of rows.  Rows outside the image and the columns beyond Wp are zero-filled by plain stores.
+        // The whole band goes from global to shared memory as asynchronous copies (cp.async, 4 * vec bytes each, no
+        // register staging), all in flight at once -- one memory latency for the band.  A warp owns rows
+        // (warp, warp + 16, ...), a lane the chunks (lane, lane + 32, ...) of a row: no division per chunk.  Rows
+        // outside the image, the pad columns and the columns between Wp and the float4 boundary are zero-filled by
+        // plain stores to disjoint addresses.
         const float* simg = S.score + (size_t)b * Hp * Wp;
         const int vec = P.vec;
         const int cpr = Wp / vec;                 // copies per row (Wp % vec == 0)
         const int y_lo = max(0, R - ys), y_hi = min(L, Hp - ys + R);  // local rows inside the image: [y_lo, y_hi)
-        for (int i = tid; i < (y_hi - y_lo) * cpr; i += kThreads) {
-            const int lr = i / cpr, c = i - lr * cpr;
-            const int l = y_lo + lr, x = c * vec;
-            const float* src = simg + (size_t)(ys - R + l) * Wp + x;
-            const uint32_t dst = V_s + 4u * (uint32_t)(l * WS + PAD + x);
-            if (vec == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-            else if (vec == 2) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-            else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+        const int tailc = 4 * W4 - Wp;            // columns between Wp and the float4 boundary (0..3)
+        for (int l = warp; l < L; l += kWarps) {
+            float* vrow = V + (size_t)l * WS;
+            const uint32_t drow = V_s + 4u * (uint32_t)(l * WS + PAD);
+            if (l >= y_lo && l < y_hi) {
+                const float* srow = simg + (size_t)(ys - R + l) * Wp;
+                if (vec == 4) {
+                    for (int c = lane; c < cpr; c += 32)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(drow + 16u * c), "l"(srow + 4 * c) : "memory");
+                } else if (vec == 2) {
+                    for (int c = lane; c < cpr; c += 32)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(drow + 8u * c), "l"(srow + 2 * c) : "memory");
+                } else {
+                    for (int c = lane; c < cpr; c += 32)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(drow + 4u * c), "l"(srow + c) : "memory");
+                }
+                if (lane < tailc) vrow[PAD + Wp + lane] = 0.0f;
+            } else {
+                for (int g = lane; g < W4; g += 32) *reinterpret_cast<float4*>(vrow + PAD + 4 * g) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if constexpr (PAD > 0) {  // PAD floats of zeros on either side of the row
+                if (lane < PAD / 2) {
+                    const int off = lane < PAD / 4 ? 4 * lane : 4 * W4 + PAD + 4 * (lane - PAD / 4);
+                    *reinterpret_cast<float4*>(vrow + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        const int tailc = 4 * W4 - Wp;            // columns between Wp and the float4 boundary (0..3)
-        for (int i = tid; i < L * W4; i += kThreads) {
-            const int l = i / W4, g = i - l * W4;
-            if (l < y_lo || l >= y_hi) *reinterpret_cast<float4*>(V + (size_t)l * WS + PAD + 4 * g) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (tailc > 0)
-            for (int i = tid; i < (y_hi - y_lo) * tailc; i += kThreads) {
-                const int lr = i / tailc, c = i - lr * tailc;
-                V[(size_t)(y_lo + lr) * WS + PAD + Wp + c] = 0.0f;
-            }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     EINX_TRACE(1);
     {
-        // Phase 2, over shared memory: border frame and mask (written back to `score` where they change a pixel)
-        // and the bitmap of positive pixels.  A warp owns a fixed run of 128 columns, so its border-column test is
-        // loop invariant, and walks the rows of the band.
+        // Phase 2, over shared memory: the bitmap of positive pixels, one 32-pixel word per thread and step (eight
+        // float4 loads, rotated by the lane so that a quarter-warp touches eight different bank groups), and -- on the
+        // few words that hold border-frame or masked pixels -- the zeroing of those pixels in the band and, by the
+        // band that owns the row, in `score` itself (detector_util.py:138-164 works in place).
         float* simg = S.score + (size_t)b * Hp * Wp;
         const uint8_t* mimg = S.mask ? S.mask + (size_t)b * Hp * Wp : nullptr;
         const int bd = P.border;
-        const int wpr = min(NCW, kWarps);            // warps side by side on a row
-        const int lstep = kWarps / wpr;              // rows walked in parallel
+        const int xe = Wp - bd;  // columns >= xe belong to the frame
         int cnt = 0;
-        if (warp < wpr * lstep) {
-            for (int cw = warp % wpr; cw < NCW; cw += wpr) {
-                const int g = cw * 32 + lane, x = 4 * g;
-                const bool in_s = g < W4;
-                unsigned colkill = 0, inimg = 0;  // border columns / columns inside the image among this lane's 4 pixels
+        for (int wi = tid; wi < L * SW; wi += kThreads) {
+            const int l = wi / SW, sidx = wi - l * SW;
+            const int y = ys - R + l, x0 = 32 * sidx;
+            const bool rowin = y >= 0 && y < Hp;
+            const bool own = l >= R && l < R + nrows;
+            uint32_t pos = 0;
+            if (rowin && x0 < Wp) {
+                const uint32_t base = V_s + 4u * (uint32_t)(l * WS + PAD + x0);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if ((x + j) < bd || (x + j) >= Wp - bd) colkill |= 1u << j;
-                    if (x + j < Wp) inimg |= 1u << j;
+                for (int k = 0; k < 8; ++k) {
+                    const int kk = (k + lane) & 7;
+                    if (x0 + 4 * kk < 4 * W4) {
+                        const float4 q = lds128(base + 16u * kk);
+                        const uint32_t nib = (q.x > 0.0f ? 1u : 0u) | (q.y > 0.0f ? 2u : 0u) | (q.z > 0.0f ? 4u : 0u) | (q.w > 0.0f ? 8u : 0u);
+                        pos |= nib << (4 * kk);
+                    }
                 }
-                for (int l = warp / wpr; l < L; l += lstep) {
-                    const int y = ys - R + l;
-                    const bool own = l >= R && l < R + nrows;
-                    const bool rowin = y >= 0 && y < Hp;
-                    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-                    float* vrow = V + (size_t)l * WS + PAD + x;
-                    if (in_s && rowin) q = *reinterpret_cast<const float4*>(vrow);
-                    float e[4] = {q.x, q.y, q.z, q.w};
-                    unsigned kill = ((y < bd) | (y >= Hp - bd)) ? 0xfu : colkill;
-                    if (mimg && rowin && in_s) {
-                        const uint8_t* mrow = mimg + (size_t)y * Wp + x;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if ((inimg & (1u << j)) && mrow[j] == 0) kill |= 1u << j;
-                    }
-                    unsigned nz = 0, bits = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (e[j] != 0.0f) nz |= 1u << j;
-                        if (e[j] > 0.0f) bits |= 1u << j;
-                    }
-                    bits &= ~kill;
-                    if (nz & kill) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (kill & (1u << j)) e[j] = 0.0f;
-                        *reinterpret_cast<float4*>(vrow) = make_float4(e[0], e[1], e[2], e[3]);
-                        if (own) {  // the band that owns the row writes the zeroed frame / mask back
-                            float* srow = simg + (size_t)y * Wp + x;
-                            if (P.vec == 4) {
-                                *reinterpret_cast<float4*>(srow) = make_float4(e[0], e[1], e[2], e[3]);
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    if (nz & kill & (1u << j)) srow[j] = 0.0f;
-                            }
+                uint32_t kill = 0;
+                if (y < bd || y >= Hp - bd) {
+                    kill = 0xffffffffu;
+                } else {
+                    if (x0 < bd) kill |= (bd - x0 >= 32) ? 0xffffffffu : ((1u << (bd - x0)) - 1u);
+                    if (x0 + 32 > xe) kill |= (xe <= x0) ? 0xffffffffu : (0xffffffffu << (xe - x0));
+                }
+                const uint32_t inimg = (Wp - x0 >= 32) ? 0xffffffffu : ((1u << (Wp - x0)) - 1u);
+                if (mimg) {
+                    const uint8_t* mrow = mimg + (size_t)y * Wp + x0;
+                    for (int j = 0; j < 32; ++j)
+                        if (((inimg >> j) & 1u) && mrow[j] == 0) kill |= 1u << j;
+                }
+                kill &= inimg;
+                if (kill) {
+                    uint32_t kk = kill;
+                    float* vrow = V + (size_t)l * WS + PAD + x0;
+                    float* srow = simg + (size_t)y * Wp + x0;
+                    while (kk) {
+                        const int j = __ffs(kk) - 1;
+                        kk &= kk - 1;
+                        if (vrow[j] != 0.0f) {
+                            vrow[j] = 0.0f;
+                            if (own) srow[j] = 0.0f;  // the band that owns the row writes the zeroed frame / mask back
                         }
                     }
-                    if (own) cnt += __popc(bits);
-                    unsigned word = bits << (4 * (lane & 7));
-                    word |= __shfl_xor_sync(0xffffffffu, word, 1);
-                    word |= __shfl_xor_sync(0xffffffffu, word, 2);
-                    word |= __shfl_xor_sync(0xffffffffu, word, 4);
-                    if ((lane & 7) == 0 && in_s) UB[(size_t)l * SB + 1 + (x >> 5)] = word;
+                    pos &= ~kill;
                 }
             }
+            UB[(size_t)l * SB + 1 + sidx] = pos;
+            if (own) cnt += __popc(pos);
         }
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         if (lane == 0 && cnt) atomicAdd(&sh.und, cnt);
@@ -539,9 +537,10 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
 #pragma unroll
                         for (int c = 0; c < 4; ++c) p3[j2][c] = fmax3(h[j2][c], h[j1][c], h[j][c]);
                     };
-                    // Output row y = (row just ingested in slot j) - R: all of its window rows are in the ring.  A pixel
-                    // equal to its window maximum is a candidate unless the rows above already hold an equal value
-                    // (first-occurrence rule); candidates of 8 rows x 4 columns collect in one register.
+                    // Output row y = (row just ingested in slot j) - R: all of its window rows are in the ring.  A positive
+                    // pixel equal to its window maximum is a CANDIDATE; the first-occurrence rule (no equal value earlier in
+                    // raster order inside the window) is settled for the few candidates in pass 2, not here for every pixel.
+                    // Candidates of 8 rows x 4 columns collect in one register.
                     unsigned acc = 0;
                     auto emit = [&](auto slot, int y) {
                         constexpr int j = decltype(slot)::value;
@@ -556,41 +555,11 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
 #pragma unroll
                             for (int c = 0; c < 4; ++c) M[c] = fmaxf(M[c], p3[ji][c]);
                         }
-                        bool any;
-                        if constexpr (R >= 3) {
-                            // a zero pixel equal to its (all-zero) window implies the thread's other pixels are zero too
-                            any = (cv[jc][0] == M[0]) | (cv[jc][1] == M[1]) | (cv[jc][2] == M[2]) | (cv[jc][3] == M[3]);
-                            any = any && fmaxf(fmaxf(cv[jc][0], cv[jc][1]), fmaxf(cv[jc][2], cv[jc][3])) > 0.0f;
-                        } else {
-                            any = false;
+                        unsigned nib = 0;
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) any |= (cv[jc][c] > 0.0f && cv[jc][c] == M[c]);
-                        }
-                        if (any && active) {
-                            float up[4];  // maximum of the window rows above: rows y-R .. y-1
-                            if constexpr (R >= 3) {
-                                constexpr int jl = (j + P2 - R - 3) % P2;      // p3 of row y-3: rows y-3 .. y-1
-#pragma unroll
-                                for (int c = 0; c < 4; ++c) up[c] = p3[jl][c];
-#pragma unroll
-                                for (int i = 0; 3 * i < R - 3; ++i) {
-                                    const int ji = (j + 3 * i + 1) % P2;       // rows y-R+3i .. y-R+3i+2
-#pragma unroll
-                                    for (int c = 0; c < 4; ++c) up[c] = fmaxf(up[c], p3[ji][c]);
-                                }
-                            } else {
-#pragma unroll
-                                for (int c = 0; c < 4; ++c) {
-                                    up[c] = h[(jc + P2 - 1) % P2][c];
-                                    if (R == 2) up[c] = fmaxf(up[c], h[(jc + P2 - 2) % P2][c]);
-                                }
-                            }
-                            unsigned nib = 0;
-#pragma unroll
-                            for (int c = 0; c < 4; ++c)
-                                if (cv[jc][c] > 0.0f && cv[jc][c] == M[c] && up[c] < cv[jc][c]) nib |= 1u << c;
-                            acc |= nib << (4 * ((y - R) & 7));
-                        }
+                        for (int c = 0; c < 4; ++c)
+                            if (cv[jc][c] >= M[c] && cv[jc][c] > 0.0f) nib |= 1u << c;
+                        if (active) acc |= nib << (4 * ((y - R) & 7));
                         if (((y - R) & 7) == 7 || y == e - 1) {
                             // runs start on multiples of 8 rows, so this (8 rows x 4 columns) word has one writer
                             CB[(size_t)((y - R) >> 3) * CBW + g] = acc;
@@ -618,8 +587,9 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
                 EINX_TRACE(trace_slot); ++trace_slot;
                 __syncthreads();
                 EINX_TRACE(trace_slot); ++trace_slot;
-                // ---- dense pass 2: candidates -> maxima.  What is left of the first-occurrence test of
-                // detector_util.py:298-308: no equal value to the left in the same row.
+                // ---- dense pass 2: candidates -> maxima.  The first-occurrence test of detector_util.py:298-308 (the
+                // pooling index is the first maximum of the window in raster order): no equal value in the window rows
+                // above, none to the left in the same row.  Only candidates pay for it (one in ~80 pixels of a round).
                 for (int wi = tid; wi < ((nrows + 7) >> 3) * CBW; wi += kThreads) {
                     uint32_t c = CB[wi];
                     if (!c) continue;
@@ -636,6 +606,12 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
                         bool tie = false;
 #pragma unroll
                         for (int d = 1; d <= R; ++d) tie |= (lds32(px - 4 * d) == v);
+#pragma unroll
+                        for (int dy = 1; dy <= R; ++dy) {
+                            const uint32_t rowp = px - 4u * (uint32_t)(dy * WS);
+#pragma unroll
+                            for (int d = -R; d <= R; ++d) tie |= (lds32(rowp + 4 * d) == v);
+                        }
                         if (tie) continue;
                         atomicOr(&LM[widx], m);
                         if (MULTI) {  // the neighbours dilate their copies of my edge rows
