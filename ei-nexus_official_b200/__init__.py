@@ -13,7 +13,7 @@ from .detection import (depth_to_space, detect, detect_pair, events_mask, logits
 from .dist import gather_matches, pack_matches, shard_range
 from .match import NearestNeighborMatcher, filter_matches, mnn, mnn_dense, sigmoid_log_double_softmax
 from .metrics import Repeatability, gt_assign, pairwise_min_dist
-from .patch import patch_reference
+from .patch import patch_reference, unpatch_reference
 from .pipeline import CapturedStep, ExtractMatchPipeline, HostBatch, HostStreamer, PathConfig
 from .voxel import (distance_map_device, draw_events_accumulation_image, event_stack_device, events_image_signed_device,
                     events_to_distance_map, events_image_device, events_to_event_stack,
@@ -24,7 +24,7 @@ __all__ = [
     "EinxError", "context_for", "contexts_of", "launch_count", "events_to_voxel_grid", "time_normalization", "pack_events", "voxelize_batch",
     "voxelize_device", "detect", "detect_pair", "prob_map_to_points_map", "prob_map_to_positions_with_prob", "sample",
     "sparsify_full_resolution_descriptors", "sparsify_low_resolution_descriptors", "NearestNeighborMatcher",
-    "mnn", "mnn_dense", "ExtractMatchPipeline", "CapturedStep", "HostBatch", "HostStreamer", "PathConfig", "patch_reference", "shard_range", "pack_matches",
+    "mnn", "mnn_dense", "ExtractMatchPipeline", "CapturedStep", "HostBatch", "HostStreamer", "PathConfig", "patch_reference", "unpatch_reference", "shard_range", "pack_matches",
     "gather_matches", "logits_to_prob", "depth_to_space", "logits_to_score", "events_mask",
     "draw_events_accumulation_image", "events_image_device", "filter_matches", "events_to_event_stack",
     "events_to_time_surface", "event_stack_device", "time_surface_device", "sigmoid_log_double_softmax",

@@ -99,6 +99,19 @@ def _guarded(name, ours, original):
     return fn
 
 
+_PATCHED = []  # (module, attribute, original) of everything patch_reference() replaced, for unpatch_reference()
+
+
+def unpatch_reference():
+    """Put the reference's own functions back (everything patch_reference() replaced in this process)."""
+    n = 0
+    while _PATCHED:
+        m, attr, original = _PATCHED.pop()
+        setattr(m, attr, original)
+        n += 1
+    return n
+
+
 def patch_reference(modules=None, datasets: bool = False):
     """Returns {module name: [patched attribute, ...]}.
 
@@ -119,5 +132,6 @@ def patch_reference(modules=None, datasets: bool = False):
             if getattr(cur, "__module__", "").startswith(__package__):
                 continue
             setattr(m, attr, _guarded(attr, fn, cur))
+            _PATCHED.append((m, attr, cur))
             done.setdefault(m.__name__, []).append(attr)
     return done

@@ -3,7 +3,7 @@
 
 TEST / BENCH INFRASTRUCTURE ONLY (see oracle/einx_oracle.py): nothing under ei-nexus_official_b200/ imports it.
 
-The reference is pure Python, so there is nothing to compile: the six leaf modules the path lives in are copied
+The reference is pure Python, so there is nothing to compile: the leaf modules the path lives in (and the extractor modules around it) are copied
 verbatim from the reference checkout into oracle/_ref/ (git-ignored -- the sources never enter this repository's
 history -- but shipped to the GPU box with the working tree, like the built libeinx.so).  oracle/ref_arm.py loads
 them from there with stub parent packages (core/modules/__init__.py pulls kornia / hydra /
@@ -27,6 +27,15 @@ FILES = [
     "core/modules/utils/util.py",
     "core/modules/matchers/MNN.py",
     "datasets/representations.py",
+    # the extractor modules around the path (conv backbone + heads in stock PyTorch, Padder / filter glue): the
+    # integration test runs their forward() with and without einx.patch_reference()
+    "core/modules/event_extractors/EventExtractors.py",
+    "core/modules/net/backbone.py",
+    "core/modules/net/detector_head.py",
+    "core/modules/net/descriptor_head.py",
+    "core/modules/net/vgg.py",
+    "core/modules/net/pointnet.py",
+    "core/modules/net/conv.py",
 ]
 
 

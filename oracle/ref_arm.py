@@ -58,6 +58,39 @@ def load():
     return _mods
 
 
+_extractors = None
+
+
+def load_extractors():
+    """core/modules/event_extractors/EventExtractors.py of the reference (VGGExtractor: SuperPoint type, cell 8;
+    VGGExtractorNP: SiLK type, cell 1) with its net/ modules; `kornia` (imported, not used on this path) is stubbed."""
+    global _extractors
+    if _extractors is not None:
+        return _extractors
+    load()
+    if not os.path.isfile(f"{REF}/core/modules/event_extractors/EventExtractors.py"):
+        raise RuntimeError("oracle/_ref/ has no extractor modules: re-run `python oracle/make_ref.py`")
+    sys.modules.setdefault("kornia", types.ModuleType("kornia"))
+    for name in ("core.modules.net", "core.modules.event_extractors"):
+        m = types.ModuleType(name)
+        m.__path__ = [f"{REF}/{name.replace('.', '/')}"]
+        sys.modules.setdefault(name, m)
+
+    def ld(name, path):
+        if name in sys.modules and getattr(sys.modules[name], "__file__", None) == path:
+            return sys.modules[name]
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+        return mod
+
+    for leaf in ("vgg", "conv", "pointnet", "backbone", "detector_head", "descriptor_head"):
+        ld(f"core.modules.net.{leaf}", f"{REF}/core/modules/net/{leaf}.py")
+    _extractors = ld("core.modules.event_extractors.EventExtractors", f"{REF}/core/modules/event_extractors/EventExtractors.py")
+    return _extractors
+
+
 def pair_pipeline(ev, bins, H, W, score0, raw0, score1, raw1, kind, top_k, scale, nms_dist=4, border=4, prob_thresh=1.0):
     """One event-image pair through the reference functions (same arguments as einx_oracle.pair_pipeline).
 

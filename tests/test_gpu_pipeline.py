@@ -197,3 +197,47 @@ def test_sampler_split_operands_feed_the_matcher(einx):
         ref = einx.mnn(d0, d1, c0, c1, k0, k1, precision="fp32")
         agree = (ref["matches0"] == b["matches0"]).float().mean().item()
         assert agree > 0.999, agree  # (index parity modulo fp32 near-ties is adjudicated in test_gpu_mnn_tc.py)
+
+
+def test_bench_default_combination_against_oracle(einx):
+    """The combination bench.py times -- C2 shapes, precision fp16x3 (pre-split operands written by the sampler),
+    three streams, one CUDA-graph replay per step -- against the oracle pipeline pair by pair: voxel grid within
+    1e-5 relative, keypoints bit-exact, match indices identical except where the fp32 and fp64 oracles themselves
+    disagree (summation-order near-ties), adjudicated like the standalone matcher tests."""
+    from oracle import einx_oracle as O
+
+    synth = importlib.import_module("ei-nexus_official_b200.synth")
+    name, B = "c2_ec_superpoint", 4
+    c = synth.CONFIGS[name]
+    evs, maps = [], [[], [], [], []]
+    for i in range(B):
+        ev, sides = synth.pair_inputs(name, 500 + i, None)
+        evs.append(ev)
+        for k, m in enumerate((sides[0][0], sides[0][1], sides[1][0], sides[1][1])):
+            maps[k].append(m)
+    maps = [np.concatenate(m) for m in maps]
+    cfg = einx.PathConfig(bins=c["bins"], height=c["H"], width=c["W"], top_k=c["top_k"], descriptor_mode=c["kind"],
+                          descriptor_scale=c["scale"], precision="fp16x3", concurrent=True)
+    pipe = einx.ExtractMatchPipeline(cfg)
+    ev = tuple(t.to(DEV) for t in einx.pack_events(evs))
+    dmaps = [torch.from_numpy(m.copy()).to(DEV) for m in maps]
+    step = pipe.capture(ev, *dmaps)
+    for _ in range(2):
+        for d, m in zip(dmaps, maps):  # the step zeroes the border of the score maps in place: refresh, then replay
+            d.copy_(torch.from_numpy(m))
+        out = step.replay()
+    torch.cuda.synchronize()
+    for i in range(B):
+        grid, p0, p1, m = O.pair_pipeline(evs[i], c["bins"], c["H"], c["W"], maps[0][i:i + 1].copy(), maps[1][i:i + 1],
+                                          maps[2][i:i + 1].copy(), maps[3][i:i + 1], "low", c["top_k"], c["scale"])
+        g = out["voxel_grid"][i].cpu().numpy()
+        assert np.all(np.abs(g - grid) <= 1e-5 * np.maximum(np.abs(grid), 1.0) + 1e-6)
+        n0, n1 = int(out["counts0"][i]), int(out["counts1"][i])
+        assert np.array_equal(out["keypoints0"][i, :n0].cpu().numpy(), p0) and np.array_equal(out["keypoints1"][i, :n1].cpu().numpy(), p1)
+        d0, d1 = out["descriptors0"][i, :n0].cpu().numpy(), out["descriptors1"][i, :n1].cpu().numpy()
+        r32 = O.mnn_match(d0, d1)
+        r64 = O.mnn_match(d0, d1, sim_dtype=np.float64)
+        got = out["matches0"][i, :n0].cpu().numpy()
+        stable = r32["matches0"] == r64["matches0"]
+        assert stable.mean() >= 0.999 and np.array_equal(got[stable], r32["matches0"][stable])
+        assert int(out["num_matches"][i]) == int((got > -1).sum())
