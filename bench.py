@@ -313,7 +313,12 @@ def run_extra_configs(args, synth, einx, dev, world, rank, dist):
         evs = [synth.events(rng, c["events"], c["H"], c["W"], c["style"], c["dt"]) for _ in range(B)]
         ev = tuple(t.to(dev) for t in einx.pack_events(evs))
         sc = [torch.from_numpy(synth.score_map(rng, B, Hp, Wp)).to(dev) for _ in range(2)]
-        rw = [torch.randn((B, c["D"], Hp // c["cell"], Wp // c["cell"]), device=dev, generator=g) for _ in range(2)]
+        # SiLK-type (full-resolution gather) maps in torch.channels_last -- the layout cuDNN's convolutions produce
+        # natively on Blackwell: a keypoint's D channels are one contiguous read (einx_sample mode GATHER_NHWC); in
+        # NCHW the same gather is one 32-byte sector per 4-byte channel value
+        rw = [torch.randn((B, Hp // c["cell"], Wp // c["cell"], c["D"]), device=dev, generator=g).permute(0, 3, 1, 2)
+              if c["kind"] == "gather" else
+              torch.randn((B, c["D"], Hp // c["cell"], Wp // c["cell"]), device=dev, generator=g) for _ in range(2)]
         cfg = einx.PathConfig(bins=c["bins"], height=c["H"], width=c["W"], top_k=c["top_k"], descriptor_mode=c["kind"],
                               descriptor_scale=c["scale"], precision=args.precision)
         pipe = einx.ExtractMatchPipeline(cfg)
@@ -343,6 +348,7 @@ def run_extra_configs(args, synth, einx, dev, world, rank, dist):
                      "keypoints_per_side_mean": round(float(o["counts0"].float().mean()), 1),
                      "matches_per_pair_mean": round(float(o["num_matches"].float().mean()), 1),
                      "descriptors": "i.i.d. N(0,1) maps sampled at the keypoints, L2-normalised x scale",
+                     "descriptor_layout": "channels_last (NHWC memory)" if c["kind"] == "gather" else "NCHW",
                      "bf16_match_agreement": round(agree, 5), "mnn_precision": args.precision}
         del cap, pipe, serial, ev, sc, rw, o
         torch.cuda.empty_cache()

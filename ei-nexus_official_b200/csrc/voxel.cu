@@ -573,7 +573,8 @@ extern "C" int einx_voxelize(einx_ctx* ctx, const float* x, const float* y, cons
     voxel_scatter_kernel<<<dim3(per_window, B), kScatterThreads, 0, stream>>>(x, y, t, p, ev_offsets, bins, H, W, out);
     einx_prof_end(ctx, 0, stream);
     EINX_CHECK_LAUNCH(ctx);
-    if (normalize && (ncell & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+    static const bool two_kernel_norm = getenv("EINX_VOXEL_NORM_2K") != nullptr;
+    if (normalize && !two_kernel_norm && (ncell & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
         // fused path: smallest cluster whose slices fit shared memory
         const size_t fixed = align_up(sizeof(NormShared), 16);
         int CS = 0;
