@@ -18,11 +18,12 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
            "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
            "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic", "lts__t_bytes.sum"]
-NAMES = {"voxel_scatter_kernel": "voxel_scatter", "voxel_tile_kernel": "voxel_tile", "detect_kernel": "detect",
+NAMES = {"nms_kernel": "detect", "mnn_tc_kernel<(int)3": "mnn_similarity_fp16x3", "mnn_tc_kernel<3": "mnn_similarity_fp16x3",
+         "voxel_scatter_kernel": "voxel_scatter", "voxel_tile_kernel": "voxel_tile", "detect_kernel": "detect",
          "sample_bilinear_slab_kernel": "sample", "sample_kernel": "sample", "mnn_tc_kernel<(int)1": "mnn_similarity_tf32x3",
          "mnn_tc_kernel<1": "mnn_similarity_tf32x3", "mnn_tc_kernel<(int)0": "mnn_similarity_bf16",
-         "mnn_tc_kernel<0": "mnn_similarity_bf16", "mnn_tc_kernel<(int)2": "mnn_similarity_fp16x3",
-         "mnn_tc_kernel<2": "mnn_similarity_fp16x3", "mnn_fp32_kernel": "mnn_similarity_fp32"}
+         "mnn_tc_kernel<0": "mnn_similarity_bf16", "mnn_tc_kernel<(int)2": "mnn_similarity_fp16x3_inkernel",
+         "mnn_tc_kernel<2": "mnn_similarity_fp16x3_inkernel", "mnn_fp32_kernel": "mnn_similarity_fp32"}
 
 
 def main():
