@@ -14,6 +14,7 @@ struct einx_ctx {
     void* ws;             // grow-only device workspace
     size_t ws_bytes;
     cudaStream_t ws_stream;  // stream the workspace was allocated on (cudaMallocAsync)
+    int32_t* redo_flags;     // [65536] per-image flags of the tiled detect kernel (outside the workspace: the redo pass reuses that)
     int64_t launches;
     int profile;                    // einx_profile_enable
     cudaEvent_t prof_ev[4][2];      // [slot][begin/end], created lazily

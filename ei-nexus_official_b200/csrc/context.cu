@@ -110,6 +110,7 @@ void einx_destroy(einx_ctx* ctx) {
         cudaDeviceSynchronize();
         cudaFree(ctx->ws);  // (valid for stream-ordered allocations too; the stream may be gone by now)
     }
+    if (ctx->redo_flags) cudaFree(ctx->redo_flags);
     for (int s = 0; s < EINX_PROFILE_SLOTS; ++s)
         for (int k = 0; k < 2; ++k)
             if (ctx->prof_ev[s][k]) cudaEventDestroy(ctx->prof_ev[s][k]);

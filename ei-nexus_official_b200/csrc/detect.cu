@@ -71,6 +71,16 @@ struct NmsParams {
     float* surv_val;
     int32_t* surv_idx;
     long long* trace;  // developer aid (EINX_DETECT_TRACE=1): clock64() at phase boundaries of CTA 0
+    // Tiled form for maps that no single cluster holds (1280 x 720): an image is cut into NT row tiles, each run by its
+    // own cluster on the sub-image [own rows +- apron).  After k rounds a pixel's state depends on the initial values
+    // within 2 R k rows of it, so the own rows of a tile are exact whenever its run took at most apron / (2 R) rounds;
+    // a tile that needed more raises its image's flag and the exact large-map kernel redoes that image.
+    int NT;          // tiles per image (0: untiled)
+    int tile_rows;   // own rows per tile
+    int apron;       // rows of context on either side of the own rows
+    int seg_cap;     // survivor slots per (tile, band) segment
+    int32_t* seg_cnt;   // [B * NT * T] survivors written per segment
+    int32_t* redo;      // [B] set to 1 when a tile of the image ran more rounds than its apron covers
 };
 
 #define EINX_TRACE(slot)                                                                                  \
@@ -283,11 +293,20 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
     cg::cluster_group cluster = cg::this_cluster();
     const int T = MULTI ? P.T : 1;
     const int rank = MULTI ? (int)cluster.block_rank() : 0;
-    const int bg = blockIdx.x / T;                         // image of the launch
+    const int unit = blockIdx.x / T;                       // image (or image tile) of the launch
+    const bool tiled = MULTI && P.NT > 0;
+    const int bg = tiled ? unit / P.NT : unit;             // image of the launch
+    const int tile = tiled ? unit - bg * P.NT : 0;
     const NmsSide& S = P.side[bg >= P.Bsplit ? 1 : 0];
     const int b = bg >= P.Bsplit ? bg - P.Bsplit : bg;    // image of its side
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int WS = P.WS, SB = P.SB, SW = P.SB - 2, Hp = P.Hp, Wp = P.Wp, W4 = P.W4, NCW = P.NCW;
+    const int WS = P.WS, SB = P.SB, SW = P.SB - 2, Wp = P.Wp, W4 = P.W4, NCW = P.NCW;
+    const int Hfull = P.Hp;                                // rows of the whole map
+    // the (sub-)image this cluster works on: rows [y_off, y_off + Hp) of the map; own rows [own_lo, own_hi) (map rows)
+    const int own_lo = tiled ? tile * P.tile_rows : 0;
+    const int own_hi = tiled ? min(Hfull, own_lo + P.tile_rows) : Hfull;
+    const int y_off = tiled ? max(0, own_lo - P.apron) : 0;
+    const int Hp = tiled ? min(Hfull, own_hi + P.apron) - y_off : Hfull;
     EINX_TRACE(0);
 
     // balanced row bands
@@ -350,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
         // (warp, warp + 16, ...), a lane the chunks (lane, lane + 32, ...) of a row: no division per chunk.  Rows
         // outside the image, the pad columns and the columns between Wp and the float4 boundary are zero-filled by
         // plain stores to disjoint addresses.
-        const float* simg = S.score + (size_t)b * Hp * Wp;
+        const float* simg = S.score + ((size_t)b * Hfull + y_off) * Wp;
         const int vec = P.vec;
         const int cpr = Wp / vec;                 // copies per row (Wp % vec == 0)
         const int y_lo = max(0, R - ys), y_hi = min(L, Hp - ys + R);  // local rows inside the image: [y_lo, y_hi)
@@ -391,8 +410,8 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
         // float4 loads, rotated by the lane so that a quarter-warp touches eight different bank groups), and -- on the
         // few words that hold border-frame or masked pixels -- the zeroing of those pixels in the band and, by the
         // band that owns the row, in `score` itself (detector_util.py:138-164 works in place).
-        float* simg = S.score + (size_t)b * Hp * Wp;
-        const uint8_t* mimg = S.mask ? S.mask + (size_t)b * Hp * Wp : nullptr;
+        float* simg = S.score + ((size_t)b * Hfull + y_off) * Wp;
+        const uint8_t* mimg = S.mask ? S.mask + ((size_t)b * Hfull + y_off) * Wp : nullptr;
         const int bd = P.border;
         const int xe = Wp - bd;  // columns >= xe belong to the frame
         int cnt = 0;
@@ -400,7 +419,9 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
             const int l = wi / SW, sidx = wi - l * SW;
             const int y = ys - R + l, x0 = 32 * sidx;
             const bool rowin = y >= 0 && y < Hp;
-            const bool own = l >= R && l < R + nrows;
+            const int gy = y + y_off;  // row of the whole map
+            const bool band_own = l >= R && l < R + nrows;               // rows this band counts as undecided
+            const bool own = band_own && gy >= own_lo && gy < own_hi;      // rows this band writes back to `score`
             uint32_t pos = 0;
             if (rowin && x0 < Wp) {
                 const uint32_t base = V_s + 4u * (uint32_t)(l * WS + PAD + x0);
@@ -414,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
                     }
                 }
                 uint32_t kill = 0;
-                if (y < bd || y >= Hp - bd) {
+                if (gy < bd || gy >= Hfull - bd) {
                     kill = 0xffffffffu;
                 } else {
                     if (x0 < bd) kill |= (bd - x0 >= 32) ? 0xffffffffu : ((1u << (bd - x0)) - 1u);
@@ -443,7 +464,7 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
                 }
             }
             UB[(size_t)l * SB + 1 + sidx] = pos;
-            if (own) cnt += __popc(pos);
+            if (band_own) cnt += __popc(pos);
         }
         cnt = __reduce_add_sync(0xffffffffu, cnt);
         if (lane == 0 && cnt) atomicAdd(&sh.und, cnt);
@@ -456,12 +477,14 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
         else __syncthreads();
     };
 
+    int rounds_done = 0;  // rounds that changed the state (uniform over the cluster)
     if constexpr (R > 0) {
         const int cap = min(P.LC, 8 * kThreads);   // worklist capacity (phase 3 holds 8 entries per thread)
         bool sparse = false;
         int n_wl = 0;           // worklist length (sparse rounds; uniform in the CTA)
         int trace_slot = 2;
         for (int round = 0;; ++round) {
+            rounds_done = round;
             sync_all();  // every band's V / UB / LM / count is final for this round
             trace_slot = round < 16 ? 2 + 7 * round : 126;
             EINX_TRACE(trace_slot); ++trace_slot;
@@ -814,6 +837,51 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
     }
 
     EINX_TRACE(120);
+    if (tiled) {
+        // ---- tiled form: the survivors of this band's rows that the tile owns, in raster order, into the band's
+        // segment; nms_tile_tail_kernel strings the segments of an image together, selects the threshold and writes
+        // the keypoints.  A tile whose run outlasted its apron flags the image for the exact redo.
+        const size_t seg = (size_t)unit * T + rank;
+        float* sl = P.surv_val + seg * P.seg_cap;
+        int32_t* si = P.surv_idx + seg * P.seg_cap;
+        const int nwords = nrows * SW;
+        const int per = (nwords + kThreads - 1) / kThreads;
+        const int w0 = min(tid * per, nwords), w1 = min(w0 + per, nwords);
+        int mine = 0, own_n = 0;
+        for (int wi = w0; wi < w1; ++wi) {
+            const int lr = wi / SW, sx = wi - lr * SW;
+            const int gy = y_off + ys + lr;
+            if (gy >= own_lo && gy < own_hi) mine += __popc(LM[(size_t)(lr + R) * SB + 1 + sx]);
+        }
+        int pos = block_excl_scan(mine, sh.warp_scan, own_n);
+        for (int wi = w0; wi < w1; ++wi) {
+            const int lr = wi / SW, sx = wi - lr * SW;
+            const int gy = y_off + ys + lr;
+            if (gy < own_lo || gy >= own_hi) continue;
+            uint32_t w = LM[(size_t)(lr + R) * SB + 1 + sx];
+            while (w) {
+                const int bit = __ffs(w) - 1;
+                w &= w - 1;
+                const int x = 32 * sx + bit;
+                if (pos < P.seg_cap) {
+                    sl[pos] = V[(size_t)(lr + R) * WS + PAD + x];
+                    si[pos] = gy * Wp + x;
+                }
+                ++pos;
+            }
+        }
+        if (tid == 0) {
+            P.seg_cnt[seg] = min(own_n, P.seg_cap);
+            if (rank == 0) {
+                // rows of context actually present on either side (a side that ends at the map's edge needs none)
+                const int top = y_off > 0 ? own_lo - y_off : (1 << 28);
+                const int bottom = y_off + Hp < Hfull ? (y_off + Hp) - own_hi : (1 << 28);
+                if (2 * R * rounds_done > min(top, bottom)) P.redo[bg] = 1;
+            }
+        }
+        cluster.sync();  // nobody leaves while a neighbour may still read its shared memory
+        return;
+    }
     // ---- survivors -> ordered per-image list ------------------------------------------------- //
     // At the fixpoint the selected pixels (LM bits of the own rows) are exactly the survivors.  The lists
     // live in the shared-memory scratch (UB + list buffer, both dead now) for single-CTA images, in the
@@ -966,12 +1034,218 @@ __global__ void __launch_bounds__(kThreads, 1) nms_kernel(const NmsParams P) {
     EINX_TRACE(125);
 }
 
+// ---- tiled form, second kernel: one CTA per image ------------------------------------------------ //
+// Selects the top-k threshold over the survivors of all (tile, band) segments of an image
+// (detector_util.py:108-133) and writes the keypoint rows in raster order (= segment order) and, optionally, the
+// dense map (zeroed by the host beforehand).  The selection only needs the multiset of values: a warp reads its
+// segments once, the values stay in registers through the four radix passes.
+constexpr int kTailThreads = 1024;
+constexpr int kTailWarps = kTailThreads / 32;
+constexpr int kTailHeld = 40;
+
+struct TailShared {
+    unsigned int hist[4][256];
+    unsigned int sel_min, sel_cnt;
+    int warp_scan[kTailWarps + 1];
+};
+
+__device__ __forceinline__ int tail_block_scan(int v, int* scratch, int& total) {  // exclusive scan over 1024 threads
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    __syncthreads();
+    if (lane == 31) scratch[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const int w = scratch[lane];
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += n;
+        }
+        scratch[lane] = winc - w;
+        if (lane == 31) scratch[kTailWarps] = winc;
+    }
+    __syncthreads();
+    total = scratch[kTailWarps];
+    return inc - v + scratch[warp];
+}
+
+__global__ void __launch_bounds__(kTailThreads, 1) nms_tile_tail_kernel(const NmsParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TailShared& sh = *reinterpret_cast<TailShared*>(smem_raw);
+    // work items: 32 consecutive entries of a segment, in segment order (= raster order)
+    int* item_off = reinterpret_cast<int*>(smem_raw + align_up(sizeof(TailShared), 16));  // [nseg + 1] first item of a segment
+    int* item_pos = item_off + (P.NT * P.T + 1);                                          // [kTailHeld * 32] kept rows before an item
+    int* seg_n = item_pos + kTailHeld * kTailWarps;                                       // [nseg] entries of a segment
+    unsigned short* item_seg = reinterpret_cast<unsigned short*>(seg_n + P.NT * P.T);     // [kTailHeld * 32] segment of an item
+    const int bg = blockIdx.x;
+    const NmsSide& S = P.side[bg >= P.Bsplit ? 1 : 0];
+    const int b = bg >= P.Bsplit ? bg - P.Bsplit : bg;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nseg = P.NT * P.T, Hp = P.Hp, Wp = P.Wp;
+    const int32_t* cnt = P.seg_cnt + (size_t)bg * nseg;
+    const float* seg_val = P.surv_val + (size_t)bg * nseg * P.seg_cap;
+    const int32_t* seg_idx = P.surv_idx + (size_t)bg * nseg * P.seg_cap;
+    if (tid == 0) { sh.sel_min = 0xffffffffu; sh.sel_cnt = 0; }
+    for (int i = tid; i < 4 * 256; i += kTailThreads) (&sh.hist[0][0])[i] = 0u;
+    int nitems, total;
+    {
+        const int c = tid < nseg ? __ldcg(cnt + tid) : 0;
+        const int ex = tail_block_scan((c + 31) >> 5, sh.warp_scan, nitems);
+        if (tid < nseg) { item_off[tid] = ex; seg_n[tid] = c; }
+        if (tid == 0) item_off[nseg] = nitems;
+        (void)tail_block_scan(c, sh.warp_scan, total);
+    }
+    __syncthreads();
+    for (int sgm = warp; sgm < nseg; sgm += kTailWarps)   // segment of every item (a warp per segment)
+        for (int it = item_off[sgm] + lane; it < item_off[sgm + 1]; it += 32) item_seg[it] = (unsigned short)sgm;
+    __syncthreads();
+    // values into registers: warp w takes items w, w + 32, ...: slot u of a lane is entry `lane` of item w + 32 u
+    // (the host guarantees nitems <= kTailHeld * 32)
+    unsigned ev[kTailHeld];
+    auto item_segment = [&](int it) { return (int)item_seg[it]; };
+#pragma unroll
+    for (int u = 0; u < kTailHeld; ++u) {
+        const int it = warp + kTailWarps * u;
+        ev[u] = 0u;
+        if (it < nitems) {
+            const int sgm = item_segment(it);
+            const int i = 32 * (it - item_off[sgm]) + lane;
+            if (i < seg_n[sgm]) ev[u] = __float_as_uint(__ldcg(seg_val + (size_t)sgm * P.seg_cap + i));
+        }
+    }
+    float thr = P.prob_thresh;
+    if (P.use_topk == 2) {
+        thr = fminf(0.0f, P.prob_thresh);
+    } else if (P.use_topk == 1) {
+        const int n = Hp * Wp;
+        const int zeros = n - total;
+        float a = 0.0f, bq = 0.0f;
+        if (P.rank_hi >= zeros) {
+            const bool lo_on_zero = P.rank_lo < zeros;   // lo falls on a zero, hi on the smallest survivor
+            const unsigned j = lo_on_zero ? 0u : (unsigned)(P.rank_lo - zeros);
+            const bool need_next = !lo_on_zero && P.rank_hi != P.rank_lo;
+            // j-th smallest of the positive floats (bit patterns; empty slots hold 0 and are skipped) via 4 radix passes
+            unsigned mask = 0, prefix = 0, rank = j;
+#pragma unroll 1
+            for (int p = 0; p < 4; ++p) {
+                const int shift = 24 - 8 * p;
+                unsigned int* hist = sh.hist[p];
+#pragma unroll
+                for (int u = 0; u < kTailHeld; ++u) {
+                    if (warp + kTailWarps * u >= nitems) break;  // warp-uniform
+                    const bool in = ev[u] != 0u && (ev[u] & mask) == prefix;
+                    const unsigned digit = (ev[u] >> shift) & 255u;
+                    const unsigned peers = __match_any_sync(0xffffffffu, in ? digit : 0x100u);
+                    if (in && (int)(__ffs(peers) - 1) == lane) atomicAdd(&hist[digit], (unsigned)__popc(peers));
+                }
+                __syncthreads();
+                unsigned c[8], mine = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { c[k] = hist[lane * 8 + k]; mine += c[k]; }
+                unsigned inc = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned nn = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += nn;
+                }
+                const unsigned before = inc - mine;
+                const bool here = (before <= rank) && (rank < inc);
+                unsigned cum = before;
+                int bin = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (cum + c[k] <= rank && bin == k) { cum += c[k]; bin = k + 1; }
+                }
+                const unsigned src = __ffs(__ballot_sync(0xffffffffu, here)) - 1;
+                rank = __shfl_sync(0xffffffffu, rank - cum, src);
+                prefix |= __shfl_sync(0xffffffffu, (unsigned)(lane * 8 + bin), src) << shift;
+                mask |= 255u << shift;
+            }
+            const unsigned abits = prefix;
+            float va = __uint_as_float(abits), vb = va;
+            if (need_next) {
+                unsigned cn = 0, mn = 0xffffffffu;
+#pragma unroll
+                for (int u = 0; u < kTailHeld; ++u)
+                    if (ev[u] != 0u) {
+                        if (ev[u] <= abits) cn++;
+                        else mn = min(mn, ev[u]);
+                    }
+                cn = __reduce_add_sync(0xffffffffu, cn);
+                mn = __reduce_min_sync(0xffffffffu, mn);
+                if (lane == 0) {
+                    if (cn) atomicAdd(&sh.sel_cnt, cn);
+                    atomicMin(&sh.sel_min, mn);
+                }
+                __syncthreads();
+                vb = (sh.sel_cnt > j + 1u) ? va : __uint_as_float(sh.sel_min);
+            }
+            if (lo_on_zero) { bq = va; a = 0.0f; }
+            else { a = va; bq = vb; }
+        }
+        const float thr_k = __fsub_rn(bq, __fmul_rn(__fsub_rn(bq, a), 0.5f));
+        thr = fminf(thr_k, P.prob_thresh);
+    }
+    // kept rows per item, prefix in item order (= raster order), then the rows -- values still from the registers
+#pragma unroll
+    for (int u = 0; u < kTailHeld; ++u) {
+        const bool keep = ev[u] != 0u && __uint_as_float(ev[u]) > thr;
+        const unsigned kb = __ballot_sync(0xffffffffu, keep);
+        const int it = warp + kTailWarps * u;
+        if (lane == 0 && it < nitems) item_pos[it] = __popc(kb);
+    }
+    __syncthreads();
+    int ktotal = 0;
+    for (int base = 0; base < nitems; base += kTailThreads) {  // (nitems <= 1280: at most two rounds)
+        const int i = base + tid;
+        const int c = i < nitems ? item_pos[i] : 0;
+        int chunk_total;
+        const int ex = tail_block_scan(c, sh.warp_scan, chunk_total);
+        __syncthreads();
+        if (i < nitems) item_pos[i] = ktotal + ex;
+        ktotal += chunk_total;
+    }
+    __syncthreads();
+    if (tid == 0) S.counts[b] = ktotal;
+    float* krows = S.kpts + (size_t)b * P.kcap * 3;
+    float* out = S.nms_map ? S.nms_map + (size_t)b * Hp * Wp : nullptr;
+#pragma unroll
+    for (int u = 0; u < kTailHeld; ++u) {
+        const int it = warp + kTailWarps * u;
+        if (it >= nitems) break;  // warp-uniform
+        const bool keep = ev[u] != 0u && __uint_as_float(ev[u]) > thr;
+        const unsigned kb = __ballot_sync(0xffffffffu, keep);
+        if (kb == 0u) continue;   // warp-uniform
+        const int sgm = item_segment(it);
+        if (keep) {
+            const int my = item_pos[it] + __popc(kb & ((1u << lane) - 1u));
+            const int i = 32 * (it - item_off[sgm]) + lane;
+            const int idx = __ldcg(seg_idx + (size_t)sgm * P.seg_cap + i);
+            const float v = __uint_as_float(ev[u]);
+            if (my < P.kcap) {
+                const int y = idx / Wp, x = idx - y * Wp;
+                krows[(size_t)my * 3 + 0] = (float)y + 0.5f;
+                krows[(size_t)my * 3 + 1] = (float)x + 0.5f;
+                krows[(size_t)my * 3 + 2] = v;
+            }
+            if (out) out[idx] = v;
+        }
+    }
+}
+
 template <int R, bool MULTI>
 int launch_nms(einx_ctx* ctx, const NmsParams& P, size_t smem, cudaStream_t stream) {
     auto kern = nms_kernel<R, MULTI>;
     EINX_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(P.B * P.T);
+    cfg.gridDim = dim3(P.B * P.T * (P.NT > 0 ? P.NT : 1));
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
@@ -1090,7 +1364,75 @@ int detect_impl(einx_ctx* ctx, const NmsSide* sides, int nsides, int Bside, int 
         if (rb + 2 * R >= 32768 || Wp >= 65536) break;  // worklist entries pack (row << 16 | x), bit 31 = flag
         if (list_entries(rb) > 0) { T = t; break; }
     }
-    if (T == 0) {  // no cluster of bands holds the map in shared memory: L2-resident variant
+    if (T == 0) {
+        // No cluster of bands holds the map in shared memory.  Tiled form: row tiles of `own` rows, each run by its own
+        // 8-band cluster on the sub-image [own rows +- apron); exact whenever a tile's run takes at most
+        // apron / (2 R) rounds (8 here), checked on the device; the L2-resident kernel of detect_large.cu then redoes
+        // only the images that raised their flag.  EINX_DETECT_TILED=0 keeps the old path.
+        static const bool tiled_off = getenv("EINX_DETECT_TILED") && atoi(getenv("EINX_DETECT_TILED")) == 0;
+        const int Tt = kMaxCluster;
+        int rb_max = 0;  // largest band (rows) that fits one CTA
+        for (int rb = 2 * (R > 0 ? R : 1); rb + 2 * R < 32768 && Wp < 65536; ++rb) {
+            if (list_entries(rb) > 0) rb_max = rb; else break;
+        }
+        const int apron = 16 * (R > 0 ? R : 1);          // 8 rounds of 2 R rows
+        const int own = Tt * rb_max - 2 * apron;         // own rows of an interior tile
+        if (!tiled_off && R > 0 && rb_max >= 2 * R + 8 && own >= 4 * R && B <= 65536) {
+            P.NT = (Hp + own - 1) / own;
+            P.tile_rows = own;
+            P.apron = apron;
+            P.T = Tt;
+            int hs_max = 0;  // tallest sub-image over the tiles
+            for (int t = 0; t < P.NT; ++t) {
+                const int lo = t * own, hi = lo + own < Hp ? lo + own : Hp;
+                const int y0 = lo - apron > 0 ? lo - apron : 0, y1 = hi + apron < Hp ? hi + apron : Hp;
+                if (y1 - y0 > hs_max) hs_max = y1 - y0;
+            }
+            P.RB = (hs_max + Tt - 1) / Tt;
+            P.LC = list_entries(P.RB);
+            P.NSEG = kWarps / P.NCW > 0 ? kWarps / P.NCW : 1;
+            if (P.NSEG > P.RB) P.NSEG = P.RB;
+            P.SR = ((P.RB + P.NSEG - 1) / P.NSEG + 7) / 8 * 8;
+            P.tail_smem = 0;
+            P.seg_cap = ((P.RB + R) / (R + 1)) * ((Wp + R) / (R + 1));
+            const size_t nseg = (size_t)B * P.NT * Tt;
+            const size_t seg_elems = nseg * P.seg_cap;
+            const size_t list_bytes = align_up(seg_elems * 4, 256);
+            const size_t cnt_bytes = align_up(nseg * 4, 256);
+            int rc = einx_ws_reserve(ctx, 2 * list_bytes + cnt_bytes, stream);
+            if (rc) return rc;
+            if (!ctx->redo_flags) EINX_CUDA(ctx, cudaMalloc(&ctx->redo_flags, 65536 * sizeof(int32_t)));
+            unsigned char* ws = (unsigned char*)ctx->ws;
+            P.surv_val = (float*)ws;
+            P.surv_idx = (int32_t*)(ws + list_bytes);
+            P.seg_cnt = (int32_t*)(ws + 2 * list_bytes);
+            P.redo = ctx->redo_flags;
+            EINX_CUDA(ctx, cudaMemsetAsync(P.redo, 0, (size_t)B * sizeof(int32_t), stream));
+            const size_t smem = smem_for(P.RB, P.LC);
+            // one profiling bracket around the three launches (tiles, tail, conditional redo)
+            const int prof = ctx->profile;
+            einx_prof_begin(ctx, 1, stream);
+            ctx->profile = 0;
+            struct Restore { einx_ctx* c; int p; cudaStream_t s; ~Restore() { c->profile = p; einx_prof_end(c, 1, s); } } restore{ctx, prof, stream};
+            rc = dispatch_radius<true>(ctx, R, P, smem, stream);
+            if (rc) return rc;
+            if (P.NT * Tt > kTailThreads) return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_detect: %d tiles per image", P.NT);
+            for (int i = 0; i < nsides; ++i)   // the dense map (when asked for) is zeros plus the kept survivors
+                if (sides[i].nms_map) EINX_CUDA(ctx, cudaMemsetAsync(sides[i].nms_map, 0, sizeof(float) * (size_t)Bside * Hp * Wp, stream));
+            // (every survivor of an image sits in a register of the tail CTA: items of 32 entries, kTailHeld per warp)
+            if ((size_t)P.scap / 32 + (size_t)P.NT * Tt > (size_t)kTailHeld * kTailWarps)
+                return einx_fail(ctx, EINX_ERR_UNSUPPORTED, "einx_detect: %dx%d map has more survivors than the tiled tail holds", Hp, Wp);
+            const size_t tail_smem = align_up(sizeof(TailShared), 16) + (size_t)(2 * P.NT * Tt + 1 + kTailHeld * kTailWarps) * sizeof(int) + (size_t)kTailHeld * kTailWarps * sizeof(unsigned short);
+            nms_tile_tail_kernel<<<B, kTailThreads, tail_smem, stream>>>(P);
+            EINX_CHECK_LAUNCH(ctx);
+            // the exact path for the images (if any) whose tiles needed more rounds than their apron covers
+            for (int i = 0; i < nsides; ++i) {
+                rc = einx_detect_large(ctx, sides[i].score, sides[i].mask, Bside, Hp, Wp, nms_radius, border, prob_thresh, top_k,
+                                       sides[i].nms_map, sides[i].kpts, kcap, sides[i].counts, stream_, P.redo + (size_t)i * Bside);
+                if (rc) return rc;
+            }
+            return EINX_OK;
+        }
         for (int i = 0; i < nsides; ++i) {
             const int rc = einx_detect_large(ctx, sides[i].score, sides[i].mask, Bside, Hp, Wp, nms_radius, border, prob_thresh,
                                              top_k, sides[i].nms_map, sides[i].kpts, kcap, sides[i].counts, stream_);

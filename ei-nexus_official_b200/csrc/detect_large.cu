@@ -65,6 +65,7 @@ struct DetectParams {
     uint32_t* gRD;
     uint32_t* gPS;
     long long* trace;  // developer aid (EINX_DETECT_TRACE=1): clock64() at phase boundaries of CTA 0
+    const int32_t* only_if;  // optional [B]: images whose flag is 0 are left alone (the tiled kernel already did them)
 };
 
 #define EINX_TRACE(slot)                                                          \
@@ -277,6 +278,7 @@ __global__ void __maxnreg__(48) detect_kernel(const DetectParams P) {
     const int rank = (int)cluster.block_rank();
     const int CS = P.CS;
     const int b = blockIdx.x / CS;
+    if (P.only_if && P.only_if[b] == 0) return;  // (uniform over the cluster: nobody waits for anybody)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int S = P.S, WS = P.WS, HS = 32 * P.S, Hp = P.Hp, Wp = P.Wp;
 
@@ -794,7 +796,7 @@ int dispatch_radius(einx_ctx* ctx, int R, const DetectParams& P, size_t smem, cu
 
 int einx_detect_large(einx_ctx* ctx, float* score, const uint8_t* mask, int B, int Hp, int Wp, int nms_radius,
                            int border, float prob_thresh, int top_k, float* nms_map, float* kpts, int kcap,
-                           int32_t* counts, einx_stream stream_) {
+                           int32_t* counts, einx_stream stream_, const int32_t* only_if) {
     if (!ctx) return EINX_ERR_INVALID;
     if (B < 0 || Hp <= 0 || Wp <= 0 || nms_radius < 0 || border < 0 || kcap < 0)
         return einx_fail(ctx, EINX_ERR_INVALID, "einx_detect: bad argument B=%d Hp=%d Wp=%d r=%d border=%d kcap=%d", B,
@@ -809,6 +811,7 @@ int einx_detect_large(einx_ctx* ctx, float* score, const uint8_t* mask, int B, i
     DetectParams P = {};
     P.score = score; P.mask = mask; P.nms_map = nms_map; P.kpts = kpts; P.counts = counts;
     P.B = B; P.Hp = Hp; P.Wp = Wp; P.border = border; P.kcap = kcap;
+    P.only_if = only_if;
     P.S = (Wp + 31) / 32;
     const int PAD = (R + 3) / 4 * 4;
     P.WS = 32 * P.S + 2 * PAD;

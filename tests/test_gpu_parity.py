@@ -484,3 +484,28 @@ def test_pipeline_vs_oracle(einx, synth, cfg_name, n_events):
         d1 = out["descriptors1"][i, :n1].cpu().numpy()
         adjudicate(out["matches0"][i, :n0].cpu().numpy(), d0, d1)
         assert (out["matches0"][i, n0:] == -1).all()
+
+
+def test_detect_tiled_large_map_redo_path(einx, synth):
+    """Maps that no cluster holds (1280x720) run as row tiles with aprons; a tile whose NMS needs more rounds than its
+    apron covers flags its image and the exact L2-resident kernel redoes that image only.  Image 0 is i.i.d. (6 rounds:
+    tiled result stands), image 1 carries a long monotone ramp (one new maximum per round along it: dozens of rounds)."""
+    rng = np.random.default_rng(77)
+    Hp, Wp, k = 720, 1280, 4096
+    m = synth.score_map(rng, 2, Hp, Wp)
+    ramp = np.linspace(0.2, 0.9, 900, dtype=np.float32)
+    m[1, 0, 300:340, 100:1000] = ramp[None, :] + 1e-3 * rng.random((40, 900), dtype=np.float32)
+    src = cuda(m)
+    nms, kpts, counts = einx.detect(src, 1.0, 4, 4, k, want_map=True)
+    ref_in = m.copy()
+    ref = O.prob_map_to_points_map(ref_in, 1.0, 4, 4, k)
+    assert np.array_equal(src.cpu().numpy(), ref_in)
+    assert np.array_equal(nms.cpu().numpy(), ref)
+    pos = O.prob_map_to_positions_with_prob(ref)
+    for i in range(2):
+        n = int(counts[i])
+        assert n == len(pos[i]) and np.array_equal(kpts[i, :n].cpu().numpy(), pos[i])
+    # both sides in one launch, keypoints only (the pipeline's call)
+    (k0, c0), (k1, c1) = einx.detect_pair(cuda(m[:1]), cuda(m[1:]), 1.0, 4, 4, k)
+    assert int(c0[0]) == len(pos[0]) and np.array_equal(k0[0, :len(pos[0])].cpu().numpy(), pos[0])
+    assert int(c1[0]) == len(pos[1]) and np.array_equal(k1[0, :len(pos[1])].cpu().numpy(), pos[1])
