@@ -649,10 +649,12 @@ def run_einx(args, synth):
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps,
                     "h2d_GBps_achieved": round(h2d_bytes / (ms_e2e / args.steps * 1e-3) / 1e9, 1) if ms_e2e == ms_e2e else None,
+                    "h2d_GBps_aggregate": round(world * h2d_bytes / (ms_e2e / args.steps * 1e-3) / 1e9, 1) if ms_e2e == ms_e2e else None,
                     "note": "all inputs (events AND the fp32 score / descriptor maps of both sides) cross PCIe every step: "
                             "bound by the host->device link, see h2d_GBps_achieved"},
             "e2e_events_only": ({"value": pairs / (ms_e2e_ev * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e_ev / args.steps,
                                  "h2d_bytes_per_step": ev_host_sets[0].nbytes, "d2h_bytes_per_step": d2h_bytes,
+                                 "h2d_GBps_aggregate": round(world * ev_host_sets[0].nbytes / (ms_e2e_ev / args.steps * 1e-3) / 1e9, 1),
                                  "note": "events from pinned host memory, maps device-resident (as produced by on-device conv "
                                          "backbones: the boundary of EIM.forward, core/modules/EIM.py:89-93)"}
                                 if ms_e2e_ev == ms_e2e_ev else None),
