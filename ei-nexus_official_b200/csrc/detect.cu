@@ -149,6 +149,20 @@ __device__ __forceinline__ int block_excl_scan(int v, int* scratch, int& total) 
 // j-th smallest (0-based) of the positive floats in list[0..n) via 4 radix passes on their bit patterns, then the
 // next order statistic; every thread returns the same (a, b).  One histogram per pass (zeroed by the caller long
 // before) and every warp locating the bin for itself: a pass costs one barrier.
+// One histogram increment per lane.  Score values share their leading bytes (probabilities in [0.5, 1) have one
+// exponent), so in the first pass -- and in every pass of a tie-heavy map -- most lanes of a warp hit the same bin: the
+// lanes that agree with the first active lane go out as ONE atomic, the rest individually.  (match.any would aggregate
+// every group, but its cost grows with the number of distinct digits in the warp: ~30 in the later passes.)
+__device__ __forceinline__ void hist_add(unsigned int* hist, bool in, unsigned digit) {
+    const unsigned act = __ballot_sync(0xffffffffu, in);
+    if (act == 0u) return;  // warp-uniform
+    const int leader = __ffs(act) - 1;
+    const unsigned dl = __shfl_sync(0xffffffffu, digit, leader);
+    const unsigned same = __ballot_sync(0xffffffffu, in && digit == dl);
+    if ((int)(threadIdx.x & 31) == leader) atomicAdd(&hist[dl], (unsigned)__popc(same));
+    else if (in && digit != dl) atomicAdd(&hist[digit], 1u);
+}
+
 template <bool GLOBAL>
 __device__ __forceinline__ float list_ld(const float* list, int i) {
     return GLOBAL ? __ldcg(list + i) : list[i];  // global lists are written by other CTAs of the cluster: L2 only
@@ -175,10 +189,7 @@ __device__ void select_two(const float* list, int n, int j, bool need_next, Shar
             for (int u = 0; u < kHeld; ++u) {
                 if (u * kThreads >= n) break;  // uniform
                 const bool in = threadIdx.x + u * kThreads < n && (ev[u] & mask) == prefix;
-                // warp-aggregate equal digits (score values share their exponent byte): one atomic per distinct digit
-                const unsigned digit = (ev[u] >> shift) & 255u;
-                const unsigned peers = __match_any_sync(0xffffffffu, in ? digit : 0x100u);
-                if (in && (int)(__ffs(peers) - 1) == lane) atomicAdd(&hist[digit], (unsigned)__popc(peers));
+                hist_add(hist, in, (ev[u] >> shift) & 255u);
             }
         } else {
             for (int i = threadIdx.x; i < n; i += kThreads) {
@@ -1141,9 +1152,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) nms_tile_tail_kernel(const Nm
                 for (int u = 0; u < kTailHeld; ++u) {
                     if (warp + kTailWarps * u >= nitems) break;  // warp-uniform
                     const bool in = ev[u] != 0u && (ev[u] & mask) == prefix;
-                    const unsigned digit = (ev[u] >> shift) & 255u;
-                    const unsigned peers = __match_any_sync(0xffffffffu, in ? digit : 0x100u);
-                    if (in && (int)(__ffs(peers) - 1) == lane) atomicAdd(&hist[digit], (unsigned)__popc(peers));
+                    hist_add(hist, in, (ev[u] >> shift) & 255u);
                 }
                 __syncthreads();
                 unsigned c[8], mine = 0;
