@@ -506,9 +506,38 @@ voxel_tile_kernel(const float* __restrict__ x, const float* __restrict__ y, cons
 
 }  // namespace
 
+static int voxelize_chunk(einx_ctx* ctx, const float* x, const float* y, const double* t, const float* p,
+                          const int64_t* ev_offsets, int B, int bins, int H, int W, int normalize, float* out,
+                          einx_stream stream_);
+
 extern "C" int einx_voxelize(einx_ctx* ctx, const float* x, const float* y, const double* t, const float* p,
                              const int64_t* ev_offsets, int B, int bins, int H, int W, int normalize,
                              float* out, einx_stream stream_) {
+    if (!ctx) return EINX_ERR_INVALID;
+    // Development knob (EINX_VOXEL_CHUNK_MB): zero / scatter / normalise the batch in chunks of windows whose grids fit
+    // that many MB, so that a chunk's grid stays in L2 between its three kernels.
+    static const int chunk_mb = getenv("EINX_VOXEL_CHUNK_MB") ? atoi(getenv("EINX_VOXEL_CHUNK_MB")) : 0;
+    if (chunk_mb > 0 && B > 1 && bins > 0 && H > 0 && W > 0 && ev_offsets && out) {
+        const size_t per = (size_t)bins * H * W * 4;
+        int cw = (int)(((size_t)chunk_mb << 20) / per);
+        if (cw < 1) cw = 1;
+        if (cw < B) {
+            const int nchunks = (B + cw - 1) / cw;
+            cw = (B + nchunks - 1) / nchunks;  // balanced
+            for (int b0 = 0; b0 < B; b0 += cw) {
+                const int nb = B - b0 < cw ? B - b0 : cw;
+                int rc = voxelize_chunk(ctx, x, y, t, p, ev_offsets + b0, nb, bins, H, W, normalize, out + (size_t)b0 * per / 4, stream_);
+                if (rc) return rc;
+            }
+            return EINX_OK;
+        }
+    }
+    return voxelize_chunk(ctx, x, y, t, p, ev_offsets, B, bins, H, W, normalize, out, stream_);
+}
+
+static int voxelize_chunk(einx_ctx* ctx, const float* x, const float* y, const double* t, const float* p,
+                          const int64_t* ev_offsets, int B, int bins, int H, int W, int normalize, float* out,
+                          einx_stream stream_) {
     if (!ctx) return EINX_ERR_INVALID;
     if (B < 0 || bins <= 0 || H <= 0 || W <= 0)
         return einx_fail(ctx, EINX_ERR_INVALID, "einx_voxelize: bad shape B=%d bins=%d H=%d W=%d", B, bins, H, W);
