@@ -330,7 +330,6 @@ def run_extra_configs(args, synth, einx, dev, world, rank, dist):
         import dataclasses
         ctx = einx.context_for(dev)
         serial = einx.ExtractMatchPipeline(dataclasses.replace(cfg, concurrent=False))
-        serial.pair_detect = True
         serial(ev, sc[0], rw[0], sc[1], rw[1])
         ctx.profile(True)
         serial(ev, sc[0], rw[0], sc[1], rw[1])
@@ -551,7 +550,6 @@ def run_einx(args, synth):
     # Sustained conditions, hence the sustained cuBLAS figure as the tensor peak.
     import dataclasses
     serial = einx.ExtractMatchPipeline(dataclasses.replace(cfg, concurrent=False))
-    serial.pair_detect = True  # one detect launch for both sides, as in the timed step
     ctx.profile(True)
     for rep in range(2 + nprof):
         for j in range(10):

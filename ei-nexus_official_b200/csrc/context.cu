@@ -99,6 +99,16 @@ int einx_create(int device, einx_ctx** out) {
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
     ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    {
+        // per-image flags of the tiled detect kernel: allocated here (not on first use) so that no entry point ever
+        // calls cudaMalloc -- which is illegal while the caller's stream is being captured into a CUDA graph
+        DeviceGuard g(device);
+        if (cudaMalloc(&ctx->redo_flags, 65536 * sizeof(int32_t)) != cudaSuccess) {
+            cudaGetLastError();
+            free(ctx);
+            return einx_fail(nullptr, EINX_ERR_NOMEM, "einx_create: out of device memory");
+        }
+    }
     *out = ctx;
     return EINX_OK;
 }

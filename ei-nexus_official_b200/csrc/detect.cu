@@ -1410,7 +1410,6 @@ int detect_impl(einx_ctx* ctx, const NmsSide* sides, int nsides, int Bside, int 
             const size_t cnt_bytes = align_up(nseg * 4, 256);
             int rc = einx_ws_reserve(ctx, 2 * list_bytes + cnt_bytes, stream);
             if (rc) return rc;
-            if (!ctx->redo_flags) EINX_CUDA(ctx, cudaMalloc(&ctx->redo_flags, 65536 * sizeof(int32_t)));
             unsigned char* ws = (unsigned char*)ctx->ws;
             P.surv_val = (float*)ws;
             P.surv_idx = (int32_t*)(ws + list_bytes);

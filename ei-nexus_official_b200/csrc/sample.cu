@@ -205,7 +205,13 @@ sample_gather_nhwc_kernel(const float* __restrict__ raw, int C, int Hd, int Wd, 
 // C * 2 * Wd floats, so one CTA per (image, coarse row pair) stages them with coalesced loads and
 // serves every keypoint whose upper tap row is that pair's first row: the descriptor map is read
 // about twice from L2/HBM instead of ~8x in sectors, and every tap becomes a conflict-free LDS.
-constexpr int kSlabThreads = 256;
+#ifndef EINX_SLAB_THREADS
+#define EINX_SLAB_THREADS 256
+#endif
+#ifndef EINX_SLAB_MINB
+#define EINX_SLAB_MINB 3
+#endif
+constexpr int kSlabThreads = EINX_SLAB_THREADS;
 constexpr int kSlabWarps = kSlabThreads / 32;
 
 struct Tap {  // one keypoint's bilinear footprint, computed once and shared by the 32 channel lanes
@@ -220,7 +226,7 @@ __device__ __forceinline__ float bilinear_unnormalize(float p, float size_padded
 }
 
 template <int NJ>  // channel groups of 32 held per lane: C == 32 * NJ exactly, or NJ == kMaxPerLane with guards
-__global__ void __launch_bounds__(kSlabThreads, 3)
+__global__ void __launch_bounds__(kSlabThreads, EINX_SLAB_MINB)
 sample_bilinear_slab_kernel(const float* __restrict__ raw, int C, int Hd, int Wd, float Hp, float Wp,
                             const float* __restrict__ kpts, const int32_t* __restrict__ counts, int kcap, float scale,
                             int normalize, float* __restrict__ desc, int SP, SplitOut so) {

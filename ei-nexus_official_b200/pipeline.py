@@ -31,6 +31,7 @@ class PathConfig:
     precision: str = "fp32"    # MNN arithmetic: fp32 | tf32x3 | fp16x3 (both fp32-accurate tensor-core splits) | bf16
     normalize_voxels: bool = True
     concurrent: bool = True    # run voxelisation and the two sides' detect -> sample chains on three streams
+    pair_detect: bool = True   # both sides' maps in one detect launch (einx_detect_pair) when their shapes agree
 
 
 class ExtractMatchPipeline:
@@ -86,7 +87,7 @@ class ExtractMatchPipeline:
             r = describe.sample(raw, k, n, mode, size, c.descriptor_scale, True, split=want_split)
             return r if want_split else (r, None)
 
-        if not c.concurrent and getattr(self, "pair_detect", False) and score0.shape == score1.shape:
+        if not c.concurrent and c.pair_detect and score0.shape == score1.shape:
             grid = self.voxelize(*events)
             (k0, c0), (k1, c1) = _detect.detect_pair(score0, score1, c.detection_threshold, c.nms_radius, c.remove_borders,
                                                     c.top_k, mask0, mask1)
@@ -105,7 +106,7 @@ class ExtractMatchPipeline:
             s_vox.wait_stream(main)
             with torch.cuda.stream(s_vox):
                 grid = self.voxelize(*events)
-            if score0.shape == score1.shape:
+            if c.pair_detect and score0.shape == score1.shape:
                 # both sides' maps in ONE detect launch (an image is owned by one CTA, so 2B images fill the machine
                 # where two launches of B would run back to back); the two sampling kernels then run side by side
                 (k0, c0), (k1, c1) = _detect.detect_pair(score0, score1, c.detection_threshold, c.nms_radius,
