@@ -20,6 +20,17 @@ __device__ __forceinline__ void split_store(const SplitOut& so, size_t idx, floa
     so.hi[idx] = h;
     so.lo[idx] = __float2half_rn(x - __half2float(h));
 }
+// two values of one lane (channels 32 apart): packed conversions, half the conversion instructions of two split_store calls
+__device__ __forceinline__ void split_store2(const SplitOut& so, size_t idx0, size_t idx1, float d0, float d1) {
+    const float x0 = d0 * 1024.0f, x1 = d1 * 1024.0f;
+    const __half2 h = __floats2half2_rn(x0, x1);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x0 - f.x, x1 - f.y);
+    so.hi[idx0] = __low2half(h);
+    so.hi[idx1] = __high2half(h);
+    so.lo[idx0] = __low2half(l);
+    so.lo[idx1] = __high2half(l);
+}
 __device__ __forceinline__ void split_store4(const SplitOut& so, size_t idx, float4 d) {  // idx % 4 == 0
     const float x0 = d.x * 1024.0f, x1 = d.y * 1024.0f, x2 = d.z * 1024.0f, x3 = d.w * 1024.0f;
     const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
@@ -225,6 +236,33 @@ __device__ __forceinline__ float bilinear_unnormalize(float p, float size_padded
     return __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.0f), (float)size_in), 1.0f), 2.0f);
 }
 
+// one keypoint's descriptor row from a lane's NJ values (channels lane + 32 j): fp32 row and, when asked for, the fp16
+// operand pair -- two channel groups per packed conversion
+template <int NJ>
+__device__ __forceinline__ void store_row(float* __restrict__ out, const SplitOut& so, size_t row, const float (&v)[NJ], float mul,
+                                          int lane, int C) {
+    if (NJ != kMaxPerLane && NJ % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < NJ; j += 2) {
+            const int c0 = lane + 32 * j, c1 = c0 + 32;
+            const float d0 = v[j] * mul, d1 = v[j + 1] * mul;
+            out[c0] = d0;
+            out[c1] = d1;
+            if (so.hi) split_store2(so, row + c0, row + c1, d0, d1);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int c = lane + 32 * j;
+            if (NJ != kMaxPerLane || c < C) {
+                const float d = v[j] * mul;
+                out[c] = d;
+                if (so.hi) split_store(so, row + c, d);
+            }
+        }
+    }
+}
+
 template <int NJ>  // channel groups of 32 held per lane: C == 32 * NJ exactly, or NJ == kMaxPerLane with guards
 __global__ void __launch_bounds__(kSlabThreads, EINX_SLAB_MINB)
 sample_bilinear_slab_kernel(const float* __restrict__ raw, int C, int Hd, int Wd, float Hp, float Wp,
@@ -374,27 +412,11 @@ sample_bilinear_slab_kernel(const float* __restrict__ raw, int C, int Hd, int Wd
             }
             if (live0) {
                 float* out = desc + ((size_t)b * kcap + t0.k) * C;
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) {
-                    const int c = lane + 32 * j;
-                    if (NJ != kMaxPerLane || c < C) {
-                        const float d = v0[j] * mul0;
-                        out[c] = d;
-                        if (so.hi) split_store(so, ((size_t)b * kcap + t0.k) * C + c, d);
-                    }
-                }
+                store_row<NJ>(out, so, ((size_t)b * kcap + t0.k) * C, v0, mul0, lane, C);
             }
             if (live1) {
                 float* out = desc + ((size_t)b * kcap + t1.k) * C;
-#pragma unroll
-                for (int j = 0; j < NJ; ++j) {
-                    const int c = lane + 32 * j;
-                    if (NJ != kMaxPerLane || c < C) {
-                        const float d = v1[j] * mul1;
-                        out[c] = d;
-                        if (so.hi) split_store(so, ((size_t)b * kcap + t1.k) * C + c, d);
-                    }
-                }
+                store_row<NJ>(out, so, ((size_t)b * kcap + t1.k) * C, v1, mul1, lane, C);
             }
         }
     }
