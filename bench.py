@@ -499,12 +499,17 @@ def run_einx(args, synth):
             break
     log(f"[rank {rank}] e2e warm-up: {n_warm} steps, {time.perf_counter() - t_warm:.1f}s, last blocks "
         f"{[round(1e3 * b / 8, 2) for b in blocks[-3:]]} ms/step")
-    ms_e2e = timed(step_e2e, args.steps, 0)[0] if step_e2e else float("nan")
-    ms_e2e_ev = float("nan")
+    # The e2e arms issue eagerly (0.8 ms of host time per step against 3 ms of PCIe time), so a burst of host-side
+    # noise on a shared box can make one timed run host bound: each arm is timed three times, K steps each; the median
+    # run is reported and all three are listed.
+    ms_e2e, ms_e2e_ev, e2e_trials, e2e_ev_trials = float("nan"), float("nan"), [], []
     if step_e2e:
+        e2e_trials = [timed(step_e2e, args.steps, 0)[0] for _ in range(3)]
+        ms_e2e = sorted(e2e_trials)[1]
         for i in range(max(3, args.warmup)):
             step_e2e_events(i)
-        ms_e2e_ev = timed(step_e2e_events, args.steps, 0)[0]
+        e2e_ev_trials = [timed(step_e2e_events, args.steps, 0)[0] for _ in range(3)]
+        ms_e2e_ev = sorted(e2e_ev_trials)[1]
     if not args.no_graph:
         # one captured step per resident batch: a step is then a single CUDA-graph launch
         captured.extend(pipe.capture(ev, s0, r0, s1, r1) for ev, (s0, r0, s1, r1) in dev_sets)
@@ -646,11 +651,13 @@ def run_einx(args, synth):
             "data": "synthetic", "config": workload_config(args, synth),
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps,
+                    "trials_ms_per_step": [round(t / args.steps, 4) for t in e2e_trials], "reported": "median of 3 runs of K steps",
                     "h2d_GBps_achieved": round(h2d_bytes / (ms_e2e / args.steps * 1e-3) / 1e9, 1) if ms_e2e == ms_e2e else None,
                     "h2d_GBps_aggregate": round(world * h2d_bytes / (ms_e2e / args.steps * 1e-3) / 1e9, 1) if ms_e2e == ms_e2e else None,
                     "note": "all inputs (events AND the fp32 score / descriptor maps of both sides) cross PCIe every step: "
                             "bound by the host->device link, see h2d_GBps_achieved"},
             "e2e_events_only": ({"value": pairs / (ms_e2e_ev * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e_ev / args.steps,
+                                 "trials_ms_per_step": [round(t / args.steps, 4) for t in e2e_ev_trials],
                                  "h2d_bytes_per_step": ev_host_sets[0].nbytes, "d2h_bytes_per_step": d2h_bytes,
                                  "h2d_GBps_aggregate": round(world * ev_host_sets[0].nbytes / (ms_e2e_ev / args.steps * 1e-3) / 1e9, 1),
                                  "note": "events from pinned host memory, maps device-resident (as produced by on-device conv "
