@@ -3,8 +3,8 @@
 // :138-164, :243-337, :451-484 (see include/einx.h); bit-exact for non-negative, NaN-free maps.
 //
 // One image per CTA (or per thread-block CLUSTER of row bands when the map does not fit one CTA's
-// shared memory); the map is read from HBM once, lives in shared memory through all rounds, and the
-// keypoints are written once.
+// shared memory; or, beyond one cluster, per row TILE of the map, each tile a cluster of its own -- see NmsParams);
+// the map is read from HBM once, lives in shared memory through all rounds, and the keypoints are written once.
 //
 // The fixpoint of detector_util.py:286-335 is greedy NMS in (value desc,
 // raster asc) order, so the rounds only have to respect two facts: a pixel that is the first-occurrence
@@ -15,10 +15,11 @@
 //   dense round   one sweep per thread over 4 columns x a run of rows: the horizontal window maxima of a
 //                 row come from three float4 loads, the vertical ones from a register ring of 3-row
 //                 partial maxima (9 = 3 x 3 rows), ~9 instructions per pixel, no second plane in shared
-//                 memory.  A pixel equal to its window maximum (rare) takes the slow path: exact
-//                 first-occurrence test, LM bit, entry in the list of new maxima.  Then every new maximum
-//                 zeroes its window in V and clears it in UB (a scatter over list x window rows); the
-//                 count of undecided pixels is kept exact from the bits those atomics actually cleared.
+//                 memory.  A positive pixel equal to its window maximum is a candidate (a bit per pixel, 8 rows x
+//                 4 columns per register); pass 2 settles the first-occurrence rule for the candidates only (no
+//                 equal value earlier in raster order inside the window), sets the LM bit of the new maxima; these
+//                 are dilated on 32-bit words, and the undecided pixels under the dilation are cleared in UB and
+//                 zeroed in V; the count of undecided pixels is kept exact.
 //   sparse round  once the undecided pixels fit the worklist: per undecided pixel, look only at the
 //                 undecided neighbours (UB bits of the 2R+1 window rows; selected pixels can not be in
 //                 the window of an undecided one), then clear the windows of the new maxima in UB.  V is
