@@ -175,7 +175,7 @@ def workload_config(args, synth):
         "mnn_precision": args.precision,
         "streams": "1 (serial)" if args.serial else "3 (voxelise | side 0 | side 1, joined before MNN)",
         "e2e_chunks": args.e2e_chunks,
-        "launch": "eager" if args.no_graph else "CUDA graph replay, one captured step per resident batch (e2e arm: eager)",
+        "launch": "eager" if args.no_graph else "CUDA graph replay, one captured step per resident batch (e2e arms: one captured graph per sub-batch)",
         "l2_policy": f"{NUM_INPUT_SETS} distinct resident input batches rotated between steps (inputs larger than L2)",
     }
 
@@ -499,9 +499,8 @@ def run_einx(args, synth):
             break
     log(f"[rank {rank}] e2e warm-up: {n_warm} steps, {time.perf_counter() - t_warm:.1f}s, last blocks "
         f"{[round(1e3 * b / 8, 2) for b in blocks[-3:]]} ms/step")
-    # The e2e arms issue eagerly (0.8 ms of host time per step against 3 ms of PCIe time), so a burst of host-side
-    # noise on a shared box can make one timed run host bound: each arm is timed three times, K steps each; the median
-    # run is reported and all three are listed.
+    # Each e2e arm is timed three times, K steps each; the median run is reported and all three are listed (the arms are
+    # bound by the PCIe link of a shared, virtualised host: one run can land on a noisy moment).
     ms_e2e, ms_e2e_ev, e2e_trials, e2e_ev_trials = float("nan"), float("nan"), [], []
     if step_e2e:
         e2e_trials = [timed(step_e2e, args.steps, 0)[0] for _ in range(3)]

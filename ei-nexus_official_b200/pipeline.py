@@ -268,10 +268,18 @@ class HostStreamer:
     compute stream.  Everything is asynchronous: the caller synchronises (or records an event) when it
     needs the results."""
 
-    def __init__(self, pipe: ExtractMatchPipeline, device):
+    def __init__(self, pipe: ExtractMatchPipeline, device, graphs: bool = True):
+        """``graphs``: freeze the device work of a sub-batch (event unpack, the pipeline's launches on its three
+        streams, the result copies to the caller's pinned tensors) into a CUDA graph the first time a (staging set,
+        sub-batch layout, output buffers) combination is seen and replay it afterwards -- one launch per sub-batch
+        instead of ~25 eager calls, which keeps the PCIe-bound path from becoming host bound on a busy host.  A
+        sub-batch whose layout differs (ragged event counts) is captured under its own key."""
         self.pipe = pipe
         self.dev = torch.device(device)
         self.copy_stream = torch.cuda.Stream(self.dev)
+        self.use_graphs = bool(graphs)
+        self._cap_stream = torch.cuda.Stream(self.dev) if self.use_graphs else None
+        self._graphs = {}
         self._stage = {}
         self._unpacked = {}
         self._free = [None, None]  # event: the kernels that read staging set k have finished
@@ -280,7 +288,27 @@ class HostStreamer:
         st = self._stage.get(k)
         if st is None or st.numel() < nbytes:
             st = self._stage[k] = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
+            self._graphs = {key: g for key, g in self._graphs.items() if key[0] != k}  # captured addresses are gone
         return st
+
+    def _body(self, hb, k, a, b, dbuf, layout, out_host, resident_maps):
+        """Device work of one sub-batch on the current stream: unpack, pipeline, result copies."""
+        if resident_maps is None:
+            x, y, t, p, off, s0, r0, s1, r1 = HostBatch.views(dbuf, layout)
+        else:
+            x, y, t, p, off = HostBatch.views(dbuf, layout)
+            s0, r0, s1, r1 = (m[a:b] for m in resident_maps)
+        if hb.compact:  # expand the 13-byte wire format to the fp32 SoA the voxeliser reads
+            n = x.numel()
+            f = self._unpacked[k]
+            ctx = _lib.context_for(self.dev)
+            ctx.check(ctx.lib.einx_unpack_events(ctx.handle, _lib.ptr(x), _lib.ptr(y), _lib.ptr(p), n, _lib.ptr(f[0]),
+                                                 _lib.ptr(f[1]), _lib.ptr(f[2]), ctx.stream), "einx_unpack_events")
+            x, y, p = f[0, :n], f[1, :n], f[2, :n]
+        out = self.pipe((x, y, t, p, off), s0, r0, s1, r1)
+        for key in RESULT_KEYS:
+            if key in out_host:
+                out_host[key][a:b].copy_(out[key], non_blocking=True)
 
     @torch.no_grad()
     def run(self, hb: HostBatch, out_host: Dict[str, torch.Tensor], resident_maps=None) -> None:
@@ -293,6 +321,12 @@ class HostStreamer:
         for i, (a, b, hbuf, layout, _) in enumerate(hb.chunks):
             k = i & 1
             dbuf = self._staging(k, hbuf.numel())[:hbuf.numel()]
+            if hb.compact:
+                n = layout[0][2][0]  # events of the sub-batch
+                f = self._unpacked.get(k)
+                if f is None or f.shape[1] < n:
+                    self._unpacked[k] = torch.empty((3, n), dtype=torch.float32, device=self.dev)
+                    self._graphs = {key: g for key, g in self._graphs.items() if key[0] != k}
             with torch.cuda.stream(self.copy_stream):
                 if self._free[k] is not None:
                     self.copy_stream.wait_event(self._free[k])
@@ -300,23 +334,28 @@ class HostStreamer:
                 ready = torch.cuda.Event()
                 ready.record(self.copy_stream)
             main.wait_event(ready)
-            if resident_maps is None:
-                x, y, t, p, off, s0, r0, s1, r1 = HostBatch.views(dbuf, layout)
+            args = (hb, k, a, b, dbuf, layout, out_host, resident_maps)
+            if not self.use_graphs:
+                self._body(*args)
             else:
-                x, y, t, p, off = HostBatch.views(dbuf, layout)
-                s0, r0, s1, r1 = (m[a:b] for m in resident_maps)
-            if hb.compact:  # expand the 13-byte wire format to the fp32 SoA the voxeliser reads
-                n = x.numel()
-                f = self._unpacked.get(k)
-                if f is None or f.shape[1] < n:
-                    f = self._unpacked[k] = torch.empty((3, n), dtype=torch.float32, device=self.dev)
-                ctx = _lib.context_for(self.dev)
-                ctx.check(ctx.lib.einx_unpack_events(ctx.handle, _lib.ptr(x), _lib.ptr(y), _lib.ptr(p), n, _lib.ptr(f[0]),
-                                                     _lib.ptr(f[1]), _lib.ptr(f[2]), ctx.stream), "einx_unpack_events")
-                x, y, p = f[0, :n], f[1, :n], f[2, :n]
-            out = self.pipe((x, y, t, p, off), s0, r0, s1, r1)
-            for key in RESULT_KEYS:
-                if key in out_host:
-                    out_host[key][a:b].copy_(out[key], non_blocking=True)
+                key = (k, a, b, hbuf.numel(), hb.compact, tuple(layout),
+                       tuple((name, t.data_ptr()) for name, t in sorted(out_host.items())),
+                       None if resident_maps is None else tuple(m.data_ptr() for m in resident_maps))
+                graph = self._graphs.get(key)
+                if graph is None:
+                    # warm-up on the capture stream (every per-stream context gets its workspace: nothing may allocate
+                    # during capture), then capture; the warm-up already produced this sub-batch's results
+                    cap = self._cap_stream
+                    cap.wait_stream(main)
+                    with torch.cuda.stream(cap):
+                        self._body(*args)
+                    cap.synchronize()
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, stream=cap, capture_error_mode="thread_local"):
+                        self._body(*args)
+                    main.wait_stream(cap)
+                    self._graphs[key] = graph
+                else:
+                    graph.replay()
             self._free[k] = torch.cuda.Event()
             self._free[k].record(main)
