@@ -509,3 +509,22 @@ def test_detect_tiled_large_map_redo_path(einx, synth):
     (k0, c0), (k1, c1) = einx.detect_pair(cuda(m[:1]), cuda(m[1:]), 1.0, 4, 4, k)
     assert int(c0[0]) == len(pos[0]) and np.array_equal(k0[0, :len(pos[0])].cpu().numpy(), pos[0])
     assert int(c1[0]) == len(pos[1]) and np.array_equal(k1[0, :len(pos[1])].cpu().numpy(), pos[1])
+
+
+def test_detect_tiled_large_map_with_mask(einx, synth):
+    """The event mask (score[~mask] = 0, applied while loading) in the tiled form: every tile reads its own rows of
+    the mask, only the band that owns a row writes the zeros back to `score`."""
+    rng = np.random.default_rng(78)
+    Hp, Wp, k = 720, 1280, 3000
+    m = synth.score_map(rng, 1, Hp, Wp)
+    mask = (rng.random((1, Hp, Wp)) < 0.7)
+    mask[0, 200:260, :] = False  # a dead stripe across two tiles
+    src = cuda(m)
+    nms, kpts, counts = einx.detect(src, 1.0, 4, 4, k, mask=cuda(mask), want_map=True)
+    ref_in = m * mask[:, None].astype(np.float32)
+    ref = O.prob_map_to_points_map(ref_in, 1.0, 4, 4, k)   # (zeroes the border of ref_in in place)
+    assert np.array_equal(src.cpu().numpy(), ref_in)
+    assert np.array_equal(nms.cpu().numpy(), ref)
+    pos = O.prob_map_to_positions_with_prob(ref)[0]
+    n = int(counts[0])
+    assert n == len(pos) and np.array_equal(kpts[0, :n].cpu().numpy(), pos)
