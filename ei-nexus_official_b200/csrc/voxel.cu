@@ -55,6 +55,21 @@ __device__ __forceinline__ void splat_event(float* __restrict__ g, float xf, flo
     if (tn != tn) return;  // 0/0 time span: the reference's NaN bin index is out of range
     const float pol = pf < 1.0f ? -1.0f : pf;  // value[value < 1] = -1   (:88-89)
     const int x0 = (int)xf, y0 = (int)yf, t0 = (int)tn;  // .int() truncates (:83-85)
+    if ((float)x0 == xf && (float)y0 == yf) {
+        // Integer-pixel event (the EC dataset, raw sensor streams): the x+1 and y+1 corners carry weight pol * 0 and can
+        // change neither a cell nor the `!= 0` mask, and the remaining weight pol * 1 * 1 * wt is exactly pol * wt --
+        // two scalar reductions, same bits as the general path below.
+        if ((unsigned)x0 >= (unsigned)W || (unsigned)y0 >= (unsigned)H) return;
+        float* cell = g + ((size_t)t0 * H + y0) * W + x0;
+#pragma unroll
+        for (int dt = 0; dt < 2; ++dt) {
+            const int tl = t0 + dt;
+            if (tl < 0 || tl >= bins) continue;
+            const float w = __fmul_rn(pol, __fsub_rn(1.0f, fabsf(__fsub_rn((float)tl, tn))));
+            if (w != 0.0f) red_add(cell + (size_t)dt * H * W, w);
+        }
+        return;
+    }
     const float wx0 = __fmul_rn(pol, __fsub_rn(1.0f, fabsf(__fsub_rn((float)x0, xf))));
     const float wx1 = __fmul_rn(pol, __fsub_rn(1.0f, fabsf(__fsub_rn((float)(x0 + 1), xf))));
     const bool vx0 = (x0 >= 0) & (x0 < W);
